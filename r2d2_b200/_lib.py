@@ -1,0 +1,80 @@
+"""ctypes binding of libr2d2_b200.so -- the C-ABI boundary (include/r2d2_b200.h).
+
+There is NO fallback: if the shared object is missing or the device is not a
+Blackwell (sm_100) part, importing a product module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libr2d2_b200.so")
+
+_lib = None
+
+
+class R2D2Error(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise R2D2Error(
+                f"{LIB_PATH} is missing: build it with `python -m r2d2_b200.build` "
+                "(or __graft_entry__.build()); there is no CPU/PyTorch fallback")
+        _lib = C.CDLL(LIB_PATH)
+        _declare(_lib)
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise R2D2Error(f"r2d2_b200 error {rc}: {lib().r2d2_last_error().decode()}")
+
+
+def require_device() -> None:
+    check(lib().r2d2_device_ok())
+
+
+p = C.c_void_p
+i64, i32, u64, f64, f32 = C.c_int64, C.c_int32, C.c_uint64, C.c_double, C.c_float
+
+# name -> (restype, argtypes); kept in one table so tests can verify that every
+# symbol declared in include/r2d2_b200.h is exported.
+SIGNATURES = {
+    "r2d2_last_error": (C.c_char_p, []),
+    "r2d2_abi_version": (C.c_int, []),
+    "r2d2_device_ok": (C.c_int, []),
+    "r2d2_tree_create": (C.c_int, [i64, f64, f64, C.POINTER(p)]),
+    "r2d2_tree_destroy": (C.c_int, [p]),
+    "r2d2_tree_num_layers": (C.c_int, [p]),
+    "r2d2_tree_num_nodes": (i64, [p]),
+    "r2d2_tree_nodes": (p, [p]),
+    "r2d2_tree_update": (C.c_int, [p, p, p, i64, i64, i64, i64, p]),
+    "r2d2_tree_set_leaves": (C.c_int, [p, p, p, i64, p]),
+    "r2d2_tree_sample": (C.c_int, [p, i64, p, u64, p, p, p, p]),
+    "r2d2_td_loss": (C.c_int, [p] * 8 + [C.c_int, C.c_int] + [p] * 6),
+}
+
+
+def _declare(l: C.CDLL) -> None:
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(l, name)
+        fn.restype = res
+        fn.argtypes = args
+
+
+def ptr(t) -> int:
+    """data_ptr of a (contiguous, CUDA) torch tensor or None."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), "r2d2_b200 kernels take contiguous tensors"
+    return t.data_ptr()
+
+
+def stream_ptr() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,61 @@
+"""K2 fused TD kernel vs the oracle and the reference's golden Q/TD vectors."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.learner import td_and_loss, mixed_priorities
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_gpu(q, qn_on, qn_tg, action, R, G, isw, learn):
+    from r2d2_b200 import ops
+    c = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    td, prio, loss_sum, rows, dq = ops.td_loss(c(q), c(qn_on), c(qn_tg), c(action), c(R), c(G), c(isw), c(learn))
+    torch.cuda.synchronize()
+    return (td.cpu().numpy(), prio.cpu().numpy(), float(loss_sum.item()), int(rows.item()), dq.cpu().numpy())
+
+
+@pytest.mark.parametrize("name", ["learner_ragged.npz", "learner_cfg0.npz"])
+def test_td_on_reference_q_values(golden_dir, name):
+    """Feed the reference's own Q tensors: TD/priorities/loss must match its outputs."""
+    g = np.load(os.path.join(golden_dir, name))
+    K = int(g["meta"][1])
+    for k in range(K):
+        td, prio, loss_sum, rows, dq = _run_gpu(g[f"k{k}_out_q"], g[f"k{k}_out_qn_online"], g[f"k{k}_out_qn_target"],
+                                                g[f"k{k}_action"].reshape(-1), g[f"k{k}_n_step_reward"],
+                                                g[f"k{k}_gamma"], g[f"k{k}_is_weights"], g[f"k{k}_learning"])
+        assert rows == g[f"k{k}_out_td"].shape[0]
+        # same inputs, same float32 op sequence -> agreement to ~1 ulp of O(1) values
+        np.testing.assert_allclose(td, g[f"k{k}_out_td"], atol=1e-6, rtol=0)
+        np.testing.assert_allclose(prio, g[f"k{k}_out_priorities"], atol=1e-6, rtol=0)
+        assert abs(loss_sum / rows - float(g[f"k{k}_out_loss"])) < 1e-6 * max(1, abs(float(g[f"k{k}_out_loss"])))
+
+
+@pytest.mark.parametrize("B,A,lmax", [(64, 9, 40), (512, 18, 40), (7, 4, 255), (1, 1, 1)])
+def test_td_random_vs_oracle(B, A, lmax):
+    rng = np.random.default_rng(B * 1000 + A)
+    learn = rng.integers(1, lmax + 1, B).astype(np.uint8)
+    if B > 2:
+        learn[1] = lmax
+    rows = int(learn.astype(int).sum())
+    q = rng.normal(0, 2, (rows, A)).astype(np.float32)
+    qn_on = rng.normal(0, 2, (rows, A)).astype(np.float32)
+    qn_on[::7] = qn_on[::7].round()          # ties: first maximum must win
+    qn_tg = rng.normal(0, 5, (rows, A)).astype(np.float32)
+    action = rng.integers(0, A, rows).astype(np.uint8)
+    R = rng.uniform(-1, 4, rows).astype(np.float32)
+    G = np.where(rng.random(rows) < 0.1, 0.0, 0.997 ** 5).astype(np.float32)
+    isw = rng.uniform(0.1, 1, rows).astype(np.float32)
+    td, prio, loss_sum, nrows, dq = _run_gpu(q, qn_on, qn_tg, action, R, G, isw, learn)
+    t = torch.from_numpy
+    qt = t(q).requires_grad_(True)
+    loss, td_o, target, q_a = td_and_loss(qt, t(qn_on), t(qn_tg), t(action), t(R), t(G), t(isw))
+    (loss * rows).backward()
+    assert nrows == rows
+    np.testing.assert_allclose(td, td_o.numpy(), atol=2e-6, rtol=1e-6)
+    np.testing.assert_allclose(prio, mixed_priorities(td_o.numpy(), learn), atol=2e-6, rtol=1e-6)
+    assert abs(loss_sum - float(loss) * rows) <= 1e-5 * max(1.0, abs(float(loss) * rows))
+    np.testing.assert_allclose(dq, qt.grad.numpy(), atol=1e-5, rtol=1e-5)
