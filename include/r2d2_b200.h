@@ -90,6 +90,54 @@ int r2d2_td_loss(const float* q, const float* qn_online, const float* qn_target,
                  const uint8_t* learning_steps, int B, int A, float* td_out, float* prio_out,
                  float* loss_sum_out, int32_t* rows_out, float* dq_out, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * K1 / K1b  sequence-unroll network  <->  model.Network (model.py:27-150) as used by the learner
+ * (worker.py:346,347,352) and loss.backward() (worker.py:363).
+ * Parameters live in ONE caller-owned flat float32 buffer holding the reference's 20 state_dict
+ * tensors (model.py:39-63) in state_dict order, each in its PyTorch layout, each start 16-byte
+ * aligned; r2d2_net_param_layout returns the 21 offsets (in floats; [20] = total length).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct r2d2_net r2d2_net;
+
+int r2d2_net_param_layout(int action_dim, int in_channels, int64_t* offsets_out /* [21] */);
+/* Workspace for a fixed batch shape: B sequences of T frames (C,84,84), at most Lmax learning
+ * steps per sequence, max_forward = config.forward_steps (model.py:37). */
+int r2d2_net_create(int B, int T, int C, int action_dim, int Lmax, int max_forward, r2d2_net** out);
+int r2d2_net_destroy(r2d2_net* n);
+/* Row capacity of the Q outputs ([rows_capacity][A], >= B*Lmax). */
+int r2d2_net_rows_capacity(const r2d2_net* n);
+int r2d2_net_ku(const r2d2_net* n);
+/* Re-lay out `params` for slot `which` (0 = online, 1 = target).  Call after every change of that
+ * slot's parameters (optimizer step, target sync; worker.py:365,376-377). */
+int r2d2_net_pack(r2d2_net* n, int which, const float* params, void* stream);
+/* Network.calculate_q_ / calculate_q (model.py:81-150) in one unroll of b+l+f steps.
+ *   obs u8 [B][T][C][84][84] (raw frames; the /255 of worker.py:342 is folded in);
+ *   last_action u8/bool [B][T][A]; last_reward f32 [B][T]; hidden f32 [B][2][512] (Block.hidden
+ *   rows, worker.py:198: [b][0] = h0, [b][1] = c0); burn/learn/fwd u8 [B] (worker.py:229-231).
+ *   q_learn_out [rows_capacity][A]: Q(h_{b+t}) rows (calculate_q), may be NULL.
+ *   q_shift_out [rows_capacity][A]: Q(h_{min(b+F+t, b+l+f-1)}) rows (calculate_q_), may be NULL.
+ *   Rows are sequence-major; the first sum(learn) are valid.  For slot 0 the activations are kept
+ *   for r2d2_net_backward; obs/hidden must stay alive until then. */
+int r2d2_net_forward(r2d2_net* n, int which, const float* params, const uint8_t* obs, const uint8_t* last_action,
+                     const float* last_reward, const float* hidden, const uint8_t* burn, const uint8_t* learn,
+                     const uint8_t* fwd, float* q_learn_out, float* q_shift_out, void* stream);
+/* loss.backward() (worker.py:363) for the online slot: BPTT through all b+l steps (burn-in
+ * included) and the encoder.  dq [rows_capacity][A]; grads: flat buffer in the parameter layout,
+ * fully overwritten (alignment gaps are left untouched and must be zero). */
+int r2d2_net_backward(r2d2_net* n, const float* params, const float* dq, float* grads, void* stream);
+/* Test/debug access to device intermediates (see net.cu for the names). */
+void* r2d2_net_debug_ptr(r2d2_net* n, int which, const char* name);
+
+/* ------------------------------------------------------------------------------------------
+ * K5  clip_grad_norm_(max_norm) + Adam(lr, eps).step()  (worker.py:289,364-365) on the flat
+ * buffers.  grad_scale: optional device float multiplied into the gradients first;
+ * partial_ws: device double[592] scratch; step: 1-based update count; norm_out: optional device
+ * float receiving the pre-clip global norm.
+ * ---------------------------------------------------------------------------------------- */
+int r2d2_clip_adam(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                   const float* grad_scale, double* partial_ws, float max_norm, float lr, float beta1, float beta2,
+                   float eps, int64_t step, float* norm_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

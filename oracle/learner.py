@@ -175,6 +175,22 @@ def inverse_value_rescale(x: torch.Tensor, eps: float = 1e-3) -> torch.Tensor:
     return x.sign() * (t.square() - 1)
 
 
+def td_target_ieee(q_tgt: np.ndarray, R: np.ndarray, G: np.ndarray) -> np.ndarray:
+    """h(R + G*h^-1(q)) with the reference's float32 operation sequence, every op IEEE
+    round-to-nearest (NumPy).  torch's CPU ``sqrt`` is not correctly rounded for ~1.3 % of
+    inputs and h^-1 amplifies that single ulp to ~1e-4 when |q| >= 10, so this -- not the torch
+    evaluation -- is the tight check for the CUDA kernel (which uses IEEE sqrt, as torch's own
+    CUDA path does)."""
+    f = np.float32
+    x = q_tgt.astype(np.float32)
+    a = (np.abs(x) + f(1)) + f(1e-3)
+    s = a * f(4 * 1e-3) + f(1)
+    t = (np.sqrt(s) - f(1)) / f(2 * 1e-3)
+    inv = np.sign(x) * (t * t - f(1))
+    y = R.astype(np.float32) + G.astype(np.float32) * inv
+    return np.sign(y) * (np.sqrt(np.abs(y) + f(1)) - f(1)) + f(1e-3) * y
+
+
 def mixed_priorities(td: np.ndarray, learning_steps: np.ndarray) -> np.ndarray:
     """``calculate_mixed_td_errors`` (worker.py:268-276) with the NumPy-1.x
     accumulator semantics the reference was written for (int64 running offset)."""

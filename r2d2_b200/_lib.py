@@ -57,6 +57,16 @@ SIGNATURES = {
     "r2d2_tree_set_leaves": (C.c_int, [p, p, p, i64, p]),
     "r2d2_tree_sample": (C.c_int, [p, i64, p, u64, p, p, p, p]),
     "r2d2_td_loss": (C.c_int, [p] * 8 + [C.c_int, C.c_int] + [p] * 6),
+    "r2d2_net_param_layout": (C.c_int, [C.c_int, C.c_int, C.POINTER(i64)]),
+    "r2d2_net_create": (C.c_int, [C.c_int] * 6 + [C.POINTER(p)]),
+    "r2d2_net_destroy": (C.c_int, [p]),
+    "r2d2_net_rows_capacity": (C.c_int, [p]),
+    "r2d2_net_ku": (C.c_int, [p]),
+    "r2d2_net_pack": (C.c_int, [p, C.c_int, p, p]),
+    "r2d2_net_forward": (C.c_int, [p, C.c_int] + [p] * 11),
+    "r2d2_net_backward": (C.c_int, [p, p, p, p, p]),
+    "r2d2_net_debug_ptr": (p, [p, C.c_int, C.c_char_p]),
+    "r2d2_clip_adam": (C.c_int, [p, p, p, p, i64, p, p, f32, f32, f32, f32, f32, i64, p, p]),
 }
 
 

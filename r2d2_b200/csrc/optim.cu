@@ -1,0 +1,96 @@
+// K5: global-norm gradient clipping + Adam, fused over the flat parameter buffer.
+//
+// Replaces  nn.utils.clip_grad_norm_(params, 40); Adam(lr=1e-4, eps=1e-3).step()
+// (worker.py:289,364-365) with two launches over the 4.33 M-element flat buffers:
+//   1. per-CTA partial sums of g^2 (deterministic order),
+//   2. every CTA re-reduces the partials (592 floats, L2 resident), derives the clip coefficient
+//      and applies torch's single-tensor Adam update (lerp form of the first moment).
+// Bound: HBM, 4 reads + 3 writes of 4 B per parameter = 28 B/param -> 121 MB per step.
+#include "common.cuh"
+
+namespace r2d2 {
+
+constexpr int kNormBlocks = 148 * 4;
+constexpr int kNormThreads = 256;
+
+__global__ void __launch_bounds__(kNormThreads) sumsq_partial_kernel(const float* __restrict__ g, int64_t n,
+                                                                   double* __restrict__ partial) {
+    __shared__ double s[kNormThreads / 32];
+    double acc = 0.0;
+    const int64_t n4 = n >> 2;
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = g4[i];
+        acc += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+    }
+    for (int64_t i = (n4 << 2) + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        acc += (double)g[i] * g[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < kNormThreads / 32; ++w) t += s[w];
+        partial[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                        float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                                        const double* __restrict__ partial, const float* __restrict__ grad_scale,
+                                                        float max_norm, float lr, float beta1, float beta2, float eps,
+                                                        float bc1, float bc2_sqrt, float* __restrict__ norm_out) {
+    __shared__ double s_tot;
+    if (threadIdx.x < 32) {
+        double t = 0.0;
+        for (int i = threadIdx.x; i < kNormBlocks; i += 32) t += partial[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (threadIdx.x == 0) s_tot = t;
+    }
+    __syncthreads();
+    const float scale = grad_scale ? *grad_scale : 1.f;
+    const float total_norm = (float)sqrt(s_tot) * fabsf(scale);
+    // torch.nn.utils.clip_grad_norm_: coef = max_norm / (norm + 1e-6), clamped to 1
+    const float coef = fminf(max_norm / (total_norm + 1e-6f), 1.f) * scale;
+    if (norm_out && blockIdx.x == 0 && threadIdx.x == 0) *norm_out = total_norm;
+    const float step_size = lr / bc1;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float gi = g[i] * coef;
+        float mi = m[i], vi = v[i];
+        mi = mi + (gi - mi) * (1.f - beta1);                 // exp_avg.lerp_(grad, 1-beta1)
+        vi = vi * beta2 + (1.f - beta2) * gi * gi;           // exp_avg_sq.mul_(b2).addcmul_(g, g, 1-b2)
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] = p[i] - step_size * (mi / denom);
+        m[i] = mi;
+        v[i] = vi;
+    }
+}
+
+}  // namespace r2d2
+
+using namespace r2d2;
+
+extern "C" {
+
+/* clip_grad_norm_(max_norm) + Adam step on flat buffers (worker.py:364-365).
+ *   grad_scale (device float*, may be NULL): gradients are multiplied by it first (1/rows of the
+ *   mean loss, possibly after a cross-rank reduction).  partial_ws: device double[592] scratch.
+ *   step: 1-based update count (bias correction).  norm_out (device float*, may be NULL): the
+ *   pre-clip global gradient norm. */
+int r2d2_clip_adam(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                   const float* grad_scale, double* partial_ws, float max_norm, float lr, float beta1, float beta2,
+                   float eps, int64_t step, float* norm_out, void* stream) {
+    R2D2_REQUIRE(params && grads && exp_avg && exp_avg_sq && partial_ws && n > 0 && step >= 1, "bad arguments");
+    cudaStream_t s = as_stream(stream);
+    sumsq_partial_kernel<<<kNormBlocks, kNormThreads, 0, s>>>(grads, n, partial_ws);
+    const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+    const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+    clip_adam_kernel<<<kNormBlocks, 256, 0, s>>>(params, grads, exp_avg, exp_avg_sq, n, partial_ws, grad_scale, max_norm, lr,
+                                               beta1, beta2, eps, bc1, bc2_sqrt, norm_out);
+    R2D2_LAUNCH_CHECK();
+    return R2D2_OK;
+}
+
+}  // extern "C"

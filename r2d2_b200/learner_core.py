@@ -1,0 +1,214 @@
+"""Device-resident learner core: flat parameter buffers + the K1/K1b/K2/K5 pipeline.
+
+This is the engine under ``worker.Learner`` (worker.py:278-381 of the reference):
+one update = unroll(online) + unroll(target) -> fused TD -> BPTT -> [gradient
+all-reduce hook] -> clip+Adam -> re-pack, all launched on the current CUDA
+stream through the C ABI, no host synchronisation inside.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, Dict, Optional
+
+import torch
+
+from . import _lib
+
+PARAM_NAMES = [
+    "feature.0.weight", "feature.0.bias", "feature.2.weight", "feature.2.bias", "feature.4.weight", "feature.4.bias",
+    "feature.7.weight", "feature.7.bias", "recurrent.weight_ih_l0", "recurrent.weight_hh_l0", "recurrent.bias_ih_l0",
+    "recurrent.bias_hh_l0", "advantage.0.weight", "advantage.0.bias", "advantage.2.weight", "advantage.2.bias",
+    "value.0.weight", "value.0.bias", "value.2.weight", "value.2.bias",
+]
+HIDDEN = 512
+
+
+def param_shapes(action_dim: int, in_channels: int = 1):
+    """model.py:39-63 (conv1 in-channels generalised to C)."""
+    A, Cc, H = action_dim, in_channels, HIDDEN
+    return {
+        "feature.0.weight": (32, Cc, 8, 8), "feature.0.bias": (32,), "feature.2.weight": (64, 32, 4, 4),
+        "feature.2.bias": (64,), "feature.4.weight": (64, 64, 3, 3), "feature.4.bias": (64,),
+        "feature.7.weight": (512, 3136), "feature.7.bias": (512,),
+        "recurrent.weight_ih_l0": (4 * H, 512 + A + 1), "recurrent.weight_hh_l0": (4 * H, H),
+        "recurrent.bias_ih_l0": (4 * H,), "recurrent.bias_hh_l0": (4 * H,),
+        "advantage.0.weight": (H, H), "advantage.0.bias": (H,), "advantage.2.weight": (A, H), "advantage.2.bias": (A,),
+        "value.0.weight": (H, H), "value.0.bias": (H,), "value.2.weight": (1, H), "value.2.bias": (1,),
+    }
+
+
+def param_offsets(action_dim: int, in_channels: int = 1):
+    off = (C.c_int64 * 21)()
+    _lib.check(_lib.lib().r2d2_net_param_layout(action_dim, in_channels, off))
+    return list(off)
+
+
+class FlatParams:
+    """One flat fp32 device buffer + per-tensor views named like the reference state_dict."""
+
+    def __init__(self, action_dim: int, in_channels: int, device):
+        self.offsets = param_offsets(action_dim, in_channels)
+        self.shapes = param_shapes(action_dim, in_channels)
+        self.flat = torch.zeros(self.offsets[-1], dtype=torch.float32, device=device)
+        self.views: Dict[str, torch.Tensor] = {}
+        for i, name in enumerate(PARAM_NAMES):
+            shape = self.shapes[name]
+            n = 1
+            for s in shape:
+                n *= s
+            self.views[name] = self.flat[self.offsets[i]:self.offsets[i] + n].view(shape)
+
+    def load(self, state_dict) -> None:
+        for name, v in self.views.items():
+            v.copy_(state_dict[name].to(device=v.device, dtype=torch.float32))
+
+    def state_dict(self, device=None):
+        return {k: (v.detach().clone() if device is None else v.detach().to(device)) for k, v in self.views.items()}
+
+
+class DeviceLearner:
+    def __init__(self, action_dim: int, batch_size: int, seq_frames: int, in_channels: int = 1, max_learning: int = 40,
+                 max_forward: int = 5, lr: float = 1e-4, eps: float = 1e-3, grad_norm: float = 40.0,
+                 betas=(0.9, 0.999), device=None):
+        _lib.require_device()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.A, self.B, self.T, self.C = action_dim, batch_size, seq_frames, in_channels
+        self.Lmax, self.F = max_learning, max_forward
+        self.lr, self.eps, self.grad_norm, self.betas = lr, eps, grad_norm, betas
+        self.online = FlatParams(action_dim, in_channels, self.device)
+        self.target = FlatParams(action_dim, in_channels, self.device)
+        self.grads = FlatParams(action_dim, in_channels, self.device)
+        self.exp_avg = torch.zeros_like(self.online.flat)
+        self.exp_avg_sq = torch.zeros_like(self.online.flat)
+        self.num_updates = 0
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().r2d2_net_create(batch_size, seq_frames, in_channels, action_dim, max_learning,
+                                                  max_forward, C.byref(h)))
+        self._h = h
+        self.rows_cap = _lib.lib().r2d2_net_rows_capacity(h)
+        self.KU = _lib.lib().r2d2_net_ku(h)
+        d = self.device
+        R, A = self.rows_cap, action_dim
+        self.q = torch.zeros(R, A, device=d)
+        self.qn_online = torch.zeros(R, A, device=d)
+        self.qn_target = torch.zeros(R, A, device=d)
+        self.dq = torch.zeros(R, A, device=d)
+        self.td = torch.zeros(R, device=d)
+        self.prio = torch.zeros(batch_size, device=d)
+        self.loss_sum = torch.zeros(1, device=d)
+        self.rows = torch.zeros(1, dtype=torch.int32, device=d)
+        self.grad_scale = torch.ones(1, device=d)
+        self.norm = torch.zeros(1, device=d)
+        self._norm_ws = torch.zeros(592, dtype=torch.float64, device=d)
+        # hook called between backward and the optimizer: (learner) -> None, e.g. NCCL all-reduce
+        self.grad_hook: Optional[Callable[["DeviceLearner"], None]] = None
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                _lib.lib().r2d2_net_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    # ------------------------------------------------------------------ parameters
+    def load_state_dict(self, sd, target_sd=None) -> None:
+        self.online.load(sd)
+        self.target.load(target_sd if target_sd is not None else sd)
+        self.pack(0)
+        self.pack(1)
+
+    def sync_target(self) -> None:                      # worker.py:376-377
+        self.target.flat.copy_(self.online.flat)
+        self.pack(1)
+
+    def pack(self, which: int) -> None:
+        flat = self.online.flat if which == 0 else self.target.flat
+        _lib.check(_lib.lib().r2d2_net_pack(self._h, which, _lib.ptr(flat), _lib.stream_ptr()))
+
+    # ------------------------------------------------------------------ passes
+    def _pad_time(self, x: torch.Tensor) -> torch.Tensor:
+        if x.shape[1] == self.T:
+            return x.contiguous()
+        assert x.shape[1] < self.T, "batch longer than the workspace"
+        out = torch.zeros((x.shape[0], self.T) + tuple(x.shape[2:]), dtype=x.dtype, device=x.device)
+        out[:, :x.shape[1]] = x
+        return out
+
+    def prepare(self, batch: dict) -> dict:
+        """Move/shape a batch dict (see worker.py:219-238) for the kernels: device, contiguous,
+        time axis padded to T, hidden as (B,2,H), last_action as bytes."""
+        d = self.device
+        t = lambda v: v.to(d, non_blocking=True) if isinstance(v, torch.Tensor) else torch.as_tensor(v).to(d)
+        out = dict(batch)
+        out["obs"] = self._pad_time(t(batch["obs"]))
+        la = t(batch["last_action"])
+        if la.dtype == torch.bool:
+            la = la.view(torch.uint8)
+        elif la.dtype != torch.uint8:
+            la = (la != 0).to(torch.uint8)
+        out["last_action"] = self._pad_time(la)
+        out["last_reward"] = self._pad_time(t(batch["last_reward"]).float())
+        out["hidden"] = t(batch["hidden"]).float().contiguous()
+        assert out["hidden"].shape == (self.B, 2, HIDDEN), out["hidden"].shape
+        for k in ("burn_in", "learning", "forward"):
+            out[k] = t(batch[k]).to(torch.uint8).contiguous()
+        if "action" in batch:
+            out["action"] = t(batch["action"]).to(torch.uint8).reshape(-1).contiguous()
+            out["n_step_reward"] = t(batch["n_step_reward"]).float().contiguous()
+            out["gamma"] = t(batch["gamma"]).float().contiguous()
+            out["is_weights"] = t(batch["is_weights"]).float().contiguous()
+        return out
+
+    def forward(self, which: int, b: dict, q_learn: Optional[torch.Tensor], q_shift: Optional[torch.Tensor]) -> None:
+        flat = self.online.flat if which == 0 else self.target.flat
+        p = _lib.ptr
+        assert b["obs"].shape == (self.B, self.T, self.C, 84, 84) and b["obs"].dtype == torch.uint8
+        _lib.check(_lib.lib().r2d2_net_forward(self._h, which, p(flat), p(b["obs"]), p(b["last_action"]),
+                                               p(b["last_reward"]), p(b["hidden"]), p(b["burn_in"]), p(b["learning"]),
+                                               p(b["forward"]), p(q_learn), p(q_shift), _lib.stream_ptr()))
+
+    def backward(self, dq: torch.Tensor) -> None:
+        p = _lib.ptr
+        _lib.check(_lib.lib().r2d2_net_backward(self._h, p(self.online.flat), p(dq), p(self.grads.flat),
+                                                _lib.stream_ptr()))
+
+    def compute_gradients(self, b: dict) -> None:
+        """worker.py:345-363: Q passes, TD/loss/priorities, backward.  Results stay on device in
+        self.td / self.prio / self.loss_sum / self.rows / self.grads (grads of loss_sum)."""
+        self._live = b                                   # keep obs/hidden alive until backward ran
+        self.forward(0, b, self.q, self.qn_online)
+        self.forward(1, b, None, self.qn_target)
+        p = _lib.ptr
+        _lib.check(_lib.lib().r2d2_td_loss(p(self.q), p(self.qn_online), p(self.qn_target), p(b["action"]),
+                                           p(b["n_step_reward"]), p(b["gamma"]), p(b["is_weights"]), p(b["learning"]),
+                                           self.B, self.A, p(self.td), p(self.prio), p(self.loss_sum), p(self.rows),
+                                           p(self.dq), _lib.stream_ptr()))
+        self.backward(self.dq)
+        torch.reciprocal(self.rows.float(), out=self.grad_scale)      # mean over rows (worker.py:354)
+
+    def apply_gradients(self) -> None:
+        """worker.py:364-365 (+ re-pack of the online weights)."""
+        self.num_updates += 1
+        p = _lib.ptr
+        b1, b2 = self.betas
+        _lib.check(_lib.lib().r2d2_clip_adam(p(self.online.flat), p(self.grads.flat), p(self.exp_avg), p(self.exp_avg_sq),
+                                             self.online.flat.numel(), p(self.grad_scale), p(self._norm_ws),
+                                             float(self.grad_norm), float(self.lr), float(b1), float(b2), float(self.eps),
+                                             self.num_updates, p(self.norm), _lib.stream_ptr()))
+        self.pack(0)
+
+    def update(self, b: dict) -> None:
+        self.compute_gradients(b)
+        if self.grad_hook is not None:
+            self.grad_hook(self)
+        self.apply_gradients()
+
+    # ------------------------------------------------------------------ debug
+    def debug_tensor(self, which: int, name: str, numel: int, dtype=torch.float32) -> torch.Tensor:
+        from .priority_tree import _from_device_ptr
+        addr = _lib.lib().r2d2_net_debug_ptr(self._h, which, name.encode())
+        assert addr, name
+        return _from_device_ptr(addr, numel, dtype, self.device)

@@ -1,0 +1,127 @@
+"""K1/K1b/K2/K5 on the GPU vs the CPU oracle and the reference's golden learner outputs.
+
+Parity bars (north star): TD-errors and updated priorities within 1e-4 (fp32) of the reference
+learner on identical batches.  Stage checks (latent, hidden states, Q, gradients, Adam step) are
+tighter and exist to localise a failure.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import synth
+from oracle.gen_golden import CFG0_SCRIPT
+from oracle.learner import LearnerState, init_params, learner_update
+from helpers import build_oracle_replay, sample_with_seed, A
+
+pytestmark = pytest.mark.gpu
+
+DIAG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+
+
+def _diag(line):
+    os.makedirs(DIAG, exist_ok=True)
+    with open(os.path.join(DIAG, "learner_diag.txt"), "a") as f:
+        f.write(line + "\n")
+
+
+def _mk_learner(B, T, C=1, Lmax=40, F=5, params=None):
+    from r2d2_b200.learner_core import DeviceLearner
+    dl = DeviceLearner(A, B, T, in_channels=C, max_learning=Lmax, max_forward=F)
+    dl.load_state_dict(params)
+    return dl
+
+
+def _torch_batch(d):
+    return {k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v) for k, v in d.items()}
+
+
+def _stage_compare(tag, dl, d, out, fs=5):
+    """Compare every stage of one update (already run on dl) against oracle output `out`."""
+    B, T = dl.B, dl.T
+    rows = int(dl.rows.item())
+    assert rows == out["td"].shape[0]
+    KU = dl.KU
+    U = dl.debug_tensor(0, "U", T * B * KU).view(T, B, KU).cpu()
+    lat = U[:, :, :512].permute(1, 0, 2)                       # (B,T,512)
+    Tb = out["latent"].shape[1]
+    e_lat = (lat[:, :Tb] - out["latent"]).abs().max().item()
+    Hs = dl.debug_tensor(0, "Hs", T * B * 512).view(T, B, 512).cpu().permute(1, 0, 2)
+    ln = (torch.from_numpy(d["burn_in"].astype(np.int64)) + torch.from_numpy(d["learning"].astype(np.int64)))
+    mask = (torch.arange(Tb)[None, :] < ln[:, None])
+    e_h = ((Hs[:, :Tb] - out["hidden"]).abs() * mask[..., None]).max().item()
+    e_q = (dl.q[:rows].cpu() - out["q"]).abs().max().item()
+    e_qn = (dl.qn_online[:rows].cpu() - out["qn_online"]).abs().max().item()
+    e_qt = (dl.qn_target[:rows].cpu() - out["qn_target"]).abs().max().item()
+    e_td = np.abs(dl.td[:rows].cpu().numpy() - out["td"]).max()
+    e_pr = np.abs(dl.prio.cpu().numpy() - out["priorities"]).max()
+    loss = float(dl.loss_sum.item()) / rows
+    _diag(f"{tag}: latent {e_lat:.3e} hidden {e_h:.3e} q {e_q:.3e} qn_on {e_qn:.3e} qn_tg {e_qt:.3e} "
+          f"td {e_td:.3e} prio {e_pr:.3e} loss {loss:.6f} vs {out['loss']:.6f}")
+    worst = []
+    for name, g in out["grads"].items():
+        mine = dl.grads.views[name].cpu() / rows
+        err = (mine - g).abs().max().item()
+        ref = g.abs().max().item()
+        worst.append((err / (ref + 1e-12), name, err, ref))
+    worst.sort(reverse=True)
+    for rel, name, err, ref in worst[:6]:
+        _diag(f"{tag}:   grad {name}: max abs err {err:.3e} (max |g| {ref:.3e}, rel {rel:.3e})")
+    assert e_lat < 2e-5 and e_h < 2e-5, (e_lat, e_h)
+    assert max(e_q, e_qn, e_qt) < 2e-5
+    assert e_td < 1e-4 and e_pr < 1e-4                      # the north-star bar
+    assert abs(loss - out["loss"]) < 1e-5 * max(1.0, abs(out["loss"]))
+    assert worst[0][0] < 2e-3, worst[0]
+    assert abs(float(dl.norm.item()) - out["grad_norm"]) <= 1e-3 * out["grad_norm"] if dl.num_updates else True
+
+
+@pytest.mark.parametrize("ragged,B", [(True, 8), (False, 4)])
+def test_single_update_stages_vs_oracle(ragged, B):
+    torch.set_num_threads(min(32, os.cpu_count() or 8))
+    params = init_params(A, seed=3)
+    d = synth.synthetic_batch(B, A, seed=17, ragged=ragged)
+    st = LearnerState(online={k: v.clone() for k, v in params.items()},
+                      target=init_params(A, seed=4))
+    out = learner_update(st, synth.to_torch_batch(d))
+    dl = _mk_learner(B, d["obs"].shape[1], params=params)
+    dl.target.load(init_params(A, seed=4))
+    dl.pack(1)
+    dl.update(dl.prepare(_torch_batch(d)))
+    torch.cuda.synchronize()
+    _stage_compare(f"synthetic B={B} ragged={ragged}", dl, d, out)
+    # Adam step
+    for name, p in st.online.items():
+        err = (dl.online.views[name].cpu() - p).abs().max().item()
+        assert err < 5e-6, (name, err)
+
+
+@pytest.mark.parametrize("name,script", [("learner_ragged.npz", synth.RAGGED_SCRIPT), ("learner_cfg0.npz", CFG0_SCRIPT)])
+def test_consecutive_updates_vs_reference_golden(golden_dir, name, script):
+    """K consecutive updates on replay-sampled ragged batches; compared with the outputs of the
+    unmodified reference Learner.run recorded in tests/golden (TD, priorities, loss, Q, params)."""
+    g = np.load(os.path.join(golden_dir, name))
+    batch_size, K, bl, ls, bi, fs, seed0, num_blocks = (int(x) for x in g["meta"])
+    rb, _ = build_oracle_replay(script, num_blocks, batch_size, bl, ls, bi, fs)
+    params = init_params(A, seed=3)
+    dl = _mk_learner(batch_size, bi + ls + fs, Lmax=ls, F=fs, params=params)
+    for k in range(K):
+        d = sample_with_seed(rb, seed0 + k)
+        dl.update(dl.prepare(_torch_batch(d)))
+        torch.cuda.synchronize()
+        rows = int(dl.rows.item())
+        td, prio = dl.td[:rows].cpu().numpy(), dl.prio.cpu().numpy()
+        loss = float(dl.loss_sum.item()) / rows
+        e_td = np.abs(td - g[f"k{k}_out_td"]).max()
+        e_pr = np.abs(prio - g[f"k{k}_out_priorities"]).max()
+        e_q = np.abs(dl.q[:rows].cpu().numpy() - g[f"k{k}_out_q"]).max()
+        e_qn = np.abs(dl.qn_online[:rows].cpu().numpy() - g[f"k{k}_out_qn_online"]).max()
+        e_qt = np.abs(dl.qn_target[:rows].cpu().numpy() - g[f"k{k}_out_qn_target"]).max()
+        e_p = max(np.abs(dl.online.views[n].flatten()[:16].cpu().numpy() - g[f"k{k}_phead_{n}"]).max()
+                  for n in dl.online.views)
+        _diag(f"{name} k={k}: td {e_td:.3e} prio {e_pr:.3e} q {e_q:.3e} qn_on {e_qn:.3e} qn_tg {e_qt:.3e} "
+              f"loss {loss:.6f} vs {float(g[f'k{k}_out_loss']):.6f} params {e_p:.3e}")
+        assert e_td < 1e-4 and e_pr < 1e-4
+        assert max(e_q, e_qn, e_qt) < 5e-5
+        assert abs(loss - float(g[f"k{k}_out_loss"])) < 2e-5 * max(1.0, abs(loss))
+        assert e_p < 2e-5
