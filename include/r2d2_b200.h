@@ -60,9 +60,7 @@ double* r2d2_tree_nodes(r2d2_tree* t);
  *   float32 like NumPy does for an f32 array, stored as float64; every ancestor is recomputed
  *   from its two children in float64.  Duplicate slots: the LAST occurrence wins.
  *   Masking: pass old_ptr < 0 to disable.  Otherwise slots whose block
- *   (slot / seq_per_block) was overwritten between old_ptr and cur_ptr are skipped.
- *   cur_ptr_dev (optional, may be NULL): when non-NULL the current block pointer is read
- *   from this device int32 instead of cur_ptr (HBM-resident replay keeps it on device). */
+ *   (slot / seq_per_block) was overwritten between old_ptr and cur_ptr are skipped. */
 int r2d2_tree_update(r2d2_tree* t, const int64_t* idx, const float* td, int64_t n,
                      int64_t old_ptr, int64_t cur_ptr, int64_t seq_per_block, void* stream);
 /* Write already-exponentiated float64 leaf values (test/restore path; same ancestor rebuild). */
@@ -121,12 +119,28 @@ int r2d2_net_pack(r2d2_net* n, int which, const float* params, void* stream);
 int r2d2_net_forward(r2d2_net* n, int which, const float* params, const uint8_t* obs, const uint8_t* last_action,
                      const float* last_reward, const float* hidden, const uint8_t* burn, const uint8_t* learn,
                      const uint8_t* fwd, float* q_learn_out, float* q_shift_out, void* stream);
+/* The three Q tensors of one learner update (worker.py:346,347,352) in one call: both slots are unrolled on the
+ * same batch and the two recurrences advance together in shared launches. */
+int r2d2_net_forward_pair(r2d2_net* n, const float* params_online, const float* params_target, const uint8_t* obs,
+                          const uint8_t* last_action, const float* last_reward, const float* hidden, const uint8_t* burn,
+                          const uint8_t* learn, const uint8_t* fwd, float* q_learn_out, float* qn_online_out,
+                          float* qn_target_out, void* stream);
 /* loss.backward() (worker.py:363) for the online slot: BPTT through all b+l steps (burn-in
  * included) and the encoder.  dq [rows_capacity][A]; grads: flat buffer in the parameter layout,
  * fully overwritten (alignment gaps are left untouched and must be zero). */
 int r2d2_net_backward(r2d2_net* n, const float* params, const float* dq, float* grads, void* stream);
 /* Test/debug access to device intermediates (see net.cu for the names). */
 void* r2d2_net_debug_ptr(r2d2_net* n, int which, const char* name);
+
+/* GEMM backend of every contraction in K1/K1b: 0 = fp32 CUDA-core FFMA (on-device numerical
+ * reference), 1 = tcgen05 bf16x3 split (hi*hi + hi*lo + lo*hi, fp32 accumulate in TMEM: parity mode,
+ * default), 2 = tcgen05 plain bf16 (fast mode).  Process-wide; returns the previous value. */
+int r2d2_set_gemm_backend(int backend);
+/* Test entry: C[M][N] = A x B^T on plain fp32 matrices through the chosen backend / tile width.
+ * a_major, b_major: 0 = [rows][K] storage, 1 = [K][rows] storage.  splits > 1 leaves split-K
+ * partials [splits][M][N] in C. */
+int r2d2_debug_gemm(int backend, int ubn, int a_major, int b_major, int M, int N, int K, const float* A, const float* B,
+                    float* C, int splits, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K5  clip_grad_norm_(max_norm) + Adam(lr, eps).step()  (worker.py:289,364-365) on the flat

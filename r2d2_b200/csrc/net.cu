@@ -19,7 +19,7 @@
 // and at the n-step-shifted positions are two row gathers of the same unroll.
 #include <map>
 
-#include "gemm.cuh"
+#include "dispatch.cuh"
 
 namespace r2d2 {
 
@@ -28,6 +28,7 @@ constexpr int G4 = 4 * H;
 constexpr int LATENT = 512;
 constexpr int FLAT3 = 3136;     // 7*7*64
 constexpr int NPARAM = 20;
+constexpr int kRecSplits = 8;   // split-K of the BPTT recurrence GEMM (K = 2048) across CTAs
 
 enum ParamId {
     P_C1W, P_C1B, P_C2W, P_C2B, P_C3W, P_C3B, P_FCW, P_FCB, P_WIH, P_WHH, P_BIH, P_BHH,
@@ -229,7 +230,7 @@ struct EpiLstmCell {
 };
 
 // BPTT pointwise step: d(pre-activation gates) at time t
-__global__ void lstm_bwd_pointwise_kernel(const float* __restrict__ dH_t, const float* __restrict__ dhrec,
+__global__ void lstm_bwd_pointwise_kernel(const float* __restrict__ dH_t, const float* __restrict__ dhrec, int nparts,
                                           float* __restrict__ dcrec, const float* __restrict__ G_t,
                                           const float* __restrict__ C_t, const float* __restrict__ C_prev, int ld_cprev,
                                           const int* __restrict__ len_learn, int t, int B, float* __restrict__ DG_t) {
@@ -241,7 +242,8 @@ __global__ void lstm_bwd_pointwise_kernel(const float* __restrict__ dH_t, const 
         const float4 g = *reinterpret_cast<const float4*>(G_t + (size_t)b * G4 + 4 * j);
         const float gi = g.x, gf = g.y, gg = g.z, go = g.w;
         const float tc = tanhf(C_t[i]);
-        const float dh = dH_t[i] + dhrec[i];
+        float dh = dH_t[i];
+        for (int p = 0; p < nparts; ++p) dh += dhrec[(size_t)p * B * H + i];      // split-K partials of dgates.W_hh
         const float dc = dcrec[i] + dh * go * (1.f - tc * tc);
         const float cp = C_prev[(size_t)b * ld_cprev + j];
         out.x = dc * gg * gi * (1.f - gi);
@@ -374,12 +376,12 @@ static cudaError_t colsum(const float* X, int M, int N, int kind, float* g, int6
     return cudaGetLastError();
 }
 
-template <int BM, int BN, class AL, class BL>
+template <int BM, int BN, int UBN, class AL, class BL>
 static cudaError_t wgrad(const AL& al, const BL& bl, int M, int N, int K, int splits, int kind, r2d2_net* net, float* grads,
                          const int64_t* d_off, float scale, cudaStream_t s) {
     if ((size_t)splits * M * N > net->ws_floats) return cudaErrorInvalidValue;
     EpiPartial ep{net->ws, M, N};
-    cudaError_t e = launch_gemm<BM, BN, 16>(al, bl, ep, M, N, K, splits, s);
+    cudaError_t e = run_gemm<BM, BN, UBN>(al, bl, ep, M, N, K, splits, s);
     if (e != cudaSuccess) return e;
     const int64_t tot = (int64_t)M * N;
     reduce_route_kernel<<<cdiv(tot, 256), 256, 0, s>>>(net->ws, splits, M, N, kind, grads, d_off, net->A, net->C, scale);
@@ -450,7 +452,7 @@ int r2d2_net_create(int B, int T, int C, int A, int Lmax, int max_forward, r2d2_
     R2D2_CUDA_CHECK(cudaMalloc(&n->len_full, B * sizeof(int)));
     R2D2_CUDA_CHECK(cudaMalloc(&n->len_learn, B * sizeof(int)));
     R2D2_CUDA_CHECK(cudaMalloc(&n->d_rows, sizeof(int)));
-    rc |= alloc_f(&n->dH, TB * H); rc |= alloc_f(&n->DG, TB * G4); rc |= alloc_f(&n->dhrec, (size_t)B * H);
+    rc |= alloc_f(&n->dH, TB * H); rc |= alloc_f(&n->DG, TB * G4); rc |= alloc_f(&n->dhrec, (size_t)kRecSplits * B * H);
     rc |= alloc_f(&n->dcrec, (size_t)B * H); rc |= alloc_f(&n->dlat, NF * LATENT); rc |= alloc_f(&n->dpre3, NF * FLAT3);
     rc |= alloc_f(&n->dpre2, NF * 5184); rc |= alloc_f(&n->dpre1, NF * 12800); rc |= alloc_f(&n->dhid, (size_t)n->Rmax * 2 * H);
     rc |= alloc_f(&n->dout16, (size_t)n->Rmax * 16);
@@ -492,6 +494,112 @@ int r2d2_net_pack(r2d2_net* n, int which, const float* params, void* stream) {
     return R2D2_OK;
 }
 
+struct FwdArgs {
+    const float* params; const uint8_t* obs; const uint8_t* last_action; const float* last_reward; const float* hidden;
+};
+
+// encoder + input projection of one slot (model.py:39-49,92); 1/255 of worker.py:342 folded into the conv1 epilogue
+static int net_encode(r2d2_net* n, int which, const FwdArgs& fa, cudaStream_t s) {
+    const int B = n->B, T = n->T, C = n->C, A = n->A, KU = n->KU, NF = n->NF;
+    Packed& pk = n->pk[which];
+    Acts& ac = n->ac[which];
+    const int64_t* off = n->off;
+    const float* params = fa.params;
+    side_columns_kernel<<<T * B, 32, 0, s>>>(ac.U, fa.last_action, fa.last_reward, B, T, A, KU);
+    R2D2_LAUNCH_CHECK();
+    {
+        Conv1FrameK a{fa.obs, C, NF};
+        MatK b{params + off[P_C1W], 32, C * 64, C * 64};
+        EpiBias<true> e{ac.act1, params + off[P_C1B], NF * 400, 32, 32, 1.f / 255.f};
+        R2D2_CUDA_CHECK((run_gemm<128, 32, 32>(a, b, e, NF * 400, 32, C * 64, 1, s)));
+    }
+    {
+        ConvNHWC_K<20, 20, 32, 9, 9, 4, 4, 2> a{ac.act1, NF};
+        MatK b{pk.W2p, 64, 512, 512};
+        EpiBias<true> e{ac.act2, params + off[P_C2B], NF * 81, 64, 64, 1.f};
+        R2D2_CUDA_CHECK((run_gemm<128, 64, 64>(a, b, e, NF * 81, 64, 512, 1, s)));
+    }
+    {
+        ConvNHWC_K<9, 9, 64, 7, 7, 3, 3, 1> a{ac.act2, NF};
+        MatK b{pk.W3p, 64, 576, 576};
+        EpiBias<true> e{ac.act3, params + off[P_C3B], NF * 49, 64, 64, 1.f};
+        R2D2_CUDA_CHECK((run_gemm<128, 64, 64>(a, b, e, NF * 49, 64, 576, 1, s)));
+    }
+    {
+        MatK a{ac.act3, NF, FLAT3, FLAT3};
+        MatK b{pk.Wfcp, LATENT, FLAT3, FLAT3};
+        EpiLatent e{ac.U, params + off[P_FCB], B, T, KU};
+        R2D2_CUDA_CHECK((run_gemm<128, 128, 128>(a, b, e, NF, LATENT, FLAT3, 1, s)));
+    }
+    {   // LSTM input projection for all steps at once (hoisted out of the recurrence)
+        MatK a{ac.U, T * B, KU, KU};
+        MatK b{pk.Wih_p, G4, KU, KU};
+        EpiBias<false> e{ac.XP, pk.bias_p, T * B, G4, G4, 1.f};
+        R2D2_CUDA_CHECK((run_gemm<128, 128, 128>(a, b, e, T * B, G4, KU, 1, s)));
+    }
+    return R2D2_OK;
+}
+
+struct StepOps { MatK a; MatK b; EpiLstmCell e; };
+static StepOps lstm_step_ops(r2d2_net* n, int which, const float* hidden, int t) {
+    const int B = n->B;
+    Packed& pk = n->pk[which];
+    Acts& ac = n->ac[which];
+    const float* hp = t ? ac.Hs + (size_t)(t - 1) * B * H : hidden;
+    const float* cp = t ? ac.Cs + (size_t)(t - 1) * B * H : hidden + H;
+    const int ldp = t ? H : 2 * H;
+    return StepOps{MatK{hp, B, H, ldp}, MatK{pk.Whh_p, G4, H, H},
+                   EpiLstmCell{ac.XP + (size_t)t * B * G4, cp, hp, ldp, ac.Hs + (size_t)t * B * H, ac.Cs + (size_t)t * B * H,
+                               which == 0 ? ac.Gs + (size_t)t * B * G4 : nullptr, n->len_full, t, B}};
+}
+
+// recurrence (model.py:95-100 / 134-141): sequences advance while t < b+l+f.  which = 0/1: one slot; 2: both slots
+// in the same launches (two independent recurrences hide each other's per-step latency).
+static int net_recurrence(r2d2_net* n, int which, const float* hidden, cudaStream_t s) {
+    const int B = n->B, T = n->T;
+    for (int t = 0; t < T; ++t) {
+        if (which == 2) {
+            StepOps o0 = lstm_step_ops(n, 0, hidden, t), o1 = lstm_step_ops(n, 1, hidden, t);
+            R2D2_CUDA_CHECK((run_gemm_pair<64, 64, 64>(o0.a, o0.b, o0.e, o1.a, o1.b, o1.e, B, G4, H, s)));
+        } else {
+            StepOps o = lstm_step_ops(n, which, hidden, t);
+            R2D2_CUDA_CHECK((run_gemm<64, 64, 64>(o.a, o.b, o.e, B, G4, H, 1, s)));
+        }
+    }
+    return R2D2_OK;
+}
+
+// dueling head on the gathered rows (model.py:102-117, 143-148)
+static int net_heads(r2d2_net* n, int which, const float* params, float* q_learn_out, float* q_shift_out, cudaStream_t s) {
+    const int A = n->A, Rmax = n->Rmax;
+    Packed& pk = n->pk[which];
+    Acts& ac = n->ac[which];
+    const int64_t* off = n->off;
+    const int nsets = 2;
+    {
+        RowGatherK a{ac.Hs, n->row_src, nsets * Rmax, H, H};
+        MatK b{pk.Wh0, 2 * H, H, H};
+        EpiBias<true> e{ac.hid, pk.bh0, nsets * Rmax, 2 * H, 2 * H, 1.f};
+        R2D2_CUDA_CHECK((run_gemm<128, 128, 128>(a, b, e, nsets * Rmax, 2 * H, H, 1, s)));
+    }
+    if (q_learn_out)
+        head_out_kernel<<<cdiv((int64_t)Rmax * 32, 256), 256, 0, s>>>(ac.hid, params + off[P_A2W], params + off[P_A2B],
+                                                                     params + off[P_V2W], params + off[P_V2B], Rmax, A, q_learn_out);
+    if (q_shift_out)
+        head_out_kernel<<<cdiv((int64_t)Rmax * 32, 256), 256, 0, s>>>(ac.hid + (size_t)Rmax * 2 * H, params + off[P_A2W],
+                                                                     params + off[P_A2B], params + off[P_V2W],
+                                                                     params + off[P_V2B], Rmax, A, q_shift_out);
+    R2D2_LAUNCH_CHECK();
+    return R2D2_OK;
+}
+
+static int net_prep(r2d2_net* n, const uint8_t* burn, const uint8_t* learn, const uint8_t* fwd, cudaStream_t s) {
+    prep_rows_kernel<<<1, 256, (n->B + 1) * sizeof(int), s>>>(burn, learn, fwd, n->B, n->F, n->Rmax, n->row_src, n->len_full,
+                                                             n->len_learn, n->d_rows);
+    R2D2_LAUNCH_CHECK();
+    return R2D2_OK;
+}
+
 /* Forward unroll of slot `which` (0 online, 1 target).  model.py:81-150.
  *   obs u8 [B][T][C][84][84]; last_action u8/bool [B][T][A]; last_reward f32 [B][T];
  *   hidden f32 [B][2][H] ([b][0]=h0, [b][1]=c0 -- the Block.hidden layout, worker.py:198);
@@ -505,76 +613,35 @@ int r2d2_net_forward(r2d2_net* n, int which, const float* params, const uint8_t*
     R2D2_REQUIRE(n && (which == 0 || which == 1) && params && obs && last_action && last_reward && hidden && burn && learn && fwd,
                  "bad arguments");
     cudaStream_t s = as_stream(stream);
-    const int B = n->B, T = n->T, C = n->C, A = n->A, KU = n->KU, NF = n->NF, Rmax = n->Rmax;
-    Packed& pk = n->pk[which];
-    Acts& ac = n->ac[which];
-    const int64_t* off = n->off;
     if (which == 0) { n->obs = obs; n->hidden = hidden; }
+    FwdArgs fa{params, obs, last_action, last_reward, hidden};
+    int rc = net_prep(n, burn, learn, fwd, s);
+    if (!rc) rc = net_encode(n, which, fa, s);
+    if (!rc) rc = net_recurrence(n, which, hidden, s);
+    if (!rc) rc = net_heads(n, which, params, q_learn_out, q_shift_out, s);
+    return rc;
+}
 
-    prep_rows_kernel<<<1, 256, (B + 1) * sizeof(int), s>>>(burn, learn, fwd, B, n->F, Rmax, n->row_src, n->len_full, n->len_learn,
-                                                          n->d_rows);
-    side_columns_kernel<<<T * B, 32, 0, s>>>(ac.U, last_action, last_reward, B, T, A, KU);
-    R2D2_LAUNCH_CHECK();
-
-    // encoder (model.py:39-49); 1/255 of worker.py:342 folded into the conv1 epilogue
-    {
-        Conv1FrameK a{obs, C, NF};
-        MatK b{params + off[P_C1W], 32, C * 64, C * 64};
-        EpiBias<true> e{ac.act1, params + off[P_C1B], NF * 400, 32, 32, 1.f / 255.f};
-        R2D2_CUDA_CHECK((launch_gemm<128, 32, 16>(a, b, e, NF * 400, 32, C * 64, 1, s)));
-    }
-    {
-        ConvNHWC_K<20, 20, 32, 9, 9, 4, 4, 2> a{ac.act1, NF};
-        MatK b{pk.W2p, 64, 512, 512};
-        EpiBias<true> e{ac.act2, params + off[P_C2B], NF * 81, 64, 64, 1.f};
-        R2D2_CUDA_CHECK((launch_gemm<128, 64, 16>(a, b, e, NF * 81, 64, 512, 1, s)));
-    }
-    {
-        ConvNHWC_K<9, 9, 64, 7, 7, 3, 3, 1> a{ac.act2, NF};
-        MatK b{pk.W3p, 64, 576, 576};
-        EpiBias<true> e{ac.act3, params + off[P_C3B], NF * 49, 64, 64, 1.f};
-        R2D2_CUDA_CHECK((launch_gemm<128, 64, 16>(a, b, e, NF * 49, 64, 576, 1, s)));
-    }
-    {
-        MatK a{ac.act3, NF, FLAT3, FLAT3};
-        MatK b{pk.Wfcp, LATENT, FLAT3, FLAT3};
-        EpiLatent e{ac.U, params + off[P_FCB], B, T, KU};
-        R2D2_CUDA_CHECK((launch_gemm<128, 128, 16>(a, b, e, NF, LATENT, FLAT3, 1, s)));
-    }
-    {   // LSTM input projection for all steps at once (hoisted out of the recurrence)
-        MatK a{ac.U, T * B, KU, KU};
-        MatK b{pk.Wih_p, G4, KU, KU};
-        EpiBias<false> e{ac.XP, pk.bias_p, T * B, G4, G4, 1.f};
-        R2D2_CUDA_CHECK((launch_gemm<128, 128, 16>(a, b, e, T * B, G4, KU, 1, s)));
-    }
-    // recurrence (model.py:95-100 / 134-141): sequences advance while t < b+l+f
-    for (int t = 0; t < T; ++t) {
-        const float* hp = t ? ac.Hs + (size_t)(t - 1) * B * H : hidden;
-        const float* cp = t ? ac.Cs + (size_t)(t - 1) * B * H : hidden + H;
-        const int ldp = t ? H : 2 * H;
-        MatK a{hp, B, H, ldp};
-        MatK b{pk.Whh_p, G4, H, H};
-        EpiLstmCell e{ac.XP + (size_t)t * B * G4, cp, hp, ldp, ac.Hs + (size_t)t * B * H, ac.Cs + (size_t)t * B * H,
-                      which == 0 ? ac.Gs + (size_t)t * B * G4 : nullptr, n->len_full, t, B};
-        R2D2_CUDA_CHECK((launch_gemm<64, 64, 16>(a, b, e, B, G4, H, 1, s)));
-    }
-    // dueling head on the gathered rows (model.py:102-117, 143-148)
-    const int nsets = 2;
-    {
-        RowGatherK a{ac.Hs, n->row_src, nsets * Rmax, H, H};
-        MatK b{pk.Wh0, 2 * H, H, H};
-        EpiBias<true> e{ac.hid, pk.bh0, nsets * Rmax, 2 * H, 2 * H, 1.f};
-        R2D2_CUDA_CHECK((launch_gemm<128, 128, 16>(a, b, e, nsets * Rmax, 2 * H, H, 1, s)));
-    }
-    if (q_learn_out)
-        head_out_kernel<<<cdiv((int64_t)Rmax * 32, 256), 256, 0, s>>>(ac.hid, params + off[P_A2W], params + off[P_A2B],
-                                                                     params + off[P_V2W], params + off[P_V2B], Rmax, A, q_learn_out);
-    if (q_shift_out)
-        head_out_kernel<<<cdiv((int64_t)Rmax * 32, 256), 256, 0, s>>>(ac.hid + (size_t)Rmax * 2 * H, params + off[P_A2W],
-                                                                     params + off[P_A2B], params + off[P_V2W],
-                                                                     params + off[P_V2B], Rmax, A, q_shift_out);
-    R2D2_LAUNCH_CHECK();
-    return R2D2_OK;
+/* The learner's three Q tensors in one call (worker.py:346,347,352): online and target unrolls on the same
+ * batch with the two recurrences advanced together.  q_learn_out / qn_online_out from the online parameters,
+ * qn_target_out from the target parameters. */
+int r2d2_net_forward_pair(r2d2_net* n, const float* params_online, const float* params_target, const uint8_t* obs,
+                          const uint8_t* last_action, const float* last_reward, const float* hidden, const uint8_t* burn,
+                          const uint8_t* learn, const uint8_t* fwd, float* q_learn_out, float* qn_online_out,
+                          float* qn_target_out, void* stream) {
+    R2D2_REQUIRE(n && params_online && params_target && obs && last_action && last_reward && hidden && burn && learn && fwd &&
+                     q_learn_out && qn_online_out && qn_target_out,
+                 "bad arguments");
+    cudaStream_t s = as_stream(stream);
+    n->obs = obs; n->hidden = hidden;
+    FwdArgs f0{params_online, obs, last_action, last_reward, hidden}, f1{params_target, obs, last_action, last_reward, hidden};
+    int rc = net_prep(n, burn, learn, fwd, s);
+    if (!rc) rc = net_encode(n, 0, f0, s);
+    if (!rc) rc = net_encode(n, 1, f1, s);
+    if (!rc) rc = net_recurrence(n, 2, hidden, s);
+    if (!rc) rc = net_heads(n, 0, params_online, q_learn_out, qn_online_out, s);
+    if (!rc) rc = net_heads(n, 1, params_target, nullptr, qn_target_out, s);
+    return rc;
 }
 
 /* BPTT + encoder backward of the ONLINE slot (loss.backward(), worker.py:363).
@@ -597,13 +664,13 @@ int r2d2_net_backward(r2d2_net* n, const float* params, const float* dq, float* 
     {   // layer-2 weights: [A+1 (pad 16)] x [1024] = dout16^T . hid
         MatM a{n->dout16, 16, Rmax, 16};
         MatM b{ac.hid, 2 * H, Rmax, 2 * H};
-        R2D2_CUDA_CHECK((wgrad<64, 64>(a, b, 16, 2 * H, Rmax, 4, R_H2, n, grads, d_off, 1.f, s)));
+        R2D2_CUDA_CHECK((wgrad<64, 64, 128>(a, b, 16, 2 * H, Rmax, 4, R_H2, n, grads, d_off, 1.f, s)));
         R2D2_CUDA_CHECK(colsum(n->dout16, Rmax, 16, B_H2, grads, off[P_A2B], off[P_V2B], A, n->colws, s));
     }
     {   // layer-0 weights: [1024] x [512] = dhid^T . Hsel
         MatM a{n->dhid, 2 * H, Rmax, 2 * H};
         RowGatherM b{ac.Hs, n->row_src, H, Rmax, H};
-        R2D2_CUDA_CHECK((wgrad<128, 128>(a, b, 2 * H, H, Rmax, 4, R_H0, n, grads, d_off, 1.f, s)));
+        R2D2_CUDA_CHECK((wgrad<128, 128, 128>(a, b, 2 * H, H, Rmax, 4, R_H0, n, grads, d_off, 1.f, s)));
         R2D2_CUDA_CHECK(colsum(n->dhid, Rmax, 2 * H, B_H0, grads, off[P_A0B], off[P_V0B], A, n->colws, s));
     }
     R2D2_CUDA_CHECK(cudaMemsetAsync(n->dH, 0, TB * H * sizeof(float), s));
@@ -611,75 +678,75 @@ int r2d2_net_backward(r2d2_net* n, const float* params, const float* dq, float* 
         MatK a{n->dhid, Rmax, 2 * H, 2 * H};
         MatM b{pk.Wh0, H, 2 * H, H};
         EpiScatterRows e{n->dH, n->row_src, n->d_rows, Rmax};
-        R2D2_CUDA_CHECK((launch_gemm<128, 128, 16>(a, b, e, Rmax, H, 2 * H, 1, s)));
+        R2D2_CUDA_CHECK((run_gemm<128, 128, 128>(a, b, e, Rmax, H, 2 * H, 1, s)));
     }
     // ---- BPTT through all b+l steps, burn-in included (no detach anywhere in model.py:122-150)
-    R2D2_CUDA_CHECK(cudaMemsetAsync(n->dhrec, 0, (size_t)B * H * sizeof(float), s));
     R2D2_CUDA_CHECK(cudaMemsetAsync(n->dcrec, 0, (size_t)B * H * sizeof(float), s));
     for (int t = T - 1; t >= 0; --t) {
         const float* cprev = t ? ac.Cs + (size_t)(t - 1) * B * H : n->hidden + H;
-        lstm_bwd_pointwise_kernel<<<cdiv(B * H, 256), 256, 0, s>>>(n->dH + (size_t)t * B * H, n->dhrec, n->dcrec,
+        lstm_bwd_pointwise_kernel<<<cdiv(B * H, 256), 256, 0, s>>>(n->dH + (size_t)t * B * H, n->dhrec,
+                                                                  t == T - 1 ? 0 : kRecSplits, n->dcrec,
                                                                   ac.Gs + (size_t)t * B * G4, ac.Cs + (size_t)t * B * H, cprev,
                                                                   t ? H : 2 * H, n->len_learn, t, B, n->DG + (size_t)t * B * G4);
         if (t > 0) {
             MatK a{n->DG + (size_t)t * B * G4, B, G4, G4};
             MatM b{pk.Whh_p, H, G4, H};
-            EpiBias<false> e{n->dhrec, nullptr, B, H, H, 1.f};
-            R2D2_CUDA_CHECK((launch_gemm<64, 64, 16>(a, b, e, B, H, G4, 1, s)));
+            EpiPartial e{n->dhrec, B, H};
+            R2D2_CUDA_CHECK((run_gemm<64, 64, 64>(a, b, e, B, H, G4, kRecSplits, s)));
         }
     }
     R2D2_LAUNCH_CHECK();
     {   // recurrent weight gradients over all (t,b) rows
         MatM a{n->DG, G4, (int)TB, G4};
         HprevM bh{ac.Hs, n->hidden, B, (int)TB};
-        R2D2_CUDA_CHECK((wgrad<128, 128>(a, bh, G4, H, (int)TB, 4, R_WHH, n, grads, d_off, 1.f, s)));
+        R2D2_CUDA_CHECK((wgrad<128, 128, 128>(a, bh, G4, H, (int)TB, 4, R_WHH, n, grads, d_off, 1.f, s)));
         MatM bu{ac.U, KU, (int)TB, KU};
-        R2D2_CUDA_CHECK((wgrad<128, 128>(a, bu, G4, KU, (int)TB, 4, R_WIH, n, grads, d_off, 1.f, s)));
+        R2D2_CUDA_CHECK((wgrad<128, 128, 128>(a, bu, G4, KU, (int)TB, 4, R_WIH, n, grads, d_off, 1.f, s)));
         R2D2_CUDA_CHECK(colsum(n->DG, (int)TB, G4, B_LSTM, grads, off[P_BIH], off[P_BHH], A, n->colws, s));
     }
     {   // d latent (ReLU-masked), frame-major
         MatK a{n->DG, (int)TB, G4, G4};
         MatM b{pk.Wih_p, LATENT, G4, KU};
         EpiDLatent e{n->dlat, ac.U, B, T, KU};
-        R2D2_CUDA_CHECK((launch_gemm<128, 128, 16>(a, b, e, (int)TB, LATENT, G4, 1, s)));
+        R2D2_CUDA_CHECK((run_gemm<128, 128, 128>(a, b, e, (int)TB, LATENT, G4, 1, s)));
     }
     // ---- encoder backward
     {
         MatM a{n->dlat, LATENT, NF, LATENT};
         MatM b{ac.act3, FLAT3, NF, FLAT3};
-        R2D2_CUDA_CHECK((wgrad<128, 128>(a, b, LATENT, FLAT3, NF, 2, R_FC, n, grads, d_off, 1.f, s)));
+        R2D2_CUDA_CHECK((wgrad<128, 128, 128>(a, b, LATENT, FLAT3, NF, 2, R_FC, n, grads, d_off, 1.f, s)));
         R2D2_CUDA_CHECK(colsum(n->dlat, NF, LATENT, B_PLAIN, grads, off[P_FCB], 0, A, n->colws, s));
         MatK a2{n->dlat, NF, LATENT, LATENT};
         MatM b2{pk.Wfcp, FLAT3, LATENT, FLAT3};
         EpiMasked e{n->dpre3, ac.act3, NF, FLAT3, FLAT3};
-        R2D2_CUDA_CHECK((launch_gemm<128, 128, 16>(a2, b2, e, NF, FLAT3, LATENT, 1, s)));
+        R2D2_CUDA_CHECK((run_gemm<128, 128, 128>(a2, b2, e, NF, FLAT3, LATENT, 1, s)));
     }
     {   // conv3
         MatM a{n->dpre3, 64, NF * 49, 64};
         ConvNHWC_M<9, 9, 64, 7, 7, 3, 3, 1> b{ac.act2, NF};
-        R2D2_CUDA_CHECK((wgrad<64, 64>(a, b, 64, 576, NF * 49, 48, R_C3, n, grads, d_off, 1.f, s)));
+        R2D2_CUDA_CHECK((wgrad<64, 64, 64>(a, b, 64, 576, NF * 49, 32, R_C3, n, grads, d_off, 1.f, s)));
         R2D2_CUDA_CHECK(colsum(n->dpre3, NF * 49, 64, B_PLAIN, grads, off[P_C3B], 0, A, n->colws, s));
         ConvDgradK<9, 9, 7, 7, 64, 3, 3> a2{n->dpre3, NF};
         MatK b2{pk.W3d, 64, 576, 576};
         EpiMasked e{n->dpre2, ac.act2, NF * 81, 64, 64};
-        R2D2_CUDA_CHECK((launch_gemm<128, 64, 16>(a2, b2, e, NF * 81, 64, 576, 1, s)));
+        R2D2_CUDA_CHECK((run_gemm<128, 64, 64>(a2, b2, e, NF * 81, 64, 576, 1, s)));
     }
     {   // conv2
         MatM a{n->dpre2, 64, NF * 81, 64};
         ConvNHWC_M<20, 20, 32, 9, 9, 4, 4, 2> b{ac.act1, NF};
-        R2D2_CUDA_CHECK((wgrad<64, 64>(a, b, 64, 512, NF * 81, 48, R_C2, n, grads, d_off, 1.f, s)));
+        R2D2_CUDA_CHECK((wgrad<64, 64, 64>(a, b, 64, 512, NF * 81, 36, R_C2, n, grads, d_off, 1.f, s)));
         R2D2_CUDA_CHECK(colsum(n->dpre2, NF * 81, 64, B_PLAIN, grads, off[P_C2B], 0, A, n->colws, s));
         for (int cls = 0; cls < 4; ++cls) {      // stride-2 dgrad as four stride-1 problems (output parity classes)
             ConvDgradK<10, 10, 9, 9, 64, 2, 2> a2{n->dpre2, NF};
             MatK b2{pk.W2d + cls * 32 * 256, 32, 256, 256};
             EpiDgradS2 e{n->dpre1, ac.act1, NF, cls >> 1, cls & 1};
-            R2D2_CUDA_CHECK((launch_gemm<128, 32, 16>(a2, b2, e, NF * 100, 32, 256, 1, s)));
+            R2D2_CUDA_CHECK((run_gemm<128, 32, 32>(a2, b2, e, NF * 100, 32, 256, 1, s)));
         }
     }
     {   // conv1 (weights only; frames need no gradient)
         MatM a{n->dpre1, 32, NF * 400, 32};
         Conv1FrameM b{n->obs, C, NF};
-        R2D2_CUDA_CHECK((wgrad<32, 64>(a, b, 32, C * 64, NF * 400, 148, R_C1, n, grads, d_off, 1.f / 255.f, s)));
+        R2D2_CUDA_CHECK((wgrad<32, 64, 64>(a, b, 32, C * 64, NF * 400, 148, R_C1, n, grads, d_off, 1.f / 255.f, s)));
         R2D2_CUDA_CHECK(colsum(n->dpre1, NF * 400, 32, B_PLAIN, grads, off[P_C1B], 0, A, n->colws, s));
     }
     return R2D2_OK;

@@ -179,9 +179,11 @@ class DeviceLearner:
         """worker.py:345-363: Q passes, TD/loss/priorities, backward.  Results stay on device in
         self.td / self.prio / self.loss_sum / self.rows / self.grads (grads of loss_sum)."""
         self._live = b                                   # keep obs/hidden alive until backward ran
-        self.forward(0, b, self.q, self.qn_online)
-        self.forward(1, b, None, self.qn_target)
         p = _lib.ptr
+        _lib.check(_lib.lib().r2d2_net_forward_pair(self._h, p(self.online.flat), p(self.target.flat), p(b["obs"]),
+                                                    p(b["last_action"]), p(b["last_reward"]), p(b["hidden"]),
+                                                    p(b["burn_in"]), p(b["learning"]), p(b["forward"]), p(self.q),
+                                                    p(self.qn_online), p(self.qn_target), _lib.stream_ptr()))
         _lib.check(_lib.lib().r2d2_td_loss(p(self.q), p(self.qn_online), p(self.qn_target), p(b["action"]),
                                            p(b["n_step_reward"]), p(b["gamma"]), p(b["is_weights"]), p(b["learning"]),
                                            self.B, self.A, p(self.td), p(self.prio), p(self.loss_sum), p(self.rows),

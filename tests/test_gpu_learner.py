@@ -26,6 +26,21 @@ def _diag(line):
         f.write(line + "\n")
 
 
+BACKENDS = {"umma_bf16x3": 1, "ffma_fp32": 0}
+# stage tolerances per GEMM backend: (latent/hidden/q abs, grad rel, adam abs)
+STAGE_TOL = {1: (1e-4, 5e-3, 5e-6), 0: (2e-5, 2e-3, 5e-6)}
+
+
+@pytest.fixture(params=list(BACKENDS))
+def backend(request):
+    from r2d2_b200 import _lib
+    be = BACKENDS[request.param]
+    prev = _lib.lib().r2d2_set_gemm_backend(be)
+    _diag(f"--- backend {request.param}")
+    yield be
+    _lib.lib().r2d2_set_gemm_backend(prev)
+
+
 def _mk_learner(B, T, C=1, Lmax=40, F=5, params=None):
     from r2d2_b200.learner_core import DeviceLearner
     dl = DeviceLearner(A, B, T, in_channels=C, max_learning=Lmax, max_forward=F)
@@ -37,7 +52,7 @@ def _torch_batch(d):
     return {k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v) for k, v in d.items()}
 
 
-def _stage_compare(tag, dl, d, out, fs=5):
+def _stage_compare(tag, dl, d, out, be, fs=5):
     """Compare every stage of one update (already run on dl) against oracle output `out`."""
     B, T = dl.B, dl.T
     rows = int(dl.rows.item())
@@ -68,16 +83,17 @@ def _stage_compare(tag, dl, d, out, fs=5):
     worst.sort(reverse=True)
     for rel, name, err, ref in worst[:6]:
         _diag(f"{tag}:   grad {name}: max abs err {err:.3e} (max |g| {ref:.3e}, rel {rel:.3e})")
-    assert e_lat < 2e-5 and e_h < 2e-5, (e_lat, e_h)
-    assert max(e_q, e_qn, e_qt) < 2e-5
+    tol_act, tol_grad, _ = STAGE_TOL[be]
+    assert e_lat < tol_act and e_h < tol_act, (e_lat, e_h)
+    assert max(e_q, e_qn, e_qt) < tol_act
     assert e_td < 1e-4 and e_pr < 1e-4                      # the north-star bar
     assert abs(loss - out["loss"]) < 1e-5 * max(1.0, abs(out["loss"]))
-    assert worst[0][0] < 2e-3, worst[0]
+    assert worst[0][0] < tol_grad, worst[0]
     assert abs(float(dl.norm.item()) - out["grad_norm"]) <= 1e-3 * out["grad_norm"] if dl.num_updates else True
 
 
 @pytest.mark.parametrize("ragged,B", [(True, 8), (False, 4)])
-def test_single_update_stages_vs_oracle(ragged, B):
+def test_single_update_stages_vs_oracle(ragged, B, backend):
     torch.set_num_threads(min(32, os.cpu_count() or 8))
     params = init_params(A, seed=3)
     d = synth.synthetic_batch(B, A, seed=17, ragged=ragged)
@@ -89,15 +105,15 @@ def test_single_update_stages_vs_oracle(ragged, B):
     dl.pack(1)
     dl.update(dl.prepare(_torch_batch(d)))
     torch.cuda.synchronize()
-    _stage_compare(f"synthetic B={B} ragged={ragged}", dl, d, out)
+    _stage_compare(f"synthetic B={B} ragged={ragged}", dl, d, out, backend)
     # Adam step
     for name, p in st.online.items():
         err = (dl.online.views[name].cpu() - p).abs().max().item()
-        assert err < 5e-6, (name, err)
+        assert err < STAGE_TOL[backend][2], (name, err)
 
 
 @pytest.mark.parametrize("name,script", [("learner_ragged.npz", synth.RAGGED_SCRIPT), ("learner_cfg0.npz", CFG0_SCRIPT)])
-def test_consecutive_updates_vs_reference_golden(golden_dir, name, script):
+def test_consecutive_updates_vs_reference_golden(golden_dir, name, script, backend):
     """K consecutive updates on replay-sampled ragged batches; compared with the outputs of the
     unmodified reference Learner.run recorded in tests/golden (TD, priorities, loss, Q, params)."""
     g = np.load(os.path.join(golden_dir, name))
@@ -122,6 +138,6 @@ def test_consecutive_updates_vs_reference_golden(golden_dir, name, script):
         _diag(f"{name} k={k}: td {e_td:.3e} prio {e_pr:.3e} q {e_q:.3e} qn_on {e_qn:.3e} qn_tg {e_qt:.3e} "
               f"loss {loss:.6f} vs {float(g[f'k{k}_out_loss']):.6f} params {e_p:.3e}")
         assert e_td < 1e-4 and e_pr < 1e-4
-        assert max(e_q, e_qn, e_qt) < 5e-5
+        assert max(e_q, e_qn, e_qt) < (5e-5 if backend == 0 else 1e-4)
         assert abs(loss - float(g[f"k{k}_out_loss"])) < 2e-5 * max(1.0, abs(loss))
         assert e_p < 2e-5
