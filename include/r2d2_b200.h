@@ -142,6 +142,12 @@ int r2d2_set_gemm_backend(int backend);
 int r2d2_debug_gemm(int backend, int ubn, int a_major, int b_major, int M, int N, int K, const float* A, const float* B,
                     float* C, int splits, void* stream);
 
+/* Precision of the v2 (pre-split bf16 hi/lo) data path: 0 = bf16x3 products (parity, default), 1 = plain bf16. */
+int r2d2_set_fast_math(int fast);
+/* Test entry for the v2 kernel: operands as bf16 hi/lo planes; major 1 = [K][rows] storage (MN-major descriptors). */
+int r2d2_debug_gemm2(int ubn, int a_major, int b_major, int M, int N, int K, const void* a_hi, const void* a_lo,
+                     const void* b_hi, const void* b_lo, float* C, int splits, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * K5  clip_grad_norm_(max_norm) + Adam(lr, eps).step()  (worker.py:289,364-365) on the flat
  * buffers.  grad_scale: optional device float multiplied into the gradients first;

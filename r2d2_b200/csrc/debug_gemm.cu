@@ -1,10 +1,15 @@
 // Test entry point: plain-matrix instances of the gather-GEMM on either backend, so the tcgen05
 // path (descriptors, swizzle, pipeline, TMEM epilogue) can be validated against the fp32 FFMA path
 // and a host reference independently of the network.
-#include "dispatch.cuh"
+#include "umma2.cuh"
+
+namespace r2d2 {
+enum GemmBackend { GEMM_FFMA = 0, GEMM_UMMA_BF16X3 = 1, GEMM_UMMA_BF16 = 2 };
+}
 
 namespace r2d2 {
 int g_gemm_backend = GEMM_UMMA_BF16X3;
+int g_fast_math = 0;
 
 template <class AL, class BL>
 static cudaError_t debug_run(int backend, int ubn, const AL& a, const BL& b, float* C, int M, int N, int K, int splits,
@@ -39,6 +44,44 @@ int r2d2_set_gemm_backend(int backend) {
     int prev = g_gemm_backend;
     if (backend >= 0 && backend <= 2) g_gemm_backend = backend;
     return prev;
+}
+
+/* v2 data path precision: 0 = bf16x3 split products (parity mode, default), 1 = plain bf16 (fast mode). */
+int r2d2_set_fast_math(int fast) {
+    int prev = g_fast_math;
+    g_fast_math = fast ? 1 : 0;
+    return prev;
+}
+
+/* v2 test entry: operands given as bf16 hi/lo planes.  a_major/b_major as in r2d2_debug_gemm (1 = [K][rows]
+ * storage, fed through MN-major descriptors).  C fp32 [splits][M][N]. */
+int r2d2_debug_gemm2(int ubn, int a_major, int b_major, int M, int N, int K, const void* a_hi, const void* a_lo,
+                     const void* b_hi, const void* b_lo, float* C, int splits, void* stream) {
+    R2D2_REQUIRE(a_hi && a_lo && b_hi && b_lo && C && M > 0 && N > 0 && K > 0 && splits >= 1, "bad arguments");
+    R2D2_REQUIRE(N % 8 == 0 && (a_major == 0 ? K % 8 == 0 : M % 8 == 0) && (b_major == 0 ? K % 8 == 0 : N % 8 == 0), "alignment");
+    cudaStream_t s = as_stream(stream);
+    const bf16 *ah = (const bf16*)a_hi, *al = (const bf16*)a_lo, *bh = (const bf16*)b_hi, *bl = (const bf16*)b_lo;
+    Epi2Partial ep{C, M, N};
+    cudaError_t e = cudaErrorInvalidValue;
+#define R2D2_DBG2(UBN, AS, BS) e = launch_umma2<UBN>(AS, BS, ep, M, N, K, splits, s)
+#define R2D2_DBG2_ALL(UBN)                                                                                      \
+    if (a_major == 0 && b_major == 0) R2D2_DBG2(UBN, (SrcMatK{ah, al, M, K, K}), (SrcMatK{bh, bl, N, K, K}));     \
+    else if (a_major == 1 && b_major == 0) R2D2_DBG2(UBN, (SrcMatMN{ah, al, M, K, M}), (SrcMatK{bh, bl, N, K, K}));
+#define R2D2_DBG2_MNB(UBN)                                                                                      \
+    if (a_major == 0 && b_major == 1) R2D2_DBG2(UBN, (SrcMatK{ah, al, M, K, K}), (SrcMatMN{bh, bl, N, K, N}));    \
+    else if (a_major == 1 && b_major == 1) R2D2_DBG2(UBN, (SrcMatMN{ah, al, M, K, M}), (SrcMatMN{bh, bl, N, K, N}));
+    switch (ubn) {
+        case 16: R2D2_DBG2_ALL(16) break;
+        case 32: R2D2_DBG2_ALL(32) break;
+        case 64: R2D2_DBG2_ALL(64) R2D2_DBG2_MNB(64) break;
+        case 128: R2D2_DBG2_ALL(128) R2D2_DBG2_MNB(128) break;
+        default: R2D2_DBG2_ALL(256) R2D2_DBG2_MNB(256) break;
+    }
+#undef R2D2_DBG2
+#undef R2D2_DBG2_ALL
+#undef R2D2_DBG2_MNB
+    R2D2_CUDA_CHECK(e);
+    return R2D2_OK;
 }
 
 /* C[M][N] = A x B^T for plain fp32 matrices.  a_major/b_major: 0 = K-major ([rows][K]), 1 = transposed

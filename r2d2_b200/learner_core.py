@@ -209,6 +209,12 @@ class DeviceLearner:
         self.apply_gradients()
 
     # ------------------------------------------------------------------ debug
+    def debug_split(self, which: int, name: str, numel: int) -> torch.Tensor:
+        """fp32 value (hi + lo) of a split bf16 tensor of the workspace."""
+        hi = self.debug_tensor(which, name + ".hi", numel, torch.bfloat16)
+        lo = self.debug_tensor(which, name + ".lo", numel, torch.bfloat16)
+        return hi.float() + lo.float()
+
     def debug_tensor(self, which: int, name: str, numel: int, dtype=torch.float32) -> torch.Tensor:
         from .priority_tree import _from_device_ptr
         addr = _lib.lib().r2d2_net_debug_ptr(self._h, which, name.encode())

@@ -105,5 +105,6 @@ class _CudaArrayView:
 
 def _from_device_ptr(addr: int, numel: int, dtype: torch.dtype, device) -> torch.Tensor:
     typestr = {torch.float64: "<f8", torch.float32: "<f4", torch.int64: "<i8", torch.int32: "<i4",
-               torch.uint8: "|u1"}[dtype]
-    return torch.as_tensor(_CudaArrayView(addr, 0, typestr, (int(numel),)), device=device)
+               torch.uint8: "|u1", torch.bfloat16: "<i2"}[dtype]
+    t = torch.as_tensor(_CudaArrayView(addr, 0, typestr, (int(numel),)), device=device)
+    return t.view(torch.bfloat16) if dtype == torch.bfloat16 else t

@@ -26,19 +26,21 @@ def _diag(line):
         f.write(line + "\n")
 
 
-BACKENDS = {"umma_bf16x3": 1, "ffma_fp32": 0}
-# stage tolerances per GEMM backend: (latent/hidden/q abs, grad rel, adam abs)
-STAGE_TOL = {1: (1e-4, 5e-3, 5e-6), 0: (2e-5, 2e-3, 5e-6)}
+BACKENDS = {"bf16x3_parity": 0, "bf16_fast": 1}
+# stage tolerances per precision mode: (latent/hidden/q abs, grad rel, adam abs, td/prio abs)
+# parity mode carries the north-star bar (TD, priorities within 1e-4); fast mode (plain bf16 products) is
+# reported and only sanity-bounded.
+STAGE_TOL = {0: (1e-4, 5e-3, 5e-6, 1e-4), 1: (5e-2, 2e-1, 2.1e-4, 5e-2)}
 
 
 @pytest.fixture(params=list(BACKENDS))
 def backend(request):
     from r2d2_b200 import _lib
     be = BACKENDS[request.param]
-    prev = _lib.lib().r2d2_set_gemm_backend(be)
-    _diag(f"--- backend {request.param}")
+    prev = _lib.lib().r2d2_set_fast_math(be)
+    _diag(f"--- mode {request.param}")
     yield be
-    _lib.lib().r2d2_set_gemm_backend(prev)
+    _lib.lib().r2d2_set_fast_math(prev)
 
 
 def _mk_learner(B, T, C=1, Lmax=40, F=5, params=None):
@@ -58,11 +60,11 @@ def _stage_compare(tag, dl, d, out, be, fs=5):
     rows = int(dl.rows.item())
     assert rows == out["td"].shape[0]
     KU = dl.KU
-    U = dl.debug_tensor(0, "U", T * B * KU).view(T, B, KU).cpu()
+    U = dl.debug_split(0, "U", T * B * KU).view(T, B, KU).cpu()
     lat = U[:, :, :512].permute(1, 0, 2)                       # (B,T,512)
     Tb = out["latent"].shape[1]
     e_lat = (lat[:, :Tb] - out["latent"]).abs().max().item()
-    Hs = dl.debug_tensor(0, "Hs", T * B * 512).view(T, B, 512).cpu().permute(1, 0, 2)
+    Hs = dl.debug_split(0, "Hs", T * B * 512).view(T, B, 512).cpu().permute(1, 0, 2)
     ln = (torch.from_numpy(d["burn_in"].astype(np.int64)) + torch.from_numpy(d["learning"].astype(np.int64)))
     mask = (torch.arange(Tb)[None, :] < ln[:, None])
     e_h = ((Hs[:, :Tb] - out["hidden"]).abs() * mask[..., None]).max().item()
@@ -83,13 +85,13 @@ def _stage_compare(tag, dl, d, out, be, fs=5):
     worst.sort(reverse=True)
     for rel, name, err, ref in worst[:6]:
         _diag(f"{tag}:   grad {name}: max abs err {err:.3e} (max |g| {ref:.3e}, rel {rel:.3e})")
-    tol_act, tol_grad, _ = STAGE_TOL[be]
+    tol_act, tol_grad, _, tol_td = STAGE_TOL[be]
     assert e_lat < tol_act and e_h < tol_act, (e_lat, e_h)
     assert max(e_q, e_qn, e_qt) < tol_act
-    assert e_td < 1e-4 and e_pr < 1e-4                      # the north-star bar
-    assert abs(loss - out["loss"]) < 1e-5 * max(1.0, abs(out["loss"]))
+    assert e_td < tol_td and e_pr < tol_td                  # parity mode: the north-star bar (1e-4)
+    assert abs(loss - out["loss"]) < (1e-5 if be == 0 else 1e-2) * max(1.0, abs(out["loss"]))
     assert worst[0][0] < tol_grad, worst[0]
-    assert abs(float(dl.norm.item()) - out["grad_norm"]) <= 1e-3 * out["grad_norm"] if dl.num_updates else True
+    assert abs(float(dl.norm.item()) - out["grad_norm"]) <= (1e-3 if be == 0 else 1e-1) * out["grad_norm"]
 
 
 @pytest.mark.parametrize("ragged,B", [(True, 8), (False, 4)])
@@ -137,7 +139,8 @@ def test_consecutive_updates_vs_reference_golden(golden_dir, name, script, backe
                   for n in dl.online.views)
         _diag(f"{name} k={k}: td {e_td:.3e} prio {e_pr:.3e} q {e_q:.3e} qn_on {e_qn:.3e} qn_tg {e_qt:.3e} "
               f"loss {loss:.6f} vs {float(g[f'k{k}_out_loss']):.6f} params {e_p:.3e}")
-        assert e_td < 1e-4 and e_pr < 1e-4
-        assert max(e_q, e_qn, e_qt) < (5e-5 if backend == 0 else 1e-4)
-        assert abs(loss - float(g[f"k{k}_out_loss"])) < 2e-5 * max(1.0, abs(loss))
-        assert e_p < 2e-5
+        tol_act, _, tol_p, tol_td = STAGE_TOL[backend]
+        assert e_td < tol_td and e_pr < tol_td
+        assert max(e_q, e_qn, e_qt) < tol_act
+        assert abs(loss - float(g[f"k{k}_out_loss"])) < (2e-5 if backend == 0 else 2e-2) * max(1.0, abs(loss))
+        assert e_p < max(2e-5, tol_p)
