@@ -1,0 +1,8 @@
+"""Drop-in alias: with this directory on PYTHONPATH the reference's train.py (`import config` /
+`from config import ...`) binds the B200 implementation -- this name IS r2d2_b200.config, so run-time edits
+such as `config.training_steps = N` reach the workers exactly as they do upstream."""
+import sys
+
+import r2d2_b200.config as _impl
+
+sys.modules[__name__] = _impl

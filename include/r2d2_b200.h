@@ -132,6 +132,30 @@ int r2d2_net_backward(r2d2_net* n, const float* params, const float* dq, float* 
 /* Test/debug access to device intermediates (see net.cu for the names). */
 void* r2d2_net_debug_ptr(r2d2_net* n, int which, const char* name);
 
+/* ------------------------------------------------------------------------------------------
+ * K4  HBM-resident replay block store  <->  ReplayBuffer.add / sample_batch storage halves
+ * (worker.py:141-161, 163-240) and the Block wire format (worker.py:23-35).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct r2d2_replay r2d2_replay;
+
+/* Ring of num_blocks slots (worker.py:43-48,70); each slot holds one packed Block at fixed byte offsets. */
+int r2d2_replay_create(int num_blocks, int block_len, int burn_in, int learning, int forward, int C, int action_dim, int H,
+                       r2d2_replay** out);
+int r2d2_replay_destroy(r2d2_replay* r);
+/* offsets_out[12] (bytes inside a slot): obs, last_action, last_reward, action, n_step_reward, gamma, hidden,
+ * burn, learn, fwd, num_seq, total.  Array shapes: obs u8 [burn_in+block_len+1][C][84][84]; last_action u8
+ * [frames][A] (one-hot); last_reward f32 [frames]; action u8 [block_len]; n_step_reward, gamma f32 [block_len];
+ * hidden f32 [block_len/learning][2][H]; burn/learn/fwd u8 [block_len/learning]; num_seq i32. */
+int r2d2_replay_layout(const r2d2_replay* r, int64_t* offsets_out);
+/* ReplayBuffer.add, storage half (worker.py:154): async H2D copy of one packed block from PINNED host memory. */
+int r2d2_replay_ingest(r2d2_replay* r, int block_idx, const void* host_blob, int64_t nbytes, void* stream);
+/* ReplayBuffer.sample_batch, slicing half (worker.py:172-238), for B sampled slots idx (device int64) with their
+ * IS weights isw (device f32).  Outputs are the device-side 14-tuple fields (see r2d2_net_forward for layouts);
+ * is_weights_rows holds each sequence's weight repeated over its learning steps (worker.py:216); rows_out i32[1]. */
+int r2d2_replay_gather(r2d2_replay* r, const int64_t* idx, const float* isw, int B, int T, uint8_t* obs, uint8_t* last_action,
+                       float* last_reward, float* hidden, uint8_t* action, float* n_step_reward, float* gamma, uint8_t* burn,
+                       uint8_t* learn, uint8_t* fwd, float* is_weights_rows, int32_t* rows_out, void* stream);
+
 /* GEMM backend of every contraction in K1/K1b: 0 = fp32 CUDA-core FFMA (on-device numerical
  * reference), 1 = tcgen05 bf16x3 split (hi*hi + hi*lo + lo*hi, fp32 accumulate in TMEM: parity mode,
  * default), 2 = tcgen05 plain bf16 (fast mode).  Process-wide; returns the previous value. */

@@ -74,7 +74,7 @@ def test_umma2_split_operands_matches_fp64(M, N, K):
         for ubn in (16, 32, 64, 128, 256):
             if bm == 1 and (ubn < 64):
                 continue
-            for fast, tol in ((0, 3e-5), (1, 2e-2)):
+            for fast, tol in ((0, 3e-5 if K < 8192 else 1e-4), (1, 2e-2)):
                 for splits in ((1, 3) if K >= 512 else (1,)):
                     prev = _lib.lib().r2d2_set_fast_math(fast)
                     C = torch.full((splits, M, N), float("nan"), device="cuda")

@@ -1,0 +1,97 @@
+"""The public worker / model surface on the GPU: Learner.update_from_batch on reference-format 14-tuples,
+Network.calculate_q_/calculate_q, and the HBM-replay learner loop."""
+import os
+import queue
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import synth
+from oracle.learner import init_params
+from helpers import build_oracle_replay, sample_with_seed, A
+
+pytestmark = pytest.mark.gpu
+
+
+def _tuple14(d):
+    t = torch.from_numpy
+    return (t(d["obs"]), t(d["last_action"]), t(d["last_reward"]), t(np.ascontiguousarray(d["hidden"])).transpose(0, 1),
+            t(d["action"]).unsqueeze(1), t(d["n_step_reward"]), t(d["gamma"]), t(d["burn_in"]), t(d["learning"]), t(d["forward"]),
+            d["idxes"], t(d["is_weights"]), d["old_ptr"], np.int32(d["env_steps"]))
+
+
+def _network(params):
+    from r2d2_b200.model import Network
+    net = Network(A)
+    net.load_state_dict(params)
+    return net
+
+
+def test_learner_api_on_reference_tuples_matches_golden(golden_dir, monkeypatch):
+    from r2d2_b200 import config
+    from r2d2_b200.worker import Learner
+    g = np.load(os.path.join(golden_dir, "learner_ragged.npz"))
+    batch_size, K, bl, ls, bi, fs, seed0, num_blocks = (int(x) for x in g["meta"])
+    monkeypatch.setattr(config, "batch_size", batch_size)
+    rb, _ = build_oracle_replay(synth.RAGGED_SCRIPT, num_blocks, batch_size)
+    model = _network(init_params(A, seed=3))
+    pq = queue.Queue()
+    learner = Learner(queue.Queue(), pq, model)
+    learner._start_time = 0.0
+    for k in range(K):
+        idxes, prio, old_ptr, loss = learner.update_from_batch(_tuple14(sample_with_seed(rb, seed0 + k)))
+        np.testing.assert_array_equal(idxes, g[f"k{k}_out_idxes"])
+        np.testing.assert_allclose(prio, g[f"k{k}_out_priorities"], atol=1e-4, rtol=0)        # north-star bar
+        assert abs(loss - float(g[f"k{k}_out_loss"])) < 2e-5
+        assert prio.dtype == np.float32 and isinstance(loss, float)
+    assert learner.num_updates == K
+    sd = learner.state_dict()
+    for n in sd:
+        np.testing.assert_allclose(sd[n].flatten()[:16].cpu().numpy(), g[f"k{K-1}_phead_{n}"], atol=2e-5, rtol=0)
+
+
+def test_network_calculate_q_surface(golden_dir):
+    g = np.load(os.path.join(golden_dir, "learner_ragged.npz"))
+    batch_size, K, bl, ls, bi, fs, seed0, num_blocks = (int(x) for x in g["meta"])
+    rb, _ = build_oracle_replay(synth.RAGGED_SCRIPT, num_blocks, batch_size)
+    d = sample_with_seed(rb, seed0)
+    net = _network(init_params(A, seed=3)).cuda()
+    t = lambda x: torch.from_numpy(x).cuda()
+    obs = t(d["obs"]).float() / 255                                   # what worker.py:336,342 hands to the network
+    hid = t(np.ascontiguousarray(d["hidden"])).transpose(0, 1)
+    hidden_state = (hid[:1], hid[1:])
+    args = (obs, t(d["last_action"]).float(), t(d["last_reward"]), hidden_state, t(d["burn_in"]), t(d["learning"]))
+    q_shift = net.calculate_q_(*args, t(d["forward"]))
+    q = net.calculate_q(*args)
+    np.testing.assert_allclose(q_shift.cpu().numpy(), g["k0_out_qn_online"], atol=1e-4, rtol=0)
+    np.testing.assert_allclose(q.cpu().numpy(), g["k0_out_q"], atol=1e-4, rtol=0)
+
+
+def test_learner_loop_on_hbm_replay(monkeypatch):
+    """Blocks in -> HBM replay -> sample/update/priority-update entirely on the device, through Learner.run."""
+    from r2d2_b200 import config
+    from r2d2_b200.worker import BLOCK_MSG, STATS_MSG, Learner, LocalBuffer
+    monkeypatch.setattr(config, "batch_size", 8)
+    monkeypatch.setattr(config, "buffer_capacity", 8 * 400)
+    monkeypatch.setattr(config, "learning_starts", 400)
+    monkeypatch.setattr(config, "training_steps", 6)
+    bq, pq = queue.Queue(), queue.Queue()
+    model = _network(init_params(A, seed=5))
+    model.share_memory()
+    before = {k: v.clone() for k, v in model.state_dict().items()}
+    learner = Learner(bq, pq, model, save_interval=10 ** 9)
+    for seed, steps, done in synth.RAGGED_SCRIPT:
+        lb = LocalBuffer(A)
+        for blk, prio, ep in synth.drive_actor(lb, seed, steps, done, A):
+            bq.put((BLOCK_MSG, blk, prio, ep))
+    learner.run()
+    assert learner.num_updates == 6 and len(learner.replay) > 400
+    msg = None
+    while not pq.empty():
+        msg = pq.get()
+    assert msg[0] == STATS_MSG and msg[1] == 6 and np.isfinite(msg[2])
+    changed = sum(float((model.state_dict()[k] - before[k]).abs().sum()) for k in before)
+    assert changed > 0                                               # weights were published to the shared model (every 4 updates)
+    leaves = learner.replay.tree.ptree[learner.replay.tree.num_nodes // 2:]
+    assert np.isfinite(leaves).all() and (leaves >= 0).all()
