@@ -1,13 +1,18 @@
 #!/usr/bin/env python
 """Learner throughput benchmark (BASELINE.json metric: learner sequences/sec).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--channels C] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--channels C] [--fast] [--impl reference]
 
-One "step" = one learner update of one batch of 64 synthetic replay sequences
-(b/l/f = 40/40/5 -> 85 frames of C x 84 x 84 each): unroll(online) + unroll(target)
--> fused TD -> BPTT -> [NCCL gradient all-reduce] -> clip+Adam -> priority update.
-Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for the
-definition of every field.
+One "step" = one learner update on one batch of 64 replay sequences (b/l/f = 40/40/5 -> 85 frames
+of C x 84 x 84 u8 each):
+
+  value  : HBM-resident pipeline   K3 sample -> K4 gather -> K1 unroll(online+target) -> K2 TD ->
+           K1b BPTT -> [NCCL all-reduce] -> K5 clip+Adam -> K3 priority update      (worker.Learner.update_from_replay)
+  e2e    : the same update through the reference-facing call with HOST buffers: a 14-tuple in pinned host
+           memory (worker.py:219-238) -> H2D -> update -> priorities + loss back to the host
+           (worker.Learner.update_from_batch)
+
+Prints ONE JSON line (rank 0).  DESIGN.md "Measurement" defines every field.
 """
 from __future__ import annotations
 
@@ -29,7 +34,9 @@ A = 9                      # MsPacman action count (train.py:22 takes it from th
 B = 64                     # config.batch_size
 BURN, LEARN, FWD = 40, 40, 5
 T = BURN + LEARN + FWD
-TREE_CAPACITY = 1 << 20    # BASELINE config #3
+BLOCK_LEN = 400
+TREE_CAPACITY = 1 << 20    # BASELINE config #3: sum tree over 2^20 sequence slots
+NUM_BLOCKS = 128           # frame store: 128 blocks x 441 frames (1.6 GB at C=4), far larger than L2
 
 
 def flops_per_sequence(C: int) -> float:
@@ -38,7 +45,7 @@ def flops_per_sequence(C: int) -> float:
     lstm = 2 * 4 * 512 * (512 + A + 1 + 512)
     head = 2 * (2 * 512 * 512 + 512 * A + 512)
     fwd = 2 * (T * enc + T * lstm) + 3 * LEARN * head
-    enc_b = 2 * (2 * (2_654_208 + 1_806_336 + 1_605_632) + 819_200 * C) - 2 * 0   # dgrad+wgrad, no conv1 dgrad
+    enc_b = 2 * (2 * (2_654_208 + 1_806_336 + 1_605_632) + 819_200 * C)       # dgrad+wgrad, no conv1 dgrad
     bwd = (BURN + LEARN) * (enc_b + 2 * lstm) + LEARN * 2 * head
     return float(fwd + bwd)
 
@@ -68,75 +75,106 @@ class ClockSampler(threading.Thread):
                 self.samples.append([x.strip() for x in out.strip().split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.1)
 
     def summary(self):
-        sm = [float(s[0]) for s in self.samples if len(s) >= 6 and s[0].replace(".", "").isdigit()]
+        ok = [s for s in self.samples if len(s) >= 6]
+        sm = [float(s[0]) for s in ok if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in ok if s[1].replace(".", "").isdigit()]
         reasons = set()
-        for s in self.samples:
-            if len(s) >= 6:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        mx = [float(s[1]) for s in self.samples if len(s) >= 6 and s[1].replace(".", "").isdigit()]
+        for s in ok:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def host_batches(n: int, C: int, seed0: int = 0):
-    from oracle import synth          # bench-only use of the synthetic generator (inputs, not compute)
-    return [synth.synthetic_batch(B, A, BURN, LEARN, FWD, channels=C, seed=seed0 + i) for i in range(n)]
-
-
-def to_pinned(d):
-    out = {}
-    for k, v in d.items():
-        if isinstance(v, np.ndarray):
-            t = torch.from_numpy(v)
-            out[k] = t.pin_memory() if t.numel() else t
-        else:
-            out[k] = v
+def synthetic_blocks(n: int, C: int, seed: int):
+    """n full actor blocks (400 steps, 10 sequences) with SURVEY 8(d) distributions, built directly as arrays."""
+    from r2d2_b200.worker import Block
+    rng = np.random.default_rng(seed)
+    frames = BURN + BLOCK_LEN + 1
+    out = []
+    for _ in range(n):
+        la = np.zeros((frames, A), dtype=bool)
+        la[np.arange(frames), rng.integers(0, A, frames)] = True
+        spb = BLOCK_LEN // LEARN
+        fwd = np.full(spb, FWD, dtype=np.uint8)
+        fwd[-1] = 1
+        blk = Block(obs=rng.integers(0, 256, size=(frames, C, 84, 84), dtype=np.uint8), last_action=la,
+                    last_reward=rng.integers(0, 2, frames).astype(np.float32),
+                    action=rng.integers(0, A, BLOCK_LEN).astype(np.uint8),
+                    n_step_reward=rng.uniform(0, 3, BLOCK_LEN).astype(np.float32),
+                    gamma=np.full(BLOCK_LEN, 0.997 ** FWD, dtype=np.float32),
+                    hidden=(0.1 * rng.standard_normal((spb, 2, 512))).astype(np.float32), num_sequences=spb,
+                    burn_in_steps=np.full(spb, BURN, dtype=np.uint8), learning_steps=np.full(spb, LEARN, dtype=np.uint8),
+                    forward_steps=fwd)
+        out.append((blk, rng.uniform(0.1, 1.0, spb).astype(np.float32)))
     return out
 
 
-# ----------------------------------------------------------------------------------------------- reference arm
-def run_reference(args):
-    """The reference's own CPU implementation of the path, timed on the host cores: the oracle
-    port (oracle/learner.py -- a torch-CPU restatement with the reference's three-pass structure;
-    the reference itself cannot travel to the GPU box).  Rank 0 only."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def host_tuple(C: int, seed: int, pinned: bool):
+    """A reference-format 14-tuple (worker.py:219-238) of host tensors."""
+    from oracle import synth            # input generator only (seeded NumPy), no compute
+    d = synth.synthetic_batch(B, A, BURN, LEARN, FWD, channels=C, seed=seed)
+    t = lambda a: (torch.from_numpy(a).pin_memory() if pinned else torch.from_numpy(a))
+    return (t(d["obs"]), t(d["last_action"]), t(d["last_reward"]), t(np.ascontiguousarray(d["hidden"])),
+            t(d["action"]).unsqueeze(1), t(d["n_step_reward"]), t(d["gamma"]), t(d["burn_in"]), t(d["learning"]), t(d["forward"]),
+            d["idxes"], t(d["is_weights"]), 0, np.int32(0)), d
+
+
+# ----------------------------------------------------------------------------------------------- CPU reference arm
+def cpu_learner_rate(C: int, steps: int, sample_B: int):
+    """Time the oracle port of the reference learner (oracle/learner.py: torch-CPU fp32, the reference's three-pass
+    structure and packed nn.LSTM op) on a bounded sample of `sample_B` sequences per update."""
+    import oracle.learner as ol
     from oracle import synth
     from oracle.learner import LearnerState, init_params, learner_update
+    ol.LSTM_MODE = "packed"
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    C = args.channels
     params = init_params(A, in_channels=C, seed=0)
     st = LearnerState(online={k: v.clone() for k, v in params.items()}, target={k: v.clone() for k, v in params.items()})
-    batches = [synth.to_torch_batch(b) for b in host_batches(2, C)]
-    for w in range(max(1, min(args.warmup, 1))):
-        learner_update(st, batches[w % 2])
-    steps = max(1, min(args.steps, 3))
+    batches = [synth.to_torch_batch(synth.synthetic_batch(sample_B, A, BURN, LEARN, FWD, channels=C, seed=s)) for s in (0, 1)]
+    best = None
+    for threads in sorted({min(cores, n) for n in (8, 16, 32, 64)}):       # pick the thread count the port runs best at
+        torch.set_num_threads(threads)
+        learner_update(st, batches[0])
+        t0 = time.perf_counter()
+        learner_update(st, batches[1])
+        dt = time.perf_counter() - t0
+        if best is None or dt < best[1]:
+            best = (threads, dt)
+    torch.set_num_threads(best[0])
     t0 = time.perf_counter()
     for k in range(steps):
         learner_update(st, batches[k % 2])
     dt = (time.perf_counter() - t0) / steps
-    val = B / dt
+    return sample_B / dt, dt, best[0], cores
+
+
+def run_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    C = args.channels
+    sample_B = 16
+    steps = max(1, min(args.steps, 5))
+    val, dt, threads, cores = cpu_learner_rate(C, steps, sample_B)
     line = {"impl": "reference", "metric": "learner sequences/sec", "value": val, "unit": "sequences/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"configs[1]: batch {B}, b/l/f {BURN}/{LEARN}/{FWD}, {C}x84x84 u8 frames, A={A}", "channels": C},
-            "cpu_baseline": {"value": val, "unit": "sequences/s", "cores": cores, "kind": "port",
-                             "sample": f"{steps} full updates of batch {B} after 1 warm-up (oracle/learner.py, torch CPU fp32, {cores} threads)"},
+            "config": {"workload": f"configs[1]: learner update, b/l/f {BURN}/{LEARN}/{FWD} (T={T}), {C}x84x84 u8 frames, A={A}",
+                       "channels": C},
+            "cpu_baseline": {"value": val, "unit": "sequences/s", "cores": threads, "kind": "port",
+                             "sample": f"{steps} full updates of a {sample_B}-sequence sample of the batch-{B} workload after warm-up "
+                                       f"(oracle/learner.py, torch CPU fp32, {threads} of {cores} host threads: fastest of 8/16/32/64)"},
             "e2e": {"value": val, "unit": "sequences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 # ----------------------------------------------------------------------------------------------- our arm
 def count_kernels(fn):
-    """Count kernels launched by one call of fn (CUPTI via torch.profiler), split ours/others."""
-    from torch.profiler import profile, ProfilerActivity
+    from torch.profiler import ProfilerActivity, profile
     torch.cuda.synchronize()
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         fn()
@@ -153,60 +191,47 @@ def count_kernels(fn):
 
 def run_ours(args):
     import torch.distributed as dist
-    from r2d2_b200.learner_core import DeviceLearner
-    from r2d2_b200.priority_tree import PriorityTree
-    from oracle.learner import init_params     # seeded init only (numpy RNG), no compute
+    from r2d2_b200 import _lib, config
+    from r2d2_b200 import dist as r2dist
+    from r2d2_b200.model import Network
+    from r2d2_b200.replay import DeviceReplay
+    from r2d2_b200.worker import Learner
+    from oracle.learner import init_params     # seeded NumPy initialiser only
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    rank, world, local = r2dist.init_from_env("nccl")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     C = args.channels
+    config.obs_shape = (C, 84, 84)
+    _lib.lib().r2d2_set_fast_math(1 if args.fast else 0)
 
-    dl = DeviceLearner(A, B, T, in_channels=C, max_learning=LEARN, max_forward=FWD, device=dev)
-    dl.load_state_dict(init_params(A, in_channels=C, seed=0))
-    tree = PriorityTree(TREE_CAPACITY, 0.9, 0.6, device=dev, seed=rank)
-    tree.update_device(torch.arange(TREE_CAPACITY, device=dev),
-                       torch.rand(TREE_CAPACITY, device=dev) + 1e-3)
-
+    model = Network(A, obs_shape=(C, 84, 84))
+    model.load_state_dict(init_params(A, in_channels=C, seed=0))
+    learner = Learner(None, None, model, save_interval=10 ** 9, device=dev)
+    learner._start_time = time.time()
+    learner.store_weights = lambda: None          # weight publication to CPU actors is off the measured path
     if world > 1:
-        rows_g = torch.zeros(1, device=dev)
+        r2dist.broadcast_parameters(learner.core)
+        learner.core.grad_hook = r2dist.make_grad_hook()
 
-        def hook(l):
-            # data-parallel exchange: SUM of d(loss_sum) and of the row counts, then one global mean
-            dist.all_reduce(l.grads.flat)
-            rows_g.copy_(l.rows)
-            dist.all_reduce(rows_g)
-            torch.reciprocal(rows_g, out=l.grad_scale)
-        dl.grad_hook = hook
+    # HBM replay shard of this rank: NUM_BLOCKS blocks, tree over 2^20 slots
+    replay = DeviceReplay(NUM_BLOCKS * BLOCK_LEN, BLOCK_LEN, BURN, LEARN, FWD, A, (C, 84, 84), 512, 0.9, 0.6, B, device=dev,
+                          seed=rank, tree_capacity=TREE_CAPACITY)
+    distinct = synthetic_blocks(16, C, seed=1000 + rank)
+    for i in range(NUM_BLOCKS):
+        blk, prio = distinct[i % len(distinct)]
+        replay.add(blk, prio, None)
+    learner.replay = replay
+    torch.cuda.synchronize()
 
-    nres = 4
-    hb = host_batches(nres, C, seed0=100 * rank)
-    resident = [dl.prepare({k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v) for k, v in b.items()}) for b in hb]
-    pinned = [to_pinned(b) for b in hb]
-    in_bytes = sum(v.numel() * v.element_size() for v in resident[0].values() if isinstance(v, torch.Tensor))
-    idx_res = [torch.randint(0, TREE_CAPACITY, (B,), device=dev) for _ in range(nres)]
+    tuples = [host_tuple(C, 100 * rank + i, pinned=True)[0] for i in range(3)]
+    in_bytes = sum(v.numel() * v.element_size() for v in tuples[0] if isinstance(v, torch.Tensor))
 
     def step_resident(i):
-        b = resident[i % nres]
-        idx, isw = tree.sample_device(B)            # K3 sample (indices drive the priority update below)
-        dl.update(b)
-        tree.update_device(idx, dl.prio)            # K3 update with the new priorities
-
-    prio_host = torch.empty(B, dtype=torch.float32).pin_memory()
-    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+        learner.update_from_replay()
 
     def step_e2e(i):
-        hbk = pinned[i % nres]
-        b = dl.prepare(hbk)                          # H2D of the 14-tuple payload from pinned host memory
-        dl.update(b)
-        prio_host.copy_(dl.prio, non_blocking=True)  # worker.py:357,369: priorities + loss back to the host
-        loss_host.copy_(dl.loss_sum, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return float(loss_host[0])
+        learner.update_from_batch(tuples[i % len(tuples)])     # H2D + update + D2H (synchronises on the result, like worker.py:357)
 
     def timed(fn, steps, warmup):
         for w in range(warmup):
@@ -233,13 +258,15 @@ def run_ours(args):
     ms_e2e = timed(step_e2e, args.steps, args.warmup)
     sampler.stop_flag = True
 
-    # unroll-only timing (K1 fwd x2 + K1b bwd) on the launching stream for the roofline
-    b0 = resident[0]
-    def unroll_only(i):
-        dl.forward(0, b0, dl.q, dl.qn_online)
-        dl.forward(1, b0, None, dl.qn_target)
-        dl.backward(dl.dq)
-    ms_unroll = timed(unroll_only, max(3, args.steps // 2), 2) if world == 1 else None
+    ms_unroll = None
+    if world == 1:                                 # K1 + K1b only, on the launching stream, for the roofline
+        core = learner.core
+        b0 = replay.batch
+
+        def unroll_only(i):
+            core.compute_forward(b0)
+            core.backward(core.dq)
+        ms_unroll = timed(unroll_only, max(5, args.steps // 2), 3)
 
     if rank == 0:
         ours, other = count_kernels(lambda: step_resident(0))
@@ -248,45 +275,32 @@ def run_ours(args):
         e2e = world * B / (ms_e2e * 1e-3)
         line = {"metric": "learner sequences/sec", "value": value, "unit": "sequences/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"configs[1]: 1xB200 learner, batch {B}/GPU, b/l/f {BURN}/{LEARN}/{FWD} (T={T}), "
-                                       f"{C}x84x84 u8 frames, A={A}, sum tree 2^20", "channels": C, "global_batch": world * B,
-                           "parallelism": f"dp{world}", "l2": f"inputs larger than L2: {nres} rotating resident batches "
-                                                              f"({nres * in_bytes / 1e6:.0f} MB) + ~1 GB of streamed activations per step"},
+                "dtype": "bf16 (plain products, fp32 accumulate)" if args.fast else "bf16x3 split products (fp32-equivalent, fp32 accumulate)",
+                "data": "synthetic",
+                "config": {"workload": f"configs[1]: 1xB200 learner per rank, batch {B}/GPU, b/l/f {BURN}/{LEARN}/{FWD} (T={T}), "
+                                       f"{C}x84x84 u8 frames, A={A}, HBM replay of {NUM_BLOCKS} blocks, sum tree 2^20",
+                           "channels": C, "global_batch": world * B, "parallelism": f"dp{world}",
+                           "l2": f"inputs larger than L2: batches are gathered from a {NUM_BLOCKS * replay.blob_bytes / 1e9:.1f} GB HBM "
+                                 f"block store; ~1 GB of activations streamed per step"},
                 "clocks": sampler.summary(),
                 "e2e": {"value": e2e, "unit": "sequences/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": in_bytes,
-                        "d2h_bytes_per_step": B * 4 + 4},
+                        "d2h_bytes_per_step": B * 4 + 8},
                 "gpu_launches": ours, "other_launches": other}
         if ms_unroll is not None:
             fl = flops_per_sequence(C) * B
             ach = fl / (ms_unroll * 1e-3) / 1e12
             line["roofline"] = {"bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s",
                                 "frac": ach / peaks["tflops"], "traffic": None, "peak_source": peaks["source"],
-                                "kernel": "K1+K1b unroll group (forward online+target, backward)", "ms": ms_unroll,
-                                "algorithmic_gflop_per_launch": fl / 1e9}
+                                "kernel": "K1+K1b unroll group (forward online+target, BPTT backward): umma2_kernel launches",
+                                "ms": ms_unroll, "algorithmic_gflop_per_launch": fl / 1e9}
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(C)
+            val, dt, threads, cores = cpu_learner_rate(C, 2, 8)
+            line["cpu_baseline"] = {"value": val, "unit": "sequences/s", "cores": threads, "kind": "port",
+                                    "sample": f"2 full updates of an 8-sequence sample of the batch-{B} workload after warm-up "
+                                              f"(oracle/learner.py, torch CPU fp32, {threads} of {cores} host threads)"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
-
-
-def cpu_baseline(C):
-    from oracle import synth
-    from oracle.learner import LearnerState, init_params, learner_update
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    params = init_params(A, in_channels=C, seed=0)
-    st = LearnerState(online={k: v.clone() for k, v in params.items()}, target={k: v.clone() for k, v in params.items()})
-    batches = [synth.to_torch_batch(b) for b in host_batches(2, C)]
-    learner_update(st, batches[0])
-    t0 = time.perf_counter()
-    n = 2
-    for k in range(n):
-        learner_update(st, batches[k % 2])
-    dt = (time.perf_counter() - t0) / n
-    return {"value": B / dt, "unit": "sequences/s", "cores": cores, "kind": "port",
-            "sample": f"{n} full updates of batch {B} after 1 warm-up (oracle/learner.py, torch CPU fp32, {cores} threads)"}
 
 
 def main():
@@ -295,13 +309,14 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--channels", type=int, default=4, help="frame channels: 4 = BASELINE.json shape, 1 = reference obs_shape")
+    ap.add_argument("--fast", action="store_true", help="plain bf16 products instead of the bf16x3 parity mode")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
     else:
+        args.warmup = max(args.warmup, 3)
         run_ours(args)
 
 

@@ -99,6 +99,26 @@ def lstm_unroll(p: Params, u: torch.Tensor, h0: torch.Tensor, c0: torch.Tensor,
     return torch.stack(outs, dim=1)
 
 
+def lstm_unroll_packed(p: Params, u: torch.Tensor, h0: torch.Tensor, c0: torch.Tensor,
+                       lengths: torch.Tensor) -> torch.Tensor:
+    """The same recurrence through torch's packed-sequence LSTM op -- literally what the reference calls
+    (pack_padded_sequence + nn.LSTM + pad_packed_sequence, model.py:95-100).  Used for the timed CPU baseline so
+    that the port is as fast as the reference's own code; ``lstm_unroll`` stays the readable specification
+    (tests check the two agree)."""
+    from torch.nn.utils.rnn import pack_padded_sequence, pad_packed_sequence
+    packed = pack_padded_sequence(u, lengths.to(torch.int64).cpu(), batch_first=True, enforce_sorted=False)
+    weights = [p["recurrent.weight_ih_l0"], p["recurrent.weight_hh_l0"], p["recurrent.bias_ih_l0"], p["recurrent.bias_hh_l0"]]
+    hx = (h0[packed.sorted_indices].unsqueeze(0), c0[packed.sorted_indices].unsqueeze(0))
+    out, _, _ = torch._VF.lstm(packed.data, packed.batch_sizes, hx, weights, True, 1, 0.0, False, False)
+    out = torch.nn.utils.rnn.PackedSequence(out, packed.batch_sizes, packed.sorted_indices, packed.unsorted_indices)
+    hs, _ = pad_packed_sequence(out, batch_first=True, total_length=u.shape[1])
+    return hs
+
+
+_LSTM_IMPL = {"loop": lstm_unroll, "packed": lstm_unroll_packed}
+LSTM_MODE = "loop"
+
+
 def dueling_head(p: Params, hidden_rows: torch.Tensor) -> torch.Tensor:
     """model.py:115-117 / 145-148."""
     adv = F.linear(F.relu(F.linear(hidden_rows, p["advantage.0.weight"], p["advantage.0.bias"])),
@@ -146,7 +166,7 @@ def calculate_q_shifted(p: Params, obs, last_action, last_reward, h0, c0, burn_i
     """``Network.calculate_q_`` (model.py:81-119).  obs is float, already /255."""
     u, latent = _recurrent_input(p, obs, last_action, last_reward)
     lengths = burn_in.to(torch.int64) + learning.to(torch.int64) + forward.to(torch.int64)
-    hs = lstm_unroll(p, u, h0, c0, lengths)
+    hs = _LSTM_IMPL[LSTM_MODE](p, u, h0, c0, lengths)
     seq, tim = shifted_rows(burn_in, learning, forward, max_forward)
     q = dueling_head(p, hs[seq, tim])
     return (q, hs, latent) if want_hidden else q
@@ -157,7 +177,7 @@ def calculate_q(p: Params, obs, last_action, last_reward, h0, c0, burn_in, learn
     """``Network.calculate_q`` (model.py:122-150)."""
     u, latent = _recurrent_input(p, obs, last_action, last_reward)
     lengths = burn_in.to(torch.int64) + learning.to(torch.int64)
-    hs = lstm_unroll(p, u, h0, c0, lengths)
+    hs = _LSTM_IMPL[LSTM_MODE](p, u, h0, c0, lengths)
     seq, tim = learning_rows(burn_in, learning)
     q = dueling_head(p, hs[seq, tim])
     return (q, hs, latent) if want_hidden else q

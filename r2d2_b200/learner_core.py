@@ -175,9 +175,8 @@ class DeviceLearner:
         _lib.check(_lib.lib().r2d2_net_backward(self._h, p(self.online.flat), p(dq), p(self.grads.flat),
                                                 _lib.stream_ptr()))
 
-    def compute_gradients(self, b: dict) -> None:
-        """worker.py:345-363: Q passes, TD/loss/priorities, backward.  Results stay on device in
-        self.td / self.prio / self.loss_sum / self.rows / self.grads (grads of loss_sum)."""
+    def compute_forward(self, b: dict) -> None:
+        """worker.py:345-357: the three Q tensors, then TD / loss / priorities / dLoss/dQ (K1 + K2)."""
         self._live = b                                   # keep obs/hidden alive until backward ran
         p = _lib.ptr
         _lib.check(_lib.lib().r2d2_net_forward_pair(self._h, p(self.online.flat), p(self.target.flat), p(b["obs"]),
@@ -188,6 +187,11 @@ class DeviceLearner:
                                            p(b["n_step_reward"]), p(b["gamma"]), p(b["is_weights"]), p(b["learning"]),
                                            self.B, self.A, p(self.td), p(self.prio), p(self.loss_sum), p(self.rows),
                                            p(self.dq), _lib.stream_ptr()))
+
+    def compute_gradients(self, b: dict) -> None:
+        """worker.py:345-363: Q passes, TD/loss/priorities, backward.  Results stay on device in
+        self.td / self.prio / self.loss_sum / self.rows / self.grads (grads of loss_sum)."""
+        self.compute_forward(b)
         self.backward(self.dq)
         torch.reciprocal(self.rows.float(), out=self.grad_scale)      # mean over rows (worker.py:354)
 

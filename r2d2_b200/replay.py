@@ -24,7 +24,8 @@ _FIELDS = ["obs", "last_action", "last_reward", "action", "n_step_reward", "gamm
 class DeviceReplay:
     def __init__(self, buffer_capacity: int, block_length: int, burn_in_steps: int, learning_steps: int, forward_steps: int,
                  action_dim: int, obs_shape=(1, 84, 84), hidden_dim: int = 512, alpha: float = 0.9, beta: float = 0.6,
-                 batch_size: int = 64, device=None, seed: int = 0, staging_slots: int = 4):
+                 batch_size: int = 64, device=None, seed: int = 0, staging_slots: int = 4,
+                 tree_capacity: Optional[int] = None):
         _lib.require_device()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.block_len, self.burn_in, self.learning, self.forward = block_length, burn_in_steps, learning_steps, forward_steps
@@ -36,7 +37,7 @@ class DeviceReplay:
         self.batch_size = batch_size
         self.T = burn_in_steps + learning_steps + forward_steps
         self.rows_cap = (batch_size * learning_steps + 7) // 8 * 8
-        self.tree = PriorityTree(self.num_sequences, alpha, beta, device=self.device, seed=seed)
+        self.tree = PriorityTree(max(self.num_sequences, tree_capacity or 0), alpha, beta, device=self.device, seed=seed)
         h = C.c_void_p()
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().r2d2_replay_create(self.num_blocks, block_length, burn_in_steps, learning_steps, forward_steps,

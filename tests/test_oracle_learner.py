@@ -54,3 +54,22 @@ def test_learner_matches_reference_golden(golden_dir, name):
             np.testing.assert_allclose(p.flatten()[:16].numpy(), g[f"k{k}_phead_{n}"], atol=3e-6, rtol=0)
             assert abs(p.double().abs().sum().item() - float(g[f"k{k}_pabs_{n}"])) <= \
                 2e-6 * p.numel() + 1e-6
+
+
+def test_packed_lstm_baseline_mode_agrees_with_specification():
+    """The fast (torch packed LSTM) mode used for the timed CPU baseline computes the same update."""
+    import oracle.learner as ol
+    d = synth.synthetic_batch(4, A, burn_in=6, learning=5, forward=3, seed=9, ragged=True)
+    outs = {}
+    for mode in ("loop", "packed"):
+        ol.LSTM_MODE = mode
+        try:
+            params = init_params(A, seed=2)
+            st = LearnerState(online={k: v.clone() for k, v in params.items()}, target={k: v.clone() for k, v in params.items()})
+            outs[mode] = learner_update(st, synth.to_torch_batch(d), max_forward=3)
+        finally:
+            ol.LSTM_MODE = "loop"
+    np.testing.assert_allclose(outs["packed"]["td"], outs["loop"]["td"], atol=2e-6, rtol=0)
+    np.testing.assert_allclose(outs["packed"]["q"].numpy(), outs["loop"]["q"].numpy(), atol=2e-6, rtol=0)
+    for k in outs["loop"]["grads"]:
+        np.testing.assert_allclose(outs["packed"]["grads"][k].numpy(), outs["loop"]["grads"][k].numpy(), atol=1e-6, rtol=1e-4)
