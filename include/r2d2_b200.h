@@ -129,6 +129,9 @@ int r2d2_net_forward_pair(r2d2_net* n, const float* params_online, const float* 
  * included) and the encoder.  dq [rows_capacity][A]; grads: flat buffer in the parameter layout,
  * fully overwritten (alignment gaps are left untouched and must be zero). */
 int r2d2_net_backward(r2d2_net* n, const float* params, const float* dq, float* grads, void* stream);
+/* Recurrence scheduling: 1 (default) = all T LSTM steps of both networks in ONE persistent cooperative kernel
+ * (W_hh slices resident in shared memory, per-network step barriers) for B <= 64; 0 = one launch per step. */
+int r2d2_set_persistent_recurrence(int on);
 /* Test/debug access to device intermediates (see net.cu for the names). */
 void* r2d2_net_debug_ptr(r2d2_net* n, int which, const char* name);
 

@@ -34,13 +34,17 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
+def _extra_flags():
+    return os.environ.get("R2D2_NVCC_EXTRA", "").split()
+
+
 def _digest() -> str:
     h = hashlib.sha256()
     for path in sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + \
             [os.path.join(os.path.dirname(HERE), "include", "r2d2_b200.h")]:
         with open(path, "rb") as f:
             h.update(path.encode() + b"\0" + f.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS + _extra_flags()).encode())
     return h.hexdigest()
 
 
@@ -55,7 +59,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     for src in sources():
         obj = os.path.join(HERE, "build", os.path.basename(src) + ".o")
-        flags = [x for x in NVCC_FLAGS if x != "--shared"]
+        flags = [x for x in NVCC_FLAGS if x != "--shared"] + _extra_flags()
         cmd = [_nvcc(), *flags, "-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)

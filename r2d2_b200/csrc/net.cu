@@ -24,7 +24,7 @@
 // and at the n-step-shifted positions are two row gathers of the same unroll.
 #include <map>
 
-#include "umma2.cuh"
+#include "recurrence.cuh"
 
 namespace r2d2 {
 
@@ -67,7 +67,9 @@ struct r2d2_net {
     r2d2::Packed pk[2];
     r2d2::Acts ac[2];
     r2d2::bf16* s2d;                 // shared by both slots
+    r2d2::SplitW W1both;             // conv1 weights of both slots stacked [64][64C]: one launch shares the frame tile
     int *row_src, *len_full, *len_learn, *d_rows;     // row_src: [2*Rmax]  (q rows | shifted rows)
+    unsigned int* rec_bar;                            // [2] step counters of the persistent recurrence
     // backward scratch
     r2d2::SplitW dhid, DG, dlat, dpre3, dpre2, dpre1T;
     float *dH, *dhrec, *dcrec, *dout16, *ws, *colws;
@@ -86,13 +88,16 @@ __device__ __forceinline__ void put_split(const SplitW& w, size_t i, float x) {
     w.lo[i] = __float2bfloat16_rn(x - __bfloat162float(h));
 }
 
-__global__ void pack_kernel(const float* __restrict__ p, const int64_t* __restrict__ off, Packed pk, int A, int C, int KU) {
+__global__ void pack_kernel(const float* __restrict__ p, const int64_t* __restrict__ off, Packed pk, SplitW w1both, int which, int A,
+                            int C, int KU) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int KIH = LATENT + A + 1;
     if (i < 32ll * 64 * C) {                     // conv1 in space-to-depth order: k = (dy*2+dx)*16C + c*16 + r*4 + q
         const int K1 = 64 * C, n = i / K1, k = i % K1, tap = k / (16 * C), ch = k % (16 * C);
         const int dy = tap >> 1, dx = tap & 1, c = ch >> 4, r = (ch >> 2) & 3, q = ch & 3;
-        put_split(pk.W1s, i, p[off[P_C1W] + (int64_t)n * K1 + c * 64 + (4 * dy + r) * 8 + 4 * dx + q]);
+        const float w = p[off[P_C1W] + (int64_t)n * K1 + c * 64 + (4 * dy + r) * 8 + 4 * dx + q];
+        put_split(pk.W1s, i, w);
+        put_split(w1both, (size_t)which * 32 * K1 + i, w);
     }
     if (i < 64 * 512) {                          // conv2: [n][c][ky][kx] -> [n][(ky*4+kx)*32 + c]
         const int n = i / 512, k = i % 512, tap = k >> 5, c = k & 31;
@@ -511,6 +516,8 @@ static cudaError_t wgrad2(const AS& a, const BS& b, int M, int N, int K, int spl
     return cudaGetLastError();
 }
 
+int g_persistent_recurrence = 1;     // 0: per-step launches (also the path for B > 64)
+
 // device copy of the parameter offsets, kept in a side table keyed by handle
 static std::map<r2d2_net*, int64_t*> g_doff;
 
@@ -572,10 +579,12 @@ int r2d2_net_create(int B, int T, int C, int A, int Lmax, int max_forward, r2d2_
     }
     if (rc) return rc;
     R2D2_CUDA_CHECK(cudaMalloc(&n->s2d, NF * 441 * 16 * C * sizeof(bf16)));
+    rc |= alloc_s(&n->W1both, 64ull * 64 * C);
     R2D2_CUDA_CHECK(cudaMalloc(&n->row_src, 2 * n->Rmax * sizeof(int)));
     R2D2_CUDA_CHECK(cudaMalloc(&n->len_full, B * sizeof(int)));
     R2D2_CUDA_CHECK(cudaMalloc(&n->len_learn, B * sizeof(int)));
     R2D2_CUDA_CHECK(cudaMalloc(&n->d_rows, sizeof(int)));
+    R2D2_CUDA_CHECK(cudaMalloc(&n->rec_bar, 2 * sizeof(unsigned int)));
     rc |= alloc_s(&n->dhid, (size_t)n->Rmax * 2 * H); rc |= alloc_s(&n->DG, TB * G4); rc |= alloc_s(&n->dlat, NF * LATENT);
     rc |= alloc_s(&n->dpre3, NF * FLAT3); rc |= alloc_s(&n->dpre2, NF * 5184); rc |= alloc_s(&n->dpre1T, NF * 12800);
     rc |= alloc_f(&n->dH, TB * H); rc |= alloc_f(&n->dhrec, (size_t)kRecSplits * B * H); rc |= alloc_f(&n->dcrec, (size_t)B * H);
@@ -600,11 +609,11 @@ int r2d2_net_destroy(r2d2_net* n) {
         for (SplitW* x : as) free_s(*x);
         cudaFree(a.XP); cudaFree(a.Cs); cudaFree(a.Gs);
     }
-    SplitW* ss[] = {&n->dhid, &n->DG, &n->dlat, &n->dpre3, &n->dpre2, &n->dpre1T};
+    SplitW* ss[] = {&n->W1both, &n->dhid, &n->DG, &n->dlat, &n->dpre3, &n->dpre2, &n->dpre1T};
     for (SplitW* x : ss) free_s(*x);
     float* fs[] = {n->dH, n->dhrec, n->dcrec, n->dout16, n->ws, n->colws};
     for (float* x : fs) cudaFree(x);
-    cudaFree(n->s2d); cudaFree(n->row_src); cudaFree(n->len_full); cudaFree(n->len_learn); cudaFree(n->d_rows);
+    cudaFree(n->rec_bar); cudaFree(n->s2d); cudaFree(n->row_src); cudaFree(n->len_full); cudaFree(n->len_learn); cudaFree(n->d_rows);
     cudaFree(g_doff[n]);
     g_doff.erase(n);
     delete n;
@@ -618,7 +627,7 @@ int r2d2_net_ku(const r2d2_net* n) { return n ? n->KU : -1; }
 int r2d2_net_pack(r2d2_net* n, int which, const float* params, void* stream) {
     R2D2_REQUIRE(n && (which == 0 || which == 1) && params, "bad arguments");
     const int64_t work = 512ll * FLAT3 > (int64_t)G4 * n->KU ? 512ll * FLAT3 : (int64_t)G4 * n->KU;
-    pack_kernel<<<cdiv(work, 256), 256, 0, as_stream(stream)>>>(params, g_doff[n], n->pk[which], n->A, n->C, n->KU);
+    pack_kernel<<<cdiv(work, 256), 256, 0, as_stream(stream)>>>(params, g_doff[n], n->pk[which], n->W1both, which, n->A, n->C, n->KU);
     R2D2_LAUNCH_CHECK();
     return R2D2_OK;
 }
@@ -637,13 +646,37 @@ static cudaError_t conv1_forward(r2d2_net* n, int which, const float* params, cu
     Epi2BiasSplit<true> e{n->ac[which].act1, params + n->off[P_C1B], n->NF * 400, 32, 32, 1.f / 255.f};
     return launch_umma2<32>(a, b, e, n->NF * 400, 32, 64 * CH, 1, s);
 }
+// conv1 of BOTH slots in one launch: columns 0-31 -> online act1, 32-63 -> target act1 (same frames, stacked weights)
+struct Epi2Conv1Pair {
+    SplitW out0, out1; const float* bias0; const float* bias1; int M; float scale;
+    __device__ __forceinline__ void store16(int m, int n, const float (&v)[16], int) const {
+        if (m >= M || n >= 64) return;
+        const SplitW& o = n < 32 ? out0 : out1;
+        const float* b = n < 32 ? bias0 : bias1;
+        const int c = n & 31;
+#pragma unroll
+        for (int j = 0; j < 16; j += 8) {
+            float r[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) r[i] = fmaxf(v[j + i] * scale + __ldg(b + c + j + i), 0.f);
+            split_store8(o.hi, o.lo, (size_t)m * 32 + c + j, r);
+        }
+    }
+};
+template <int CH>
+static cudaError_t conv1_forward_pair(r2d2_net* n, const float* p0, const float* p1, cudaStream_t s) {
+    SrcConvK<21, 21, 16 * CH, 20, 20, 2, 2, 1, false> a{n->s2d, nullptr, n->NF};
+    SrcMatK b{n->W1both.hi, n->W1both.lo, 64, 64 * CH, 64 * CH};
+    Epi2Conv1Pair e{n->ac[0].act1, n->ac[1].act1, p0 + n->off[P_C1B], p1 + n->off[P_C1B], n->NF * 400, 1.f / 255.f};
+    return launch_umma2<64>(a, b, e, n->NF * 400, 64, 64 * CH, 1, s);
+}
 template <int CH>
 static cudaError_t conv1_wgrad(r2d2_net* n, float* grads, cudaStream_t s) {
     const int NP = n->NF * 400;
     SrcMatK a{n->dpre1T.hi, n->dpre1T.lo, 32, NP, NP};
     SrcConvMN<21, 21, 16 * CH, 20, 20, 2, 2, 1, false> b{n->s2d, nullptr, n->NF};
     const int splits = (NP + 4095) / 4096;
-    return wgrad2<64>(a, b, 32, 64 * CH, NP, splits, R_C1, n, grads, g_doff[n], 1.f / 255.f, s);
+    return wgrad2<(CH == 4 ? 256 : 64)>(a, b, 32, 64 * CH, NP, splits, R_C1, n, grads, g_doff[n], 1.f / 255.f, s);
 }
 
 // frames -> space-to-depth bf16 (once per batch, shared by both slots) + row maps + h0 split
@@ -658,7 +691,7 @@ static int net_prep(r2d2_net* n, const uint8_t* obs, const float* hidden, const 
 }
 
 // encoder + input projection of one slot (model.py:39-49,92); 1/255 of worker.py:342 folded into the conv1 epilogue
-static int net_encode(r2d2_net* n, int which, const FwdArgs& fa, cudaStream_t s) {
+static int net_encode(r2d2_net* n, int which, const FwdArgs& fa, cudaStream_t s, bool conv1_done = false) {
     const int B = n->B, T = n->T, A = n->A, KU = n->KU, NF = n->NF;
     Packed& pk = n->pk[which];
     Acts& ac = n->ac[which];
@@ -666,7 +699,7 @@ static int net_encode(r2d2_net* n, int which, const FwdArgs& fa, cudaStream_t s)
     const float* params = fa.params;
     side_columns_kernel<<<T * B, 32, 0, s>>>(ac.U, fa.last_action, fa.last_reward, B, T, A, KU);
     R2D2_LAUNCH_CHECK();
-    R2D2_CUDA_CHECK(n->C == 1 ? conv1_forward<1>(n, which, params, s) : conv1_forward<4>(n, which, params, s));
+    if (!conv1_done) R2D2_CUDA_CHECK(n->C == 1 ? conv1_forward<1>(n, which, params, s) : conv1_forward<4>(n, which, params, s));
     {
         SrcConvK<20, 20, 32, 9, 9, 4, 4, 2> a{ac.act1.hi, ac.act1.lo, NF};
         SrcMatK b{pk.W2p.hi, pk.W2p.lo, 64, 512, 512};
@@ -711,6 +744,19 @@ static StepOps lstm_step_ops(r2d2_net* n, int which, const float* hidden, int t)
 // in the same launches (two independent recurrences hide each other's per-step latency).
 static int net_recurrence(r2d2_net* n, int which, const float* hidden, cudaStream_t s) {
     const int B = n->B, T = n->T;
+    if (B <= 64 && g_persistent_recurrence) {            // one cooperative launch for all T steps (recurrence.cuh)
+        RecFwdParams P;
+        for (int k = 0; k < 2; ++k) {
+            P.Whi[k] = n->pk[k].Whh_p.hi; P.Wlo[k] = n->pk[k].Whh_p.lo; P.XP[k] = n->ac[k].XP;
+            P.Hhi[k] = n->ac[k].HsX.hi; P.Hlo[k] = n->ac[k].HsX.lo; P.Cs[k] = n->ac[k].Cs;
+            P.Gs[k] = k == 0 ? n->ac[k].Gs : nullptr;
+        }
+        P.c0 = hidden + H; P.ld_c0 = 2 * H; P.len = n->len_full; P.bar = n->rec_bar; P.B = B; P.T = T;
+        P.net_base = which == 2 ? 0 : which;
+        P.fast = g_fast_math;
+        R2D2_CUDA_CHECK(launch_rec_fwd(P, which == 2 ? 2 : 1, s));
+        return R2D2_OK;
+    }
     for (int t = 0; t < T; ++t) {
         if (which == 2) {
             StepOps o0 = lstm_step_ops(n, 0, hidden, t), o1 = lstm_step_ops(n, 1, hidden, t);
@@ -779,8 +825,13 @@ int r2d2_net_forward_pair(r2d2_net* n, const float* params_online, const float* 
     n->hidden = hidden;
     FwdArgs f0{params_online, obs, last_action, last_reward, hidden}, f1{params_target, obs, last_action, last_reward, hidden};
     int rc = net_prep(n, obs, hidden, burn, learn, fwd, s);
-    if (!rc) rc = net_encode(n, 0, f0, s);
-    if (!rc) rc = net_encode(n, 1, f1, s);
+    if (!rc) {
+        cudaError_t e = n->C == 1 ? conv1_forward_pair<1>(n, params_online, params_target, s)
+                                  : conv1_forward_pair<4>(n, params_online, params_target, s);
+        R2D2_CUDA_CHECK(e);
+    }
+    if (!rc) rc = net_encode(n, 0, f0, s, true);
+    if (!rc) rc = net_encode(n, 1, f1, s, true);
     if (!rc) rc = net_recurrence(n, 2, hidden, s);
     if (!rc) rc = net_heads(n, 0, params_online, q_learn_out, qn_online_out, s);
     if (!rc) rc = net_heads(n, 1, params_target, nullptr, qn_target_out, s);
@@ -881,12 +932,17 @@ int r2d2_net_backward(r2d2_net* n, const float* params, const float* dq, float* 
         SrcConvMN<20, 20, 32, 9, 9, 4, 4, 2> b{ac.act1.hi, ac.act1.lo, NF};
         R2D2_CUDA_CHECK((wgrad2<64>(a, b, 64, 512, K2, (K2 + 4095) / 4096, R_C2, n, grads, d_off, 1.f, s)));
         R2D2_CUDA_CHECK(colsum_split(ro(n->dpre2), K2, 64, B_PLAIN, grads, off[P_C2B], 0, A, n->colws, s));
-        for (int cls = 0; cls < 4; ++cls) {      // stride-2 dgrad as four stride-1 problems (output parity classes)
+        {   // stride-2 dgrad as four stride-1 problems (output parity classes), ONE launch: blockIdx.x = class, so the
+            // CTAs that write interleaved pixels of the same dpre1T sectors run together and merge in L2
             SrcDgradK<10, 10, 9, 9, 64, 2, 2> a2{n->dpre2.hi, n->dpre2.lo, NF};
-            const size_t wo = (size_t)cls * 32 * 256;
-            SrcMatK b2{pk.W2d.hi + wo, pk.W2d.lo + wo, 32, 256, 256};
-            Epi2DgradS2T e{n->dpre1T, ro(ac.act1), NF, cls >> 1, cls & 1, (long long)NF * 400};
-            R2D2_CUDA_CHECK((launch_umma2<32>(a2, b2, e, NF * 100, 32, 256, 1, s)));
+            Multi<SrcMatK, 4> b2;
+            Multi<Epi2DgradS2T, 4> e;
+            for (int cls = 0; cls < 4; ++cls) {
+                const size_t wo = (size_t)cls * 32 * 256;
+                b2.f[cls] = SrcMatK{pk.W2d.hi + wo, pk.W2d.lo + wo, 32, 256, 256};
+                e.f[cls] = Epi2DgradS2T{n->dpre1T, ro(ac.act1), NF, cls >> 1, cls & 1, (long long)NF * 400};
+            }
+            R2D2_CUDA_CHECK((launch_umma2_multi<32, 4>(a2, b2, e, NF * 100, 256, s)));
         }
     }
     {   // conv1 (weights only; frames need no gradient)
@@ -898,6 +954,13 @@ int r2d2_net_backward(r2d2_net* n, const float* params, const float* dq, float* 
         R2D2_LAUNCH_CHECK();
     }
     return R2D2_OK;
+}
+
+/* 1 (default): the T-step recurrence runs as one persistent cooperative kernel when B <= 64; 0: per-step launches. */
+int r2d2_set_persistent_recurrence(int on) {
+    int prev = g_persistent_recurrence;
+    g_persistent_recurrence = on ? 1 : 0;
+    return prev;
 }
 
 /* test/debug access to intermediates (bf16 planes are named "<tensor>.hi" / "<tensor>.lo") */

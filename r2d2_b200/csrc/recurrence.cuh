@@ -1,0 +1,244 @@
+// Persistent LSTM recurrence (forward): ALL time steps of BOTH networks in one cooperative launch.
+//
+// Replaces T per-step GEMM launches of the stepwise path (net.cu: net_recurrence) for batches of <= 64 sequences.
+//   grid = 64 CTAs per network; CTA (net, s) owns gate columns [32 s, 32 s + 32) = hidden units [8 s, 8 s + 8)
+//   * its W_hh slice [32][512] (bf16 hi+lo, 64 KB) is staged into shared memory ONCE and stays there;
+//   * per step:  acquire the network's step barrier  ->  cp.async h_{t-1} [64][512] hi+lo (128 KB, from L2, in 8
+//     k-blocks with their own mbarriers so the MMAs start on the first block)  ->  96 tcgen05.mma (M=64, N=32, K=16,
+//     bf16x3) into a 32-column TMEM accumulator  ->  epilogue: 128 threads each own (sequence b, 4 hidden units):
+//     gates = acc + XP[t], LSTM cell with the cell state c and the previous h held in REGISTERS across steps,
+//     stores h_t (split), c_t, gates  ->  __threadfence + release-arrive on the network's barrier counter.
+//   The two networks never wait for each other (separate counters): their step latencies overlap across SMs.
+// UMMA M=64 accumulator layout (cta_group::1): row m lives in TMEM lane (m & 15) + 32 * (m >> 4), i.e. the first 16
+// lanes of each 32-lane quadrant (cute tmem_frg: Shape<(16,4),N> : Stride<(1,32),128>).
+#pragma once
+#include "umma2.cuh"
+
+namespace r2d2 {
+
+constexpr int REC_H = 512, REC_G4 = 2048, REC_SLICE = 32, REC_CTAS_PER_NET = REC_G4 / REC_SLICE;   // 64
+constexpr int REC_KB = REC_H / UM_BK;                                                              // 8 k-blocks of 64
+constexpr int REC_A_TILE = 64 * UM_BK * 2;          // 8 KB  (64 rows x 64 k bf16)
+constexpr int REC_B_TILE = REC_SLICE * UM_BK * 2;   // 4 KB
+constexpr int REC_SMEM = 2 * REC_KB * (REC_A_TILE + REC_B_TILE) + 1024 + 256;
+
+struct RecFwdParams {
+    const bf16* Whi[2]; const bf16* Wlo[2];   // Whh_p [2048][512] (gate-interleaved rows)
+    const float* XP[2];                       // [T*B][2048]
+    bf16* Hhi[2]; bf16* Hlo[2];               // HsX [(T+1)*B][512], block 0 = h0
+    float* Cs[2];                             // [T*B][512]
+    float* Gs[2];                             // [T*B][2048] or nullptr
+    const float* c0; int ld_c0;               // stored cell state (hidden + H, row stride 2H)
+    const int* len;                           // [B] steps each sequence advances
+    unsigned int* bar;                        // [2] step barrier counters, zero before launch
+    int B, T, net_base;                       // net_base: slot of the first CTA group (single-network launches)
+    int fast;
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_add(unsigned int* p, unsigned int v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_mn(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(UM_THREADS, 1) rec_fwd_kernel(const RecFwdParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;
+    uint8_t* smem = smem_raw + pad;
+    const uint32_t sA = raw + pad;                                       // A: [plane][kb] tiles of 8 KB
+    const uint32_t sB = sA + 2 * REC_KB * REC_A_TILE;                    // B: [plane][kb] tiles of 4 KB
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * REC_KB * (REC_A_TILE + REC_B_TILE));
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + REC_KB + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int grp = blockIdx.x / REC_CTAS_PER_NET, slice = blockIdx.x % REC_CTAS_PER_NET;
+    const int net = P.net_base + grp;
+    const int B = P.B, T = P.T;
+    const int n0 = slice * REC_SLICE;
+    const bool want_lo = !P.fast;
+
+    if (tid == 0) {
+        for (int kb = 0; kb < REC_KB; ++kb) mbar_init(smem_u32(&bars[kb]), UM_PRODUCERS / 32);
+        mbar_init(smem_u32(&bars[REC_KB]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == UM_PRODUCERS / 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(32) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < UM_PRODUCERS / 32) {
+        // ---- W_hh slice -> smem once: 32 rows x 64 chunks (x2 planes)
+        for (int u = tid; u < REC_SLICE * 64; u += UM_PRODUCERS) {
+            const int row = u >> 6, ch = u & 63, kb = ch >> 3, j = ch & 7;
+            const uint32_t dst = (uint32_t)(kb * REC_B_TILE + (row >> 3) * 1024 + (row & 7) * 128 + ((j ^ (row & 7)) << 4));
+            const size_t src = (size_t)(n0 + row) * REC_H + ch * 8;
+            cp_async16(sB + dst, P.Whi[net] + src, true);
+            if (want_lo) cp_async16(sB + REC_KB * REC_B_TILE + dst, P.Wlo[net] + src, true);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        fence_proxy_async_smem();
+
+        // ---- epilogue ownership: sequence b = 16*(warp&3) + lane (lanes < 16), 4 hidden units
+        const int b = 16 * (warp & 3) + lane;
+        const int half = warp >> 2;                       // columns [16*half, 16*half + 16) of the slice
+        const bool owner = lane < 16 && b < B;
+        const int j0 = slice * 8 + half * 4;              // first of this thread's 4 hidden units
+        float c_reg[4] = {0.f, 0.f, 0.f, 0.f}, h_reg[4] = {0.f, 0.f, 0.f, 0.f};
+        int my_len = 0;
+        if (owner) {
+            my_len = P.len[b];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                c_reg[u] = P.c0[(size_t)b * P.ld_c0 + j0 + u];
+                h_reg[u] = split_load(P.Hhi[net], P.Hlo[net], (size_t)b * REC_H + j0 + u);
+            }
+        }
+        // A staging plan: per k-block 64 rows x 8 chunks = 512 chunk slots -> 2 per thread (x2 planes)
+        const int a_row0 = tid >> 3, a_j = tid & 7;        // rows a_row0 and a_row0 + 32
+        for (int t = 0; t < T; ++t) {
+            float4 xp[4];
+            if (owner) {
+                const float4* xsrc = reinterpret_cast<const float4*>(P.XP[net] + ((size_t)t * B + b) * REC_G4 + n0 + 16 * half);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) xp[q] = __ldg(xsrc + q);
+            }
+            if (t > 0) {                                   // all CTAs of this network have published h_{t-1}
+                if (tid == 0) {
+                    const unsigned int target = (unsigned int)(REC_CTAS_PER_NET * t);
+                    for (uint32_t spins = 0; ld_acquire_u32(P.bar + net) < target; ++spins)
+                        if (spins > (1u << 28)) __trap();
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(UM_PRODUCERS) : "memory");
+            }
+            // h_{t-1} = HsX block t  -> A tiles, one cp.async group per k-block
+            const bf16* hsrc_hi = P.Hhi[net] + (size_t)t * B * REC_H;
+            const bf16* hsrc_lo = P.Hlo[net] + (size_t)t * B * REC_H;
+#pragma unroll
+            for (int kb = 0; kb < REC_KB; ++kb) {
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const int row = a_row0 + 32 * r;
+                    const uint32_t dst = (uint32_t)(kb * REC_A_TILE + (row >> 3) * 1024 + (row & 7) * 128 + ((a_j ^ (row & 7)) << 4));
+                    const bool ok = row < B;
+                    const size_t src = ok ? (size_t)row * REC_H + kb * 64 + a_j * 8 : 0;
+                    cp_async16(sA + dst, hsrc_hi + src, ok);
+                    if (want_lo) cp_async16(sA + REC_KB * REC_A_TILE + dst, hsrc_lo + src, ok);
+                }
+                cp_async_commit();
+            }
+#pragma unroll
+            for (int kb = 0; kb < REC_KB; ++kb) {
+                switch (REC_KB - 1 - kb) {                 // wait until group kb has landed
+                    case 7: cp_async_wait<7>(); break; case 6: cp_async_wait<6>(); break; case 5: cp_async_wait<5>(); break;
+                    case 4: cp_async_wait<4>(); break; case 3: cp_async_wait<3>(); break; case 2: cp_async_wait<2>(); break;
+                    case 1: cp_async_wait<1>(); break; default: cp_async_wait<0>(); break;
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bars[kb]));
+            }
+            // ---- epilogue of step t
+            mbar_wait(smem_u32(&bars[REC_KB]), (uint32_t)t & 1u);
+            tc_fence_after();
+            float acc[16];
+            tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(16 * half), acc);
+            if (owner) {
+                const bool live = t < my_len;
+                const size_t row = (size_t)t * B + b;
+                float hn4[4], cn4[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float4 x = xp[u];
+                    const float gi = 1.f / (1.f + expf(-(acc[4 * u] + x.x)));
+                    const float gf = 1.f / (1.f + expf(-(acc[4 * u + 1] + x.y)));
+                    const float gg = tanhf(acc[4 * u + 2] + x.z);
+                    const float go = 1.f / (1.f + expf(-(acc[4 * u + 3] + x.w)));
+                    const float cn = gf * c_reg[u] + gi * gg;
+                    const float hn = go * tanhf(cn);
+                    if (P.Gs[net]) *reinterpret_cast<float4*>(P.Gs[net] + row * REC_G4 + n0 + 16 * half + 4 * u) = make_float4(gi, gf, gg, go);
+                    cn4[u] = live ? cn : c_reg[u];
+                    hn4[u] = live ? hn : h_reg[u];
+                    c_reg[u] = cn4[u];
+                    h_reg[u] = hn4[u];
+                }
+                *reinterpret_cast<float4*>(P.Cs[net] + row * REC_H + j0) = make_float4(cn4[0], cn4[1], cn4[2], cn4[3]);
+                uint32_t hh[2], ll[2];
+                split2(hn4[0], hn4[1], hh[0], ll[0]);
+                split2(hn4[2], hn4[3], hh[1], ll[1]);
+                const size_t ho = ((size_t)(t + 1) * B + b) * REC_H + j0;           // HsX block t+1
+                *reinterpret_cast<uint2*>(P.Hhi[net] + ho) = make_uint2(hh[0], hh[1]);
+                *reinterpret_cast<uint2*>(P.Hlo[net] + ho) = make_uint2(ll[0], ll[1]);
+                // hi/lo re-rounding: keep the register copy equal to what other CTAs will read
+                h_reg[0] = __uint_as_float(hh[0] << 16) + __uint_as_float(ll[0] << 16);
+                h_reg[1] = __uint_as_float(hh[0] & 0xFFFF0000u) + __uint_as_float(ll[0] & 0xFFFF0000u);
+                h_reg[2] = __uint_as_float(hh[1] << 16) + __uint_as_float(ll[1] << 16);
+                h_reg[3] = __uint_as_float(hh[1] & 0xFFFF0000u) + __uint_as_float(ll[1] & 0xFFFF0000u);
+            }
+            tc_fence_before();
+            __threadfence();                               // publish h_t before the arrive
+            asm volatile("bar.sync 1, %0;" ::"n"(UM_PRODUCERS) : "memory");
+            if (tid == 0) red_release_add(P.bar + net, 1u);
+        }
+    } else {
+        // ---------------------------------------------------------------- MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16_mn(64, REC_SLICE);
+            for (int t = 0; t < T; ++t) {
+                const uint32_t ph = (uint32_t)t & 1u;
+#pragma unroll
+                for (int kb = 0; kb < REC_KB; ++kb) {
+                    mbar_wait(smem_u32(&bars[kb]), ph);
+                    tc_fence_after();
+                    const uint64_t a_hi = umma_desc_sw128(sA + kb * REC_A_TILE), a_lo = umma_desc_sw128(sA + (REC_KB + kb) * REC_A_TILE);
+                    const uint64_t b_hi = umma_desc_sw128(sB + kb * REC_B_TILE), b_lo = umma_desc_sw128(sB + (REC_KB + kb) * REC_B_TILE);
+#pragma unroll
+                    for (int k = 0; k < UM_BK / 16; ++k) {
+                        const uint64_t adv = (uint64_t)(k * 32 >> 4);
+                        uint32_t accum = (kb | k) ? 1u : 0u;
+                        if (want_lo) {
+                            umma_bf16(tmem_base, a_lo + adv, b_hi + adv, idesc, accum);
+                            umma_bf16(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
+                            accum = 1u;
+                        }
+                        umma_bf16(tmem_base, a_hi + adv, b_hi + adv, idesc, accum);
+                    }
+                }
+                umma_commit(smem_u32(&bars[REC_KB]));
+            }
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (warp == UM_PRODUCERS / 32) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(32) : "memory");
+    }
+}
+
+static inline cudaError_t launch_rec_fwd(const RecFwdParams& P, int nets, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(rec_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, REC_SMEM);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    cudaError_t e = cudaMemsetAsync(P.bar, 0, 2 * sizeof(unsigned int), s);
+    if (e != cudaSuccess) return e;
+    void* args[] = {(void*)&P};
+    return cudaLaunchCooperativeKernel((const void*)rec_fwd_kernel, dim3(nets * REC_CTAS_PER_NET), dim3(UM_THREADS), args, REC_SMEM, s);
+}
+
+}  // namespace r2d2

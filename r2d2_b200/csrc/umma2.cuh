@@ -74,46 +74,67 @@ template <int BN, bool A_LO, bool B_LO> struct Umma2Cfg {
     static constexpr int kTileA = UM_BM * UM_BK * 2;
     static constexpr int kTileB = BN * UM_BK * 2;
     static constexpr int kStageBytes = (A_LO ? 2 : 1) * kTileA + (B_LO ? 2 : 1) * kTileB;
-    static constexpr int kStages = (kStageBytes * 4 <= 200 * 1024) ? 4 : ((kStageBytes * 3 <= 200 * 1024) ? 3 : 2);
+#ifndef R2D2_STAGE_BUDGET_KB
+#define R2D2_STAGE_BUDGET_KB 100
+#endif
+    static constexpr int kBudget = R2D2_STAGE_BUDGET_KB * 1024;
+    static constexpr int kStages = (kStageBytes * 4 <= kBudget) ? 4 : ((kStageBytes * 3 <= kBudget) ? 3 : 2);
     static constexpr int kSmem = kStages * kStageBytes + 1024 + 256;
     static constexpr int kTmemCols = BN < 32 ? 32 : BN;
 };
 
-// issue the cp.async chunks of one operand tile (ROWS operand rows x 64 reduction indices)
-template <int ROWS, class Src>
-__device__ __forceinline__ void stage_operand(const Src& src, int row0, int kbase, int k_end, uint32_t hi_tile, uint32_t lo_tile,
-                                              bool want_lo, int tid) {
-    constexpr int kUnits = ROWS * 8;
-    constexpr int kIters = (kUnits + UM_PRODUCERS - 1) / UM_PRODUCERS;
+// Per-thread staging plan of one operand tile (ROWS operand rows x 64 reduction indices).  A thread's chunks keep
+// the same operand rows for the whole K loop, so the row part of the gather address (frame / pixel decomposition,
+// row-map lookup, bounds) is computed ONCE into `ctx`; per k-block only the reduction-index part is added.
+template <int ROWS, class Src> struct OperandStager {
+    static constexpr int kUnits = ROWS * 8;
+    static constexpr int kIters = (kUnits + UM_PRODUCERS - 1) / UM_PRODUCERS;
+    typename Src::RCtx ctx[kIters];
+    uint32_t dst[kIters];
+    int kofs[kIters];                // reduction-index offset of the chunk inside a stage
+
+    __device__ __forceinline__ void init(const Src& src, int row0, int tid) {
 #pragma unroll
-    for (int it = 0; it < kIters; ++it) {
-        const int u = tid + it * UM_PRODUCERS;
-        if (kUnits % UM_PRODUCERS != 0 && u >= kUnits) break;
-        const int j = u & 7;
-        int line, row, k;
-        uint32_t dst;
-        if constexpr (!Src::kMN) {
-            line = u >> 3;                       // operand row within the tile
-            row = row0 + line;
-            k = kbase + j * 8;
-            dst = (uint32_t)((line >> 3) * 1024 + (line & 7) * 128 + ((j ^ (line & 7)) << 4));
-        } else {
-            line = (u >> 3) & 63;                // reduction index within the stage
-            const int atom = u >> 9;
-            row = row0 + atom * 64 + j * 8;
-            k = kbase + line;
-            dst = (uint32_t)(atom * 8192 + (line >> 3) * 1024 + (line & 7) * 128 + ((j ^ (line & 7)) << 4));
+        for (int it = 0; it < kIters; ++it) {
+            const int u = tid + it * UM_PRODUCERS;
+            const int j = u & 7;
+            if constexpr (!Src::kMN) {
+                const int line = u >> 3;                    // operand row within the tile
+                ctx[it] = src.rctx(row0 + line);
+                kofs[it] = j * 8;
+                dst[it] = (uint32_t)((line >> 3) * 1024 + (line & 7) * 128 + ((j ^ (line & 7)) << 4));
+            } else {
+                const int line = (u >> 3) & 63, atom = u >> 9;   // reduction index within the stage, 64-row atom
+                ctx[it] = src.rctx(row0 + atom * 64 + j * 8);
+                kofs[it] = line;
+                dst[it] = (uint32_t)(atom * 8192 + (line >> 3) * 1024 + (line & 7) * 128 + ((j ^ (line & 7)) << 4));
+            }
         }
-        const long long off = (k < k_end) ? src.chunk(row, k) : -1;
-        const bool ok = off >= 0;
-        const long long o = ok ? off : 0;
-        cp_async16(hi_tile + dst, src.hi + o, ok);
-        if (Src::kHasLo && want_lo) cp_async16(lo_tile + dst, src.lo + o, ok);
     }
-}
+    __device__ __forceinline__ void issue(const Src& src, int kbase, int k_end, uint32_t hi_tile, uint32_t lo_tile, bool want_lo,
+                                          int tid) const {
+#pragma unroll
+        for (int it = 0; it < kIters; ++it) {
+            if (kUnits % UM_PRODUCERS != 0 && tid + it * UM_PRODUCERS >= kUnits) break;
+            const int k = kbase + kofs[it];
+            const long long off = (k < k_end) ? src.chunk(ctx[it], k) : -1;
+            const bool ok = off >= 0;
+            const long long o = ok ? off : 0;
+            cp_async16(hi_tile + dst[it], src.hi + o, ok);
+            if (Src::kHasLo && want_lo) cp_async16(lo_tile + dst[it], src.lo + o, ok);
+        }
+    }
+};
+
+// N operand sets selected by blockIdx.x (gridDim.x == N, one N tile): e.g. the 4 output-parity classes of a
+// stride-2 dgrad in ONE launch, so that CTAs writing interleaved elements of the same sectors run together.
+template <class F, int N> struct Multi { F f[N]; };
+template <class F, int N> __device__ __forceinline__ const F& sel_z(const Multi<F, N>& f, int) { return f.f[blockIdx.x]; }
+template <class F> struct IsMulti { static constexpr bool value = false; };
+template <class F, int N> struct IsMulti<Multi<F, N>> { static constexpr bool value = true; };
 
 template <int BN, bool FAST, class ASrcT, class BSrcT, class EpiT>
-__global__ void __launch_bounds__(UM_THREADS, 1)
+__global__ void __launch_bounds__(UM_THREADS, R2D2_STAGE_BUDGET_KB <= 104 ? 2 : 1)
 umma2_kernel(const ASrcT a_, const BSrcT b_, const EpiT ep_, int K, int k_per_split) {
     using ASrc = typename std::remove_cv<typename std::remove_reference<decltype(sel_z(a_, 0))>::type>::type;
     using BSrc = typename std::remove_cv<typename std::remove_reference<decltype(sel_z(b_, 0))>::type>::type;
@@ -135,7 +156,7 @@ umma2_kernel(const ASrcT a_, const BSrcT b_, const EpiT ep_, int K, int k_per_sp
     const ASrc& as = sel_z(a_, z);
     const BSrc& bs = sel_z(b_, z);
     const auto& ep = sel_z(ep_, z);
-    const int m0 = blockIdx.y * UM_BM, n0 = blockIdx.x * BN;
+    const int m0 = blockIdx.y * UM_BM, n0 = IsMulti<EpiT>::value ? 0 : blockIdx.x * BN;
     const int k_begin = IsPair<ASrcT>::value ? 0 : z * k_per_split;
     const int k_end = IsPair<ASrcT>::value ? K : min(K, k_begin + k_per_split);
     const int nk = (k_end - k_begin + UM_BK - 1) / UM_BK;
@@ -167,6 +188,10 @@ umma2_kernel(const ASrcT a_, const BSrcT b_, const EpiT ep_, int K, int k_per_sp
     if (warp < UM_PRODUCERS / 32) {
         // ------------------------------------------------------------------ producers (cp.async)
         constexpr int D = kStages - 1;                    // prefetch distance in stages
+        OperandStager<UM_BM, ASrc> sa;
+        OperandStager<BN, BSrc> sb;
+        sa.init(as, m0, tid);
+        sb.init(bs, n0, tid);
         for (int kt = 0; kt < nk + D; ++kt) {
             if (kt < nk) {
                 const int s = kt % kStages;
@@ -174,8 +199,8 @@ umma2_kernel(const ASrcT a_, const BSrcT b_, const EpiT ep_, int K, int k_per_sp
                 mbar_wait(smem_u32(&bars[kStages + s]), ph ^ 1u);
                 const uint32_t st = smem_base + s * Cfg::kStageBytes;
                 const int kbase = k_begin + kt * UM_BK;
-                stage_operand<UM_BM>(as, m0, kbase, k_end, st, st + kOffALo, A_LO, tid);
-                stage_operand<BN>(bs, n0, kbase, k_end, st + kOffBHi, st + kOffBLo, B_LO, tid);
+                sa.issue(as, kbase, k_end, st, st + kOffALo, A_LO, tid);
+                sb.issue(bs, kbase, k_end, st + kOffBHi, st + kOffBLo, B_LO, tid);
             }
             cp_async_commit();
             if (kt >= D) {
@@ -275,6 +300,37 @@ static inline cudaError_t launch_umma2(const ASrc& a, const BSrc& b, const Epi& 
     return cudaGetLastError();
 }
 
+// one launch over CNT operand sets selected by blockIdx.x (N <= BN: a single N tile per set)
+template <int BN, int CNT, class ASrc, class BSrc, class Epi>
+static inline cudaError_t launch_umma2_multi(const ASrc& a, const Multi<BSrc, CNT>& b, const Multi<Epi, CNT>& ep, int M, int K,
+                                             cudaStream_t s) {
+    if (M <= 0) return cudaSuccess;
+    const int k_per_split = (K + UM_BK - 1) / UM_BK * UM_BK;
+    dim3 grid(CNT, (M + UM_BM - 1) / UM_BM, 1);
+    if (g_fast_math) {
+        using Cfg = Umma2Cfg<BN, false, false>;
+        auto kern = umma2_kernel<BN, true, ASrc, Multi<BSrc, CNT>, Multi<Epi, CNT>>;
+        static bool configured = false;
+        if (!configured) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+            if (e != cudaSuccess) return e;
+            configured = true;
+        }
+        kern<<<grid, UM_THREADS, Cfg::kSmem, s>>>(a, b, ep, K, k_per_split);
+    } else {
+        using Cfg = Umma2Cfg<BN, ASrc::kHasLo, BSrc::kHasLo>;
+        auto kern = umma2_kernel<BN, false, ASrc, Multi<BSrc, CNT>, Multi<Epi, CNT>>;
+        static bool configured = false;
+        if (!configured) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+            if (e != cudaSuccess) return e;
+            configured = true;
+        }
+        kern<<<grid, UM_THREADS, Cfg::kSmem, s>>>(a, b, ep, K, k_per_split);
+    }
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------
 // chunk sources.  chunk(row, k) returns the element offset (into both planes) of the 8-element
 // chunk starting at (row, k) -- along k for K-major sources, along rows for MN-major sources --
@@ -282,52 +338,76 @@ static inline cudaError_t launch_umma2(const ASrc& a, const BSrc& b, const Epi& 
 // ---------------------------------------------------------------------------------------------
 struct SrcMatK {   // X(row, k) = p[row*ld + k]
     static constexpr bool kMN = false, kHasLo = true;
+    using RCtx = long long;
     const bf16* hi; const bf16* lo; int rows, K; long long ld;
-    __device__ __forceinline__ long long chunk(int row, int k) const { return (row < rows && k < K) ? row * ld + k : -1; }
+    __device__ __forceinline__ RCtx rctx(int row) const { return row < rows ? row * ld : -1; }
+    __device__ __forceinline__ long long chunk(RCtx c, int k) const { return (c >= 0 && k < K) ? c + k : -1; }
 };
 struct SrcMatMN {  // X(row, k) = p[k*ld + row]   (transposed use of a [K][rows] matrix)
     static constexpr bool kMN = true, kHasLo = true;
+    using RCtx = long long;
     const bf16* hi; const bf16* lo; int rows, K; long long ld;
-    __device__ __forceinline__ long long chunk(int row, int k) const { return (row < rows && k < K) ? k * ld + row : -1; }
+    __device__ __forceinline__ RCtx rctx(int row) const { return row < rows ? row : -1; }
+    __device__ __forceinline__ long long chunk(RCtx c, int k) const { return (c >= 0 && k < K) ? k * ld + c : -1; }
 };
 struct SrcRowGatherK {   // X(r, k) = p[src[r]*ld + k]
     static constexpr bool kMN = false, kHasLo = true;
+    using RCtx = long long;
     const bf16* hi; const bf16* lo; const int* src; int rows, K; long long ld;
-    __device__ __forceinline__ long long chunk(int row, int k) const {
-        if (row >= rows || k >= K) return -1;
+    __device__ __forceinline__ RCtx rctx(int row) const {
+        if (row >= rows) return -1;
         const int s = __ldg(src + row);
-        return s >= 0 ? s * ld + k : -1;
+        return s >= 0 ? s * ld : -1;
     }
+    __device__ __forceinline__ long long chunk(RCtx c, int k) const { return (c >= 0 && k < K) ? c + k : -1; }
 };
 struct SrcRowGatherMN {  // X(j, r) = p[src[r]*ld + j]
     static constexpr bool kMN = true, kHasLo = true;
+    using RCtx = long long;
     const bf16* hi; const bf16* lo; const int* src; int rows, K; long long ld;   // rows: width limit (j); K: gathered rows
-    __device__ __forceinline__ long long chunk(int row, int k) const {
-        if (row >= rows || k >= K) return -1;
+    __device__ __forceinline__ RCtx rctx(int row) const { return row < rows ? row : -1; }
+    __device__ __forceinline__ long long chunk(RCtx c, int k) const {
+        if (c < 0 || k >= K) return -1;
         const int s = __ldg(src + k);
-        return s >= 0 ? s * ld + row : -1;
+        return s >= 0 ? s * ld + c : -1;
     }
 };
-// NHWC im2col, K-major:  row m = (frame, oy, ox), k = (ky, kx, c); IC % 8 == 0
-template <int IH, int IW, int IC, int OH, int OW, int KH, int KW, int S, bool HASLO = true>
-struct SrcConvK {
-    static constexpr bool kMN = false, kHasLo = HASLO;
-    const bf16* hi; const bf16* lo; int nframes;
-    __device__ __forceinline__ long long chunk(int m, int k) const {
-        if (m >= nframes * OH * OW || k >= KH * KW * IC) return -1;
+// NHWC im2col:  pixel m = (frame, oy, ox),  kernel index kk = (ky, kx, c); IC % 8 == 0.  offset = pix(m) + tap(kk)
+template <int IH, int IW, int IC, int OH, int OW, int KH, int KW, int S>
+struct ConvGeom {
+    __device__ static __forceinline__ long long pix(int m, int nframes) {
+        if (m >= nframes * OH * OW) return -1;
         const int f = m / (OH * OW), p = m - f * (OH * OW), oy = p / OW, ox = p - oy * OW;
-        const int tap = k / IC, c = k - tap * IC, ky = tap / KW, kx = tap - ky * KW;
-        return (((long long)f * IH + S * oy + ky) * IW + S * ox + kx) * IC + c;
+        return (((long long)f * IH + S * oy) * IW + S * ox) * IC;
+    }
+    __device__ static __forceinline__ long long tap(int kk) {
+        if (kk >= KH * KW * IC) return -1;
+        const int t = kk / IC, c = kk - t * IC, ky = t / KW, kx = t - ky * KW;
+        return (long long)(ky * IW + kx) * IC + c;
     }
 };
-// the same im2col as an MN-major operand (wgrad): row = k index (8 consecutive channels), k = pixel m
 template <int IH, int IW, int IC, int OH, int OW, int KH, int KW, int S, bool HASLO = true>
-struct SrcConvMN {
-    static constexpr bool kMN = true, kHasLo = HASLO;
+struct SrcConvK {    // K-major: row = pixel, k = kernel index
+    static constexpr bool kMN = false, kHasLo = HASLO;
+    using G = ConvGeom<IH, IW, IC, OH, OW, KH, KW, S>;
+    using RCtx = long long;
     const bf16* hi; const bf16* lo; int nframes;
-    __device__ __forceinline__ long long chunk(int row, int k) const {
-        SrcConvK<IH, IW, IC, OH, OW, KH, KW, S, HASLO> g{hi, lo, nframes};
-        return g.chunk(k, row);
+    __device__ __forceinline__ RCtx rctx(int m) const { return G::pix(m, nframes); }
+    __device__ __forceinline__ long long chunk(RCtx c, int k) const {
+        const long long t = G::tap(k);
+        return (c >= 0 && t >= 0) ? c + t : -1;
+    }
+};
+template <int IH, int IW, int IC, int OH, int OW, int KH, int KW, int S, bool HASLO = true>
+struct SrcConvMN {   // MN-major (wgrad): row = kernel index (8 consecutive channels), k = pixel
+    static constexpr bool kMN = true, kHasLo = HASLO;
+    using G = ConvGeom<IH, IW, IC, OH, OW, KH, KW, S>;
+    using RCtx = long long;
+    const bf16* hi; const bf16* lo; int nframes;
+    __device__ __forceinline__ RCtx rctx(int kk) const { return G::tap(kk); }
+    __device__ __forceinline__ long long chunk(RCtx c, int m) const {
+        const long long p = G::pix(m, nframes);
+        return (c >= 0 && p >= 0) ? c + p : -1;
     }
 };
 // dgrad gather (stride-1, or one parity class of a stride-2 conv): m = (frame, y', x') on GH x GW,
@@ -335,14 +415,19 @@ struct SrcConvMN {
 template <int GH, int GW, int OH, int OW, int OC, int JH, int JW>
 struct SrcDgradK {
     static constexpr bool kMN = false, kHasLo = true;
+    struct RCtx { long long base; int y, x; };
     const bf16* hi; const bf16* lo; int nframes;
-    __device__ __forceinline__ long long chunk(int m, int k) const {
-        if (m >= nframes * GH * GW || k >= JH * JW * OC) return -1;
+    __device__ __forceinline__ RCtx rctx(int m) const {
+        if (m >= nframes * GH * GW) return RCtx{-1, 0, 0};
         const int f = m / (GH * GW), p = m - f * (GH * GW), y = p / GW, x = p - y * GW;
-        const int tap = k / OC, c = k - tap * OC, jy = tap / JW, jx = tap - jy * JW;
-        const int oy = y - jy, ox = x - jx;
+        return RCtx{(((long long)f * OH + y) * OW + x) * OC, y, x};
+    }
+    __device__ __forceinline__ long long chunk(const RCtx& c, int k) const {
+        if (c.base < 0 || k >= JH * JW * OC) return -1;
+        const int tap = k / OC, ch = k - tap * OC, jy = tap / JW, jx = tap - jy * JW;
+        const int oy = c.y - jy, ox = c.x - jx;
         if (oy < 0 || oy >= OH || ox < 0 || ox >= OW) return -1;
-        return (((long long)f * OH + oy) * OW + ox) * OC + c;
+        return c.base - (long long)(jy * OW + jx) * OC + ch;
     }
 };
 

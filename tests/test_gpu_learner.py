@@ -144,3 +144,22 @@ def test_consecutive_updates_vs_reference_golden(golden_dir, name, script, backe
         assert max(e_q, e_qn, e_qt) < tol_act
         assert abs(loss - float(g[f"k{k}_out_loss"])) < (2e-5 if backend == 0 else 2e-2) * max(1.0, abs(loss))
         assert e_p < max(2e-5, tol_p)
+
+
+def test_stepwise_recurrence_path_still_matches(golden_dir):
+    """The per-step launch path (used for B > 64) against the same golden updates as the persistent kernel."""
+    from r2d2_b200 import _lib
+    prev = _lib.lib().r2d2_set_persistent_recurrence(0)
+    try:
+        g = np.load(os.path.join(golden_dir, "learner_cfg0.npz"))
+        batch_size, K, bl, ls, bi, fs, seed0, num_blocks = (int(x) for x in g["meta"])
+        rb, _ = build_oracle_replay(CFG0_SCRIPT, num_blocks, batch_size, bl, ls, bi, fs)
+        dl = _mk_learner(batch_size, bi + ls + fs, Lmax=ls, F=fs, params=init_params(A, seed=3))
+        for k in range(K):
+            dl.update(dl.prepare(_torch_batch(sample_with_seed(rb, seed0 + k))))
+            torch.cuda.synchronize()
+            rows = int(dl.rows.item())
+            assert np.abs(dl.td[:rows].cpu().numpy() - g[f"k{k}_out_td"]).max() < 1e-4
+            assert np.abs(dl.prio.cpu().numpy() - g[f"k{k}_out_priorities"]).max() < 1e-4
+    finally:
+        _lib.lib().r2d2_set_persistent_recurrence(prev)
