@@ -169,8 +169,10 @@ int r2d2_set_gemm_backend(int backend);
 int r2d2_debug_gemm(int backend, int ubn, int a_major, int b_major, int M, int N, int K, const float* A, const float* B,
                     float* C, int splits, void* stream);
 
-/* Precision of the v2 (pre-split bf16 hi/lo) data path: 0 = bf16x3 products (parity, default), 1 = plain bf16. */
-int r2d2_set_fast_math(int fast);
+/* Precision mode of the tensor-core path: 0 = strict (bf16x3 split products everywhere, default), 1 = fast (plain
+ * bf16 products), 2 = balanced (hi+lo only for the weight operands of the encoder contractions; recurrence, input
+ * projection and dueling head stay strict).  Returns the previous mode. */
+int r2d2_set_fast_math(int mode);
 /* Test entry for the v2 kernel: operands as bf16 hi/lo planes; major 1 = [K][rows] storage (MN-major descriptors). */
 int r2d2_debug_gemm2(int ubn, int a_major, int b_major, int M, int N, int K, const void* a_hi, const void* a_lo,
                      const void* b_hi, const void* b_lo, float* C, int splits, void* stream);

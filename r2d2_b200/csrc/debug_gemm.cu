@@ -46,10 +46,12 @@ int r2d2_set_gemm_backend(int backend) {
     return prev;
 }
 
-/* v2 data path precision: 0 = bf16x3 split products (parity mode, default), 1 = plain bf16 (fast mode). */
-int r2d2_set_fast_math(int fast) {
+/* Precision mode of the tensor-core path: 0 = strict (bf16x3 split products everywhere, default), 1 = fast (plain
+ * bf16 products), 2 = balanced (hi+lo only for weight operands of the encoder contractions; recurrence, input
+ * projection and head stay strict).  Returns the previous mode. */
+int r2d2_set_fast_math(int mode) {
     int prev = g_fast_math;
-    g_fast_math = fast ? 1 : 0;
+    if (mode >= 0 && mode <= 2) g_fast_math = mode;
     return prev;
 }
 

@@ -504,12 +504,12 @@ static cudaError_t colsum_f32(const float* X, int M, int N, int kind, float* g, 
 
 using namespace r2d2;
 
-template <int UBN, class AS, class BS>
+template <int UBN, int POL = LO_STRICT, class AS, class BS>
 static cudaError_t wgrad2(const AS& a, const BS& b, int M, int N, int K, int splits, int kind, r2d2_net* net, float* grads,
                           const int64_t* d_off, float scale, cudaStream_t s) {
     if ((size_t)splits * M * N > net->ws_floats) return cudaErrorInvalidValue;
     Epi2Partial ep{net->ws, M, N};
-    cudaError_t e = launch_umma2<UBN>(a, b, ep, M, N, K, splits, s);
+    cudaError_t e = launch_umma2<UBN, POL>(a, b, ep, M, N, K, splits, s);
     if (e != cudaSuccess) return e;
     const int64_t tot = (int64_t)M * N;
     reduce_route_kernel<<<cdiv(tot, 256), 256, 0, s>>>(net->ws, splits, M, N, kind, grads, d_off, net->A, net->C, scale);
@@ -584,7 +584,7 @@ int r2d2_net_create(int B, int T, int C, int A, int Lmax, int max_forward, r2d2_
     R2D2_CUDA_CHECK(cudaMalloc(&n->len_full, B * sizeof(int)));
     R2D2_CUDA_CHECK(cudaMalloc(&n->len_learn, B * sizeof(int)));
     R2D2_CUDA_CHECK(cudaMalloc(&n->d_rows, sizeof(int)));
-    R2D2_CUDA_CHECK(cudaMalloc(&n->rec_bar, 2 * sizeof(unsigned int)));
+    R2D2_CUDA_CHECK(cudaMalloc(&n->rec_bar, 64 * sizeof(unsigned int)));
     rc |= alloc_s(&n->dhid, (size_t)n->Rmax * 2 * H); rc |= alloc_s(&n->DG, TB * G4); rc |= alloc_s(&n->dlat, NF * LATENT);
     rc |= alloc_s(&n->dpre3, NF * FLAT3); rc |= alloc_s(&n->dpre2, NF * 5184); rc |= alloc_s(&n->dpre1T, NF * 12800);
     rc |= alloc_f(&n->dH, TB * H); rc |= alloc_f(&n->dhrec, (size_t)kRecSplits * B * H); rc |= alloc_f(&n->dcrec, (size_t)B * H);
@@ -644,7 +644,7 @@ static cudaError_t conv1_forward(r2d2_net* n, int which, const float* params, cu
     const Packed& pk = n->pk[which];
     SrcMatK b{pk.W1s.hi, pk.W1s.lo, 32, 64 * CH, 64 * CH};
     Epi2BiasSplit<true> e{n->ac[which].act1, params + n->off[P_C1B], n->NF * 400, 32, 32, 1.f / 255.f};
-    return launch_umma2<32>(a, b, e, n->NF * 400, 32, 64 * CH, 1, s);
+    return launch_umma2<32, LO_WEIGHT_B>(a, b, e, n->NF * 400, 32, 64 * CH, 1, s);
 }
 // conv1 of BOTH slots in one launch: columns 0-31 -> online act1, 32-63 -> target act1 (same frames, stacked weights)
 struct Epi2Conv1Pair {
@@ -668,7 +668,7 @@ static cudaError_t conv1_forward_pair(r2d2_net* n, const float* p0, const float*
     SrcConvK<21, 21, 16 * CH, 20, 20, 2, 2, 1, false> a{n->s2d, nullptr, n->NF};
     SrcMatK b{n->W1both.hi, n->W1both.lo, 64, 64 * CH, 64 * CH};
     Epi2Conv1Pair e{n->ac[0].act1, n->ac[1].act1, p0 + n->off[P_C1B], p1 + n->off[P_C1B], n->NF * 400, 1.f / 255.f};
-    return launch_umma2<64>(a, b, e, n->NF * 400, 64, 64 * CH, 1, s);
+    return launch_umma2<64, LO_WEIGHT_B>(a, b, e, n->NF * 400, 64, 64 * CH, 1, s);
 }
 template <int CH>
 static cudaError_t conv1_wgrad(r2d2_net* n, float* grads, cudaStream_t s) {
@@ -676,7 +676,7 @@ static cudaError_t conv1_wgrad(r2d2_net* n, float* grads, cudaStream_t s) {
     SrcMatK a{n->dpre1T.hi, n->dpre1T.lo, 32, NP, NP};
     SrcConvMN<21, 21, 16 * CH, 20, 20, 2, 2, 1, false> b{n->s2d, nullptr, n->NF};
     const int splits = (NP + 4095) / 4096;
-    return wgrad2<(CH == 4 ? 256 : 64)>(a, b, 32, 64 * CH, NP, splits, R_C1, n, grads, g_doff[n], 1.f / 255.f, s);
+    return wgrad2<(CH == 4 ? 256 : 64), LO_NO_WEIGHT>(a, b, 32, 64 * CH, NP, splits, R_C1, n, grads, g_doff[n], 1.f / 255.f, s);
 }
 
 // frames -> space-to-depth bf16 (once per batch, shared by both slots) + row maps + h0 split
@@ -704,19 +704,19 @@ static int net_encode(r2d2_net* n, int which, const FwdArgs& fa, cudaStream_t s,
         SrcConvK<20, 20, 32, 9, 9, 4, 4, 2> a{ac.act1.hi, ac.act1.lo, NF};
         SrcMatK b{pk.W2p.hi, pk.W2p.lo, 64, 512, 512};
         Epi2BiasSplit<true> e{ac.act2, params + off[P_C2B], NF * 81, 64, 64, 1.f};
-        R2D2_CUDA_CHECK((launch_umma2<64>(a, b, e, NF * 81, 64, 512, 1, s)));
+        R2D2_CUDA_CHECK((launch_umma2<64, LO_WEIGHT_B>(a, b, e, NF * 81, 64, 512, 1, s)));
     }
     {
         SrcConvK<9, 9, 64, 7, 7, 3, 3, 1> a{ac.act2.hi, ac.act2.lo, NF};
         SrcMatK b{pk.W3p.hi, pk.W3p.lo, 64, 576, 576};
         Epi2BiasSplit<true> e{ac.act3, params + off[P_C3B], NF * 49, 64, 64, 1.f};
-        R2D2_CUDA_CHECK((launch_umma2<64>(a, b, e, NF * 49, 64, 576, 1, s)));
+        R2D2_CUDA_CHECK((launch_umma2<64, LO_WEIGHT_B>(a, b, e, NF * 49, 64, 576, 1, s)));
     }
     {
         SrcMatK a{ac.act3.hi, ac.act3.lo, NF, FLAT3, FLAT3};
         SrcMatK b{pk.Wfcp.hi, pk.Wfcp.lo, LATENT, FLAT3, FLAT3};
         Epi2Latent e{ac.U, params + off[P_FCB], B, T, KU};
-        R2D2_CUDA_CHECK((launch_umma2<128>(a, b, e, NF, LATENT, FLAT3, 1, s)));
+        R2D2_CUDA_CHECK((launch_umma2<128, LO_WEIGHT_B>(a, b, e, NF, LATENT, FLAT3, 1, s)));
     }
     {   // LSTM input projection for all steps at once (hoisted out of the recurrence)
         SrcMatK a{ac.U.hi, ac.U.lo, T * B, KU, KU};
@@ -753,7 +753,7 @@ static int net_recurrence(r2d2_net* n, int which, const float* hidden, cudaStrea
         }
         P.c0 = hidden + H; P.ld_c0 = 2 * H; P.len = n->len_full; P.bar = n->rec_bar; P.B = B; P.T = T;
         P.net_base = which == 2 ? 0 : which;
-        P.fast = g_fast_math;
+        P.fast = g_fast_math == 1;
         R2D2_CUDA_CHECK(launch_rec_fwd(P, which == 2 ? 2 : 1, s));
         return R2D2_OK;
     }
@@ -908,29 +908,29 @@ int r2d2_net_backward(r2d2_net* n, const float* params, const float* dq, float* 
     {
         SrcMatMN a{n->dlat.hi, n->dlat.lo, LATENT, NF, LATENT};
         SrcMatMN b{ac.act3.hi, ac.act3.lo, FLAT3, NF, FLAT3};
-        R2D2_CUDA_CHECK((wgrad2<128>(a, b, LATENT, FLAT3, NF, 2, R_FC, n, grads, d_off, 1.f, s)));
+        R2D2_CUDA_CHECK((wgrad2<128, LO_NO_WEIGHT>(a, b, LATENT, FLAT3, NF, 2, R_FC, n, grads, d_off, 1.f, s)));
         R2D2_CUDA_CHECK(colsum_split(ro(n->dlat), NF, LATENT, B_PLAIN, grads, off[P_FCB], 0, A, n->colws, s));
         SrcMatK a2{n->dlat.hi, n->dlat.lo, NF, LATENT, LATENT};
         SrcMatMN b2{pk.Wfcp.hi, pk.Wfcp.lo, FLAT3, LATENT, FLAT3};
         Epi2MaskedSplit e{n->dpre3, ro(ac.act3), NF, FLAT3, FLAT3};
-        R2D2_CUDA_CHECK((launch_umma2<128>(a2, b2, e, NF, FLAT3, LATENT, 1, s)));
+        R2D2_CUDA_CHECK((launch_umma2<128, LO_WEIGHT_B>(a2, b2, e, NF, FLAT3, LATENT, 1, s)));
     }
     {   // conv3
         const int K3 = NF * 49;
         SrcMatMN a{n->dpre3.hi, n->dpre3.lo, 64, K3, 64};
         SrcConvMN<9, 9, 64, 7, 7, 3, 3, 1> b{ac.act2.hi, ac.act2.lo, NF};
-        R2D2_CUDA_CHECK((wgrad2<64>(a, b, 64, 576, K3, (K3 + 4095) / 4096, R_C3, n, grads, d_off, 1.f, s)));
+        R2D2_CUDA_CHECK((wgrad2<64, LO_NO_WEIGHT>(a, b, 64, 576, K3, (K3 + 4095) / 4096, R_C3, n, grads, d_off, 1.f, s)));
         R2D2_CUDA_CHECK(colsum_split(ro(n->dpre3), K3, 64, B_PLAIN, grads, off[P_C3B], 0, A, n->colws, s));
         SrcDgradK<9, 9, 7, 7, 64, 3, 3> a2{n->dpre3.hi, n->dpre3.lo, NF};
         SrcMatK b2{pk.W3d.hi, pk.W3d.lo, 64, 576, 576};
         Epi2MaskedSplit e{n->dpre2, ro(ac.act2), NF * 81, 64, 64};
-        R2D2_CUDA_CHECK((launch_umma2<64>(a2, b2, e, NF * 81, 64, 576, 1, s)));
+        R2D2_CUDA_CHECK((launch_umma2<64, LO_WEIGHT_B>(a2, b2, e, NF * 81, 64, 576, 1, s)));
     }
     {   // conv2
         const int K2 = NF * 81;
         SrcMatMN a{n->dpre2.hi, n->dpre2.lo, 64, K2, 64};
         SrcConvMN<20, 20, 32, 9, 9, 4, 4, 2> b{ac.act1.hi, ac.act1.lo, NF};
-        R2D2_CUDA_CHECK((wgrad2<64>(a, b, 64, 512, K2, (K2 + 4095) / 4096, R_C2, n, grads, d_off, 1.f, s)));
+        R2D2_CUDA_CHECK((wgrad2<64, LO_NO_WEIGHT>(a, b, 64, 512, K2, (K2 + 4095) / 4096, R_C2, n, grads, d_off, 1.f, s)));
         R2D2_CUDA_CHECK(colsum_split(ro(n->dpre2), K2, 64, B_PLAIN, grads, off[P_C2B], 0, A, n->colws, s));
         {   // stride-2 dgrad as four stride-1 problems (output parity classes), ONE launch: blockIdx.x = class, so the
             // CTAs that write interleaved pixels of the same dpre1T sectors run together and merge in L2
@@ -942,7 +942,7 @@ int r2d2_net_backward(r2d2_net* n, const float* params, const float* dq, float* 
                 b2.f[cls] = SrcMatK{pk.W2d.hi + wo, pk.W2d.lo + wo, 32, 256, 256};
                 e.f[cls] = Epi2DgradS2T{n->dpre1T, ro(ac.act1), NF, cls >> 1, cls & 1, (long long)NF * 400};
             }
-            R2D2_CUDA_CHECK((launch_umma2_multi<32, 4>(a2, b2, e, NF * 100, 256, s)));
+            R2D2_CUDA_CHECK((launch_umma2_multi<32, 4, LO_WEIGHT_B>(a2, b2, e, NF * 100, 256, s)));
         }
     }
     {   // conv1 (weights only; frames need no gradient)

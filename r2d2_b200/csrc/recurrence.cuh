@@ -3,12 +3,14 @@
 // Replaces T per-step GEMM launches of the stepwise path (net.cu: net_recurrence) for batches of <= 64 sequences.
 //   grid = 64 CTAs per network; CTA (net, s) owns gate columns [32 s, 32 s + 32) = hidden units [8 s, 8 s + 8)
 //   * its W_hh slice [32][512] (bf16 hi+lo, 64 KB) is staged into shared memory ONCE and stays there;
-//   * per step:  acquire the network's step barrier  ->  cp.async h_{t-1} [64][512] hi+lo (128 KB, from L2, in 8
-//     k-blocks with their own mbarriers so the MMAs start on the first block)  ->  96 tcgen05.mma (M=64, N=32, K=16,
-//     bf16x3) into a 32-column TMEM accumulator  ->  epilogue: 128 threads each own (sequence b, 4 hidden units):
-//     gates = acc + XP[t], LSTM cell with the cell state c and the previous h held in REGISTERS across steps,
-//     stores h_t (split), c_t, gates  ->  __threadfence + release-arrive on the network's barrier counter.
-//   The two networks never wait for each other (separate counters): their step latencies overlap across SMs.
+//   * per step, warp w of the 8 producer warps owns k-block w (hidden units [64w, 64w+64)): its lane 0 acquires the
+//     counter of that k-block (incremented by the 8 CTAs that produce those units), the warp cp.asyncs the 64 x 64
+//     hi+lo tile of h_{t-1} (16 KB) and arms full[w]  ->  96 tcgen05.mma (M=64, N=32, K=16, bf16x3) into a
+//     32-column TMEM accumulator, consumed k-block by k-block as they land  ->  epilogue: 128 threads each own
+//     (sequence b, 4 hidden units): gates = acc + XP[t], LSTM cell with c and the previous h held in REGISTERS
+//     across steps, stores h_t (split), c_t, gates  ->  CTA barrier + one release-add on the counter of its k-block.
+//   Fine-grained (per 64-unit) flags let loads and MMAs of early k-blocks overlap the wait for the slowest producer;
+//   the two networks use separate counters, so their step latencies overlap across SMs.
 // UMMA M=64 accumulator layout (cta_group::1): row m lives in TMEM lane (m & 15) + 32 * (m >> 4), i.e. the first 16
 // lanes of each 32-lane quadrant (cute tmem_frg: Shape<(16,4),N> : Stride<(1,32),128>).
 #pragma once
@@ -30,7 +32,7 @@ struct RecFwdParams {
     float* Gs[2];                             // [T*B][2048] or nullptr
     const float* c0; int ld_c0;               // stored cell state (hidden + H, row stride 2H)
     const int* len;                           // [B] steps each sequence advances
-    unsigned int* bar;                        // [2] step barrier counters, zero before launch
+    unsigned int* bar;                        // [2][8] per-network, per-k-block step counters, zero before launch
     int B, T, net_base;                       // net_base: slot of the first CTA group (single-network launches)
     int fast;
 };
@@ -65,7 +67,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) rec_fwd_kernel(const RecFwdPara
     const bool want_lo = !P.fast;
 
     if (tid == 0) {
-        for (int kb = 0; kb < REC_KB; ++kb) mbar_init(smem_u32(&bars[kb]), UM_PRODUCERS / 32);
+        for (int kb = 0; kb < REC_KB; ++kb) mbar_init(smem_u32(&bars[kb]), 1);      // armed by the warp that owns k-block kb
         mbar_init(smem_u32(&bars[REC_KB]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -106,8 +108,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) rec_fwd_kernel(const RecFwdPara
                 h_reg[u] = split_load(P.Hhi[net], P.Hlo[net], (size_t)b * REC_H + j0 + u);
             }
         }
-        // A staging plan: per k-block 64 rows x 8 chunks = 512 chunk slots -> 2 per thread (x2 planes)
-        const int a_row0 = tid >> 3, a_j = tid & 7;        // rows a_row0 and a_row0 + 32
+        // A staging plan: warp w stages k-block w (64 rows x 8 chunks x 2 planes): lane -> chunk j = lane & 7, rows (lane >> 3) + 4 i
+        const int a_j = lane & 7, a_r0 = lane >> 3;
+        unsigned int* my_flag = P.bar + net * REC_KB + warp;                 // producers of hidden units [64 warp, +64)
         for (int t = 0; t < T; ++t) {
             float4 xp[4];
             if (owner) {
@@ -115,37 +118,29 @@ __global__ void __launch_bounds__(UM_THREADS, 1) rec_fwd_kernel(const RecFwdPara
 #pragma unroll
                 for (int q = 0; q < 4; ++q) xp[q] = __ldg(xsrc + q);
             }
-            if (t > 0) {                                   // all CTAs of this network have published h_{t-1}
-                if (tid == 0) {
-                    const unsigned int target = (unsigned int)(REC_CTAS_PER_NET * t);
-                    for (uint32_t spins = 0; ld_acquire_u32(P.bar + net) < target; ++spins)
+            if (t > 0) {                                   // the 8 CTAs owning this k-block have published h_{t-1}
+                if (lane == 0) {
+                    const unsigned int target = (unsigned int)(8 * t);
+                    for (uint32_t spins = 0; ld_acquire_u32(my_flag) < target; ++spins)
                         if (spins > (1u << 28)) __trap();
                 }
-                asm volatile("bar.sync 1, %0;" ::"n"(UM_PRODUCERS) : "memory");
+                __syncwarp();
             }
-            // h_{t-1} = HsX block t  -> A tiles, one cp.async group per k-block
-            const bf16* hsrc_hi = P.Hhi[net] + (size_t)t * B * REC_H;
-            const bf16* hsrc_lo = P.Hlo[net] + (size_t)t * B * REC_H;
+            {
+                const int kb = warp;
+                const bf16* hsrc_hi = P.Hhi[net] + (size_t)t * B * REC_H + kb * 64 + a_j * 8;     // HsX block t = h_{t-1}
+                const bf16* hsrc_lo = P.Hlo[net] + (size_t)t * B * REC_H + kb * 64 + a_j * 8;
 #pragma unroll
-            for (int kb = 0; kb < REC_KB; ++kb) {
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    const int row = a_row0 + 32 * r;
+                for (int i = 0; i < 16; ++i) {
+                    const int row = a_r0 + 4 * i;
                     const uint32_t dst = (uint32_t)(kb * REC_A_TILE + (row >> 3) * 1024 + (row & 7) * 128 + ((a_j ^ (row & 7)) << 4));
                     const bool ok = row < B;
-                    const size_t src = ok ? (size_t)row * REC_H + kb * 64 + a_j * 8 : 0;
+                    const size_t src = ok ? (size_t)row * REC_H : 0;
                     cp_async16(sA + dst, hsrc_hi + src, ok);
                     if (want_lo) cp_async16(sA + REC_KB * REC_A_TILE + dst, hsrc_lo + src, ok);
                 }
                 cp_async_commit();
-            }
-#pragma unroll
-            for (int kb = 0; kb < REC_KB; ++kb) {
-                switch (REC_KB - 1 - kb) {                 // wait until group kb has landed
-                    case 7: cp_async_wait<7>(); break; case 6: cp_async_wait<6>(); break; case 5: cp_async_wait<5>(); break;
-                    case 4: cp_async_wait<4>(); break; case 3: cp_async_wait<3>(); break; case 2: cp_async_wait<2>(); break;
-                    case 1: cp_async_wait<1>(); break; default: cp_async_wait<0>(); break;
-                }
+                cp_async_wait<0>();
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&bars[kb]));
@@ -188,9 +183,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) rec_fwd_kernel(const RecFwdPara
                 h_reg[3] = __uint_as_float(hh[1] & 0xFFFF0000u) + __uint_as_float(ll[1] & 0xFFFF0000u);
             }
             tc_fence_before();
-            __threadfence();                               // publish h_t before the arrive
-            asm volatile("bar.sync 1, %0;" ::"n"(UM_PRODUCERS) : "memory");
-            if (tid == 0) red_release_add(P.bar + net, 1u);
+            asm volatile("bar.sync 1, %0;" ::"n"(UM_PRODUCERS) : "memory");          // every owner's stores precede ...
+            if (tid == 0) red_release_add(P.bar + net * REC_KB + (slice >> 3), 1u);   // ... this gpu-scope release (cumulative)
         }
     } else {
         // ---------------------------------------------------------------- MMA issuer
@@ -235,7 +229,7 @@ static inline cudaError_t launch_rec_fwd(const RecFwdParams& P, int nets, cudaSt
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    cudaError_t e = cudaMemsetAsync(P.bar, 0, 2 * sizeof(unsigned int), s);
+    cudaError_t e = cudaMemsetAsync(P.bar, 0, 2 * REC_KB * sizeof(unsigned int), s);
     if (e != cudaSuccess) return e;
     void* args[] = {(void*)&P};
     return cudaLaunchCooperativeKernel((const void*)rec_fwd_kernel, dim3(nets * REC_CTAS_PER_NET), dim3(UM_THREADS), args, REC_SMEM, s);

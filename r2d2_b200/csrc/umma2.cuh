@@ -133,12 +133,12 @@ template <class F, int N> __device__ __forceinline__ const F& sel_z(const Multi<
 template <class F> struct IsMulti { static constexpr bool value = false; };
 template <class F, int N> struct IsMulti<Multi<F, N>> { static constexpr bool value = true; };
 
-template <int BN, bool FAST, class ASrcT, class BSrcT, class EpiT>
+template <int BN, bool WANT_A_LO, bool WANT_B_LO, class ASrcT, class BSrcT, class EpiT>
 __global__ void __launch_bounds__(UM_THREADS, R2D2_STAGE_BUDGET_KB <= 104 ? 2 : 1)
 umma2_kernel(const ASrcT a_, const BSrcT b_, const EpiT ep_, int K, int k_per_split) {
     using ASrc = typename std::remove_cv<typename std::remove_reference<decltype(sel_z(a_, 0))>::type>::type;
     using BSrc = typename std::remove_cv<typename std::remove_reference<decltype(sel_z(b_, 0))>::type>::type;
-    constexpr bool A_LO = ASrc::kHasLo && !FAST, B_LO = BSrc::kHasLo && !FAST;
+    constexpr bool A_LO = ASrc::kHasLo && WANT_A_LO, B_LO = BSrc::kHasLo && WANT_B_LO;
     using Cfg = Umma2Cfg<BN, A_LO, B_LO>;
     constexpr int kStages = Cfg::kStages;
     static_assert(BN == 16 || BN == 32 || BN == 64 || BN == 128 || BN == 256, "UMMA N / TMEM columns");
@@ -266,69 +266,56 @@ umma2_kernel(const ASrcT a_, const BSrcT b_, const EpiT ep_, int K, int k_per_sp
     }
 }
 
-extern int g_fast_math;   // 0: bf16x3 (parity), 1: plain bf16 (fast)
+// Precision policy.  g_fast_math: 0 = strict (every split operand contributes hi and lo: bf16x3 products),
+// 1 = fast (hi planes only: plain bf16 products), 2 = balanced: hi+lo only for WEIGHT operands of the encoder
+// contractions (activations / gradients go in as single bf16; their rounding averages out over K >= 256 terms),
+// while the recurrence, input projection and dueling head stay strict.  A call site states what its operands are:
+enum LoPolicy { LO_STRICT = 0,   // keep both lo planes unless the mode is fast
+                LO_WEIGHT_B = 1, // B is a weight matrix, A an activation/gradient tensor
+                LO_NO_WEIGHT = 2 /* neither operand is a weight (weight-gradient contractions) */ };
+extern int g_fast_math;
 
-template <int BN, class ASrc, class BSrc, class Epi>
-static inline cudaError_t launch_umma2(const ASrc& a, const BSrc& b, const Epi& ep, int M, int N, int K, int splits, cudaStream_t s) {
-    if (M <= 0 || N <= 0) return cudaSuccess;
+template <int BN, bool AL, bool BL, class ASrc, class BSrc, class Epi>
+static inline cudaError_t launch_umma2_inst(const ASrc& a, const BSrc& b, const Epi& ep, dim3 grid, int K, int k_per_split, cudaStream_t s) {
     using A0 = typename std::remove_cv<typename std::remove_reference<decltype(sel_z(a, 0))>::type>::type;
     using B0 = typename std::remove_cv<typename std::remove_reference<decltype(sel_z(b, 0))>::type>::type;
-    int k_per_split = (K + splits - 1) / splits;
-    k_per_split = (k_per_split + UM_BK - 1) / UM_BK * UM_BK;
-    dim3 grid((N + BN - 1) / BN, (M + UM_BM - 1) / UM_BM, splits);
-    if (g_fast_math) {
-        using Cfg = Umma2Cfg<BN, false, false>;
-        auto kern = umma2_kernel<BN, true, ASrc, BSrc, Epi>;
-        static bool configured = false;
-        if (!configured) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
-            if (e != cudaSuccess) return e;
-            configured = true;
-        }
-        kern<<<grid, UM_THREADS, Cfg::kSmem, s>>>(a, b, ep, K, k_per_split);
-    } else {
-        using Cfg = Umma2Cfg<BN, A0::kHasLo, B0::kHasLo>;
-        auto kern = umma2_kernel<BN, false, ASrc, BSrc, Epi>;
-        static bool configured = false;
-        if (!configured) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
-            if (e != cudaSuccess) return e;
-            configured = true;
-        }
-        kern<<<grid, UM_THREADS, Cfg::kSmem, s>>>(a, b, ep, K, k_per_split);
+    using Cfg = Umma2Cfg<BN, A0::kHasLo && AL, B0::kHasLo && BL>;
+    auto kern = umma2_kernel<BN, AL, BL, ASrc, BSrc, Epi>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+        if (e != cudaSuccess) return e;
+        configured = true;
     }
+    kern<<<grid, UM_THREADS, Cfg::kSmem, s>>>(a, b, ep, K, k_per_split);
     return cudaGetLastError();
 }
 
+template <int BN, int POL, class ASrc, class BSrc, class Epi>
+static inline cudaError_t launch_umma2_grid(const ASrc& a, const BSrc& b, const Epi& ep, dim3 grid, int K, int k_per_split, cudaStream_t s) {
+    if (g_fast_math == 1) return launch_umma2_inst<BN, false, false>(a, b, ep, grid, K, k_per_split, s);
+    if (g_fast_math == 2 && POL == LO_WEIGHT_B) return launch_umma2_inst<BN, false, true>(a, b, ep, grid, K, k_per_split, s);
+    if (g_fast_math == 2 && POL == LO_NO_WEIGHT) return launch_umma2_inst<BN, false, false>(a, b, ep, grid, K, k_per_split, s);
+    return launch_umma2_inst<BN, true, true>(a, b, ep, grid, K, k_per_split, s);
+}
+
+template <int BN, int POL = LO_STRICT, class ASrc, class BSrc, class Epi>
+static inline cudaError_t launch_umma2(const ASrc& a, const BSrc& b, const Epi& ep, int M, int N, int K, int splits, cudaStream_t s) {
+    if (M <= 0 || N <= 0) return cudaSuccess;
+    int k_per_split = (K + splits - 1) / splits;
+    k_per_split = (k_per_split + UM_BK - 1) / UM_BK * UM_BK;
+    dim3 grid((N + BN - 1) / BN, (M + UM_BM - 1) / UM_BM, splits);
+    return launch_umma2_grid<BN, POL>(a, b, ep, grid, K, k_per_split, s);
+}
+
 // one launch over CNT operand sets selected by blockIdx.x (N <= BN: a single N tile per set)
-template <int BN, int CNT, class ASrc, class BSrc, class Epi>
+template <int BN, int CNT, int POL = LO_STRICT, class ASrc, class BSrc, class Epi>
 static inline cudaError_t launch_umma2_multi(const ASrc& a, const Multi<BSrc, CNT>& b, const Multi<Epi, CNT>& ep, int M, int K,
                                              cudaStream_t s) {
     if (M <= 0) return cudaSuccess;
     const int k_per_split = (K + UM_BK - 1) / UM_BK * UM_BK;
     dim3 grid(CNT, (M + UM_BM - 1) / UM_BM, 1);
-    if (g_fast_math) {
-        using Cfg = Umma2Cfg<BN, false, false>;
-        auto kern = umma2_kernel<BN, true, ASrc, Multi<BSrc, CNT>, Multi<Epi, CNT>>;
-        static bool configured = false;
-        if (!configured) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
-            if (e != cudaSuccess) return e;
-            configured = true;
-        }
-        kern<<<grid, UM_THREADS, Cfg::kSmem, s>>>(a, b, ep, K, k_per_split);
-    } else {
-        using Cfg = Umma2Cfg<BN, ASrc::kHasLo, BSrc::kHasLo>;
-        auto kern = umma2_kernel<BN, false, ASrc, Multi<BSrc, CNT>, Multi<Epi, CNT>>;
-        static bool configured = false;
-        if (!configured) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
-            if (e != cudaSuccess) return e;
-            configured = true;
-        }
-        kern<<<grid, UM_THREADS, Cfg::kSmem, s>>>(a, b, ep, K, k_per_split);
-    }
-    return cudaGetLastError();
+    return launch_umma2_grid<BN, POL>(a, b, ep, grid, K, k_per_split, s);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -26,11 +26,11 @@ def _diag(line):
         f.write(line + "\n")
 
 
-BACKENDS = {"bf16x3_parity": 0, "bf16_fast": 1}
+BACKENDS = {"bf16x3_parity": 0, "balanced": 2, "bf16_fast": 1}
 # stage tolerances per precision mode: (latent/hidden/q abs, grad rel, adam abs, td/prio abs)
 # parity mode carries the north-star bar (TD, priorities within 1e-4); fast mode (plain bf16 products) is
 # reported and only sanity-bounded.
-STAGE_TOL = {0: (1e-4, 5e-3, 5e-6, 1e-4), 1: (5e-2, 2e-1, 2.1e-4, 5e-2)}
+STAGE_TOL = {0: (1e-4, 5e-3, 5e-6, 1e-4), 2: (1e-4, 1e-1, 5e-5, 1e-4), 1: (5e-2, 2e-1, 2.1e-4, 5e-2)}
 
 
 @pytest.fixture(params=list(BACKENDS))
@@ -89,7 +89,7 @@ def _stage_compare(tag, dl, d, out, be, fs=5):
     assert e_lat < tol_act and e_h < tol_act, (e_lat, e_h)
     assert max(e_q, e_qn, e_qt) < tol_act
     assert e_td < tol_td and e_pr < tol_td                  # parity mode: the north-star bar (1e-4)
-    assert abs(loss - out["loss"]) < (1e-5 if be == 0 else 1e-2) * max(1.0, abs(out["loss"]))
+    assert abs(loss - out["loss"]) < (1e-5 if be == 0 else (1e-4 if be == 2 else 1e-2)) * max(1.0, abs(out["loss"]))
     assert worst[0][0] < tol_grad, worst[0]
     assert abs(float(dl.norm.item()) - out["grad_norm"]) <= (1e-3 if be == 0 else 1e-1) * out["grad_norm"]
 
@@ -142,7 +142,7 @@ def test_consecutive_updates_vs_reference_golden(golden_dir, name, script, backe
         tol_act, _, tol_p, tol_td = STAGE_TOL[backend]
         assert e_td < tol_td and e_pr < tol_td
         assert max(e_q, e_qn, e_qt) < tol_act
-        assert abs(loss - float(g[f"k{k}_out_loss"])) < (2e-5 if backend == 0 else 2e-2) * max(1.0, abs(loss))
+        assert abs(loss - float(g[f"k{k}_out_loss"])) < (2e-5 if backend == 0 else (2e-4 if backend == 2 else 2e-2)) * max(1.0, abs(loss))
         assert e_p < max(2e-5, tol_p)
 
 
