@@ -203,7 +203,9 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     C = args.channels
     config.obs_shape = (C, 84, 84)
-    _lib.lib().r2d2_set_fast_math(1 if args.fast else 0)
+    if args.fast:
+        args.precision = "fast"
+    _lib.lib().r2d2_set_fast_math({"strict": 0, "fast": 1, "balanced": 2}[args.precision])
 
     model = Network(A, obs_shape=(C, 84, 84))
     model.load_state_dict(init_params(A, in_channels=C, seed=0))
@@ -275,11 +277,13 @@ def run_ours(args):
         e2e = world * B / (ms_e2e * 1e-3)
         line = {"metric": "learner sequences/sec", "value": value, "unit": "sequences/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "bf16 (plain products, fp32 accumulate)" if args.fast else "bf16x3 split products (fp32-equivalent, fp32 accumulate)",
+                "dtype": {"strict": "bf16x3 split products (fp32-equivalent), fp32 accumulate",
+                          "balanced": "bf16 activations x bf16x2 weights in the encoder, bf16x3 elsewhere, fp32 accumulate",
+                          "fast": "bf16 products, fp32 accumulate"}[args.precision],
                 "data": "synthetic",
                 "config": {"workload": f"configs[1]: 1xB200 learner per rank, batch {B}/GPU, b/l/f {BURN}/{LEARN}/{FWD} (T={T}), "
                                        f"{C}x84x84 u8 frames, A={A}, HBM replay of {NUM_BLOCKS} blocks, sum tree 2^20",
-                           "channels": C, "global_batch": world * B, "parallelism": f"dp{world}",
+                           "channels": C, "global_batch": world * B, "parallelism": f"dp{world}", "precision": args.precision,
                            "l2": f"inputs larger than L2: batches are gathered from a {NUM_BLOCKS * replay.blob_bytes / 1e9:.1f} GB HBM "
                                  f"block store; ~1 GB of activations streamed per step"},
                 "clocks": sampler.summary(),
@@ -309,7 +313,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--channels", type=int, default=4, help="frame channels: 4 = BASELINE.json shape, 1 = reference obs_shape")
-    ap.add_argument("--fast", action="store_true", help="plain bf16 products instead of the bf16x3 parity mode")
+    ap.add_argument("--precision", default="strict", choices=["strict", "balanced", "fast"],
+                    help="strict: bf16x3 split products everywhere; balanced: hi+lo only for encoder weight operands; fast: plain bf16")
+    ap.add_argument("--fast", action="store_true", help="same as --precision fast")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -132,6 +132,9 @@ int r2d2_net_backward(r2d2_net* n, const float* params, const float* dq, float* 
 /* Recurrence scheduling: 1 (default) = all T LSTM steps of both networks in ONE persistent cooperative kernel
  * (W_hh slices resident in shared memory, per-network step barriers) for B <= 64; 0 = one launch per step. */
 int r2d2_set_persistent_recurrence(int on);
+/* Debug: device buffer of T*8 uint64 that receives per-step globaltimer stamps of CTA 0 of the persistent recurrence
+ * (poll start, flag acquired, tile staged, MMAs done, epilogue done, released); NULL detaches. */
+int r2d2_debug_rec_trace(void* device_buffer);
 /* Test/debug access to device intermediates (see net.cu for the names). */
 void* r2d2_net_debug_ptr(r2d2_net* n, int which, const char* name);
 

@@ -67,6 +67,7 @@ SIGNATURES = {
     "r2d2_net_forward_pair": (C.c_int, [p] * 14),
     "r2d2_net_backward": (C.c_int, [p, p, p, p, p]),
     "r2d2_set_persistent_recurrence": (C.c_int, [C.c_int]),
+    "r2d2_debug_rec_trace": (C.c_int, [p]),
     "r2d2_net_debug_ptr": (p, [p, C.c_int, C.c_char_p]),
     "r2d2_set_gemm_backend": (C.c_int, [C.c_int]),
     "r2d2_debug_gemm": (C.c_int, [C.c_int] * 7 + [p, p, p, C.c_int, p]),

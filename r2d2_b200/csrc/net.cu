@@ -516,7 +516,8 @@ static cudaError_t wgrad2(const AS& a, const BS& b, int M, int N, int K, int spl
     return cudaGetLastError();
 }
 
-int g_persistent_recurrence = 1;     // 0: per-step launches (also the path for B > 64)
+int g_persistent_recurrence = 1;
+unsigned long long* g_rec_trace = nullptr;   // debug: device buffer [T][8] of step timestamps (r2d2_debug_rec_trace)     // 0: per-step launches (also the path for B > 64)
 
 // device copy of the parameter offsets, kept in a side table keyed by handle
 static std::map<r2d2_net*, int64_t*> g_doff;
@@ -754,6 +755,7 @@ static int net_recurrence(r2d2_net* n, int which, const float* hidden, cudaStrea
         P.c0 = hidden + H; P.ld_c0 = 2 * H; P.len = n->len_full; P.bar = n->rec_bar; P.B = B; P.T = T;
         P.net_base = which == 2 ? 0 : which;
         P.fast = g_fast_math == 1;
+        P.trace = g_rec_trace;
         R2D2_CUDA_CHECK(launch_rec_fwd(P, which == 2 ? 2 : 1, s));
         return R2D2_OK;
     }
@@ -961,6 +963,12 @@ int r2d2_set_persistent_recurrence(int on) {
     int prev = g_persistent_recurrence;
     g_persistent_recurrence = on ? 1 : 0;
     return prev;
+}
+
+/* debug: attach a device buffer of T*8 uint64 receiving globaltimer stamps of CTA 0 of the persistent recurrence */
+int r2d2_debug_rec_trace(void* device_buffer) {
+    g_rec_trace = (unsigned long long*)device_buffer;
+    return R2D2_OK;
 }
 
 /* test/debug access to intermediates (bf16 planes are named "<tensor>.hi" / "<tensor>.lo") */

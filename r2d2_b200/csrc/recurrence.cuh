@@ -22,6 +22,8 @@ constexpr int REC_H = 512, REC_G4 = 2048, REC_SLICE = 32, REC_CTAS_PER_NET = REC
 constexpr int REC_KB = REC_H / UM_BK;                                                              // 8 k-blocks of 64
 constexpr int REC_A_TILE = 64 * UM_BK * 2;          // 8 KB  (64 rows x 64 k bf16)
 constexpr int REC_B_TILE = REC_SLICE * UM_BK * 2;   // 4 KB
+constexpr int REC_NACC = 1;                         // TMEM accumulators the MMAs of a step rotate over (1: rotating is slower, measured)
+constexpr int REC_TMEM_COLS = 32;                   // >= REC_NACC * 32, power of two
 constexpr int REC_SMEM = 2 * REC_KB * (REC_A_TILE + REC_B_TILE) + 1024 + 256;
 
 struct RecFwdParams {
@@ -35,6 +37,7 @@ struct RecFwdParams {
     unsigned int* bar;                        // [2][8] per-network, per-k-block step counters, zero before launch
     int B, T, net_base;                       // net_base: slot of the first CTA group (single-network launches)
     int fast;
+    unsigned long long* trace;                // optional [T][8] globaltimer stamps of CTA 0 (debug)
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
@@ -44,6 +47,17 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
 }
 __device__ __forceinline__ void red_release_add(unsigned int* p, unsigned int v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// gate nonlinearities on the ex2 unit: absolute error ~2e-7 (ex2.approx is 2 ulp), far inside the parity budget
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) {
+    const float e = __expf(-2.f * fabsf(x));               // in (0, 1]: no overflow
+    return copysignf(__fdividef(1.f - e, 1.f + e), x);
 }
 __host__ __device__ constexpr uint32_t umma_idesc_bf16_mn(int m, int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
@@ -72,7 +86,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) rec_fwd_kernel(const RecFwdPara
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == UM_PRODUCERS / 32) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(32) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(REC_TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -118,6 +132,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) rec_fwd_kernel(const RecFwdPara
 #pragma unroll
                 for (int q = 0; q < 4; ++q) xp[q] = __ldg(xsrc + q);
             }
+            const bool tr = P.trace && blockIdx.x == 0 && tid == 0;
+            if (tr) P.trace[t * 8 + 0] = gtime();
             if (t > 0) {                                   // the 8 CTAs owning this k-block have published h_{t-1}
                 if (lane == 0) {
                     const unsigned int target = (unsigned int)(8 * t);
@@ -126,6 +142,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) rec_fwd_kernel(const RecFwdPara
                 }
                 __syncwarp();
             }
+            if (tr) P.trace[t * 8 + 1] = gtime();
             {
                 const int kb = warp;
                 const bf16* hsrc_hi = P.Hhi[net] + (size_t)t * B * REC_H + kb * 64 + a_j * 8;     // HsX block t = h_{t-1}
@@ -145,11 +162,20 @@ __global__ void __launch_bounds__(UM_THREADS, 1) rec_fwd_kernel(const RecFwdPara
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&bars[kb]));
             }
+            if (tr) P.trace[t * 8 + 2] = gtime();
             // ---- epilogue of step t
             mbar_wait(smem_u32(&bars[REC_KB]), (uint32_t)t & 1u);
             tc_fence_after();
+            if (tr) P.trace[t * 8 + 3] = gtime();
             float acc[16];
             tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(16 * half), acc);
+#pragma unroll
+            for (int a = 1; a < REC_NACC; ++a) {           // the step's MMAs were spread over REC_NACC accumulators
+                float part[16];
+                tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(a * REC_SLICE + 16 * half), part);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) acc[i] += part[i];
+            }
             if (owner) {
                 const bool live = t < my_len;
                 const size_t row = (size_t)t * B + b;
@@ -157,12 +183,12 @@ __global__ void __launch_bounds__(UM_THREADS, 1) rec_fwd_kernel(const RecFwdPara
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const float4 x = xp[u];
-                    const float gi = 1.f / (1.f + expf(-(acc[4 * u] + x.x)));
-                    const float gf = 1.f / (1.f + expf(-(acc[4 * u + 1] + x.y)));
-                    const float gg = tanhf(acc[4 * u + 2] + x.z);
-                    const float go = 1.f / (1.f + expf(-(acc[4 * u + 3] + x.w)));
+                    const float gi = fast_sigmoid(acc[4 * u] + x.x);
+                    const float gf = fast_sigmoid(acc[4 * u + 1] + x.y);
+                    const float gg = fast_tanh(acc[4 * u + 2] + x.z);
+                    const float go = fast_sigmoid(acc[4 * u + 3] + x.w);
                     const float cn = gf * c_reg[u] + gi * gg;
-                    const float hn = go * tanhf(cn);
+                    const float hn = go * fast_tanh(cn);
                     if (P.Gs[net]) *reinterpret_cast<float4*>(P.Gs[net] + row * REC_G4 + n0 + 16 * half + 4 * u) = make_float4(gi, gf, gg, go);
                     cn4[u] = live ? cn : c_reg[u];
                     hn4[u] = live ? hn : h_reg[u];
@@ -183,34 +209,48 @@ __global__ void __launch_bounds__(UM_THREADS, 1) rec_fwd_kernel(const RecFwdPara
                 h_reg[3] = __uint_as_float(hh[1] & 0xFFFF0000u) + __uint_as_float(ll[1] & 0xFFFF0000u);
             }
             tc_fence_before();
+            if (tr) P.trace[t * 8 + 4] = gtime();
             asm volatile("bar.sync 1, %0;" ::"n"(UM_PRODUCERS) : "memory");          // every owner's stores precede ...
             if (tid == 0) red_release_add(P.bar + net * REC_KB + (slice >> 3), 1u);   // ... this gpu-scope release (cumulative)
+            if (tr) P.trace[t * 8 + 5] = gtime();
         }
     } else {
         // ---------------------------------------------------------------- MMA issuer
-        if (lane == 0) {
+        // The WHOLE warp runs this loop so that the descriptor arithmetic stays warp-uniform (uniform registers feed
+        // UTCHMMA directly); only the elected lane issues.  A divergent single-thread loop pays vector->uniform register
+        // moves per MMA (~74 clk per instruction measured).
+        {
             const uint32_t idesc = umma_idesc_bf16_mn(64, REC_SLICE);
+            const bool leader = elect_one();
+            // broadcast the bases through a shuffle so the compiler can keep everything derived from them uniform
+            const uint32_t uA = __shfl_sync(0xffffffffu, sA, 0), uB = __shfl_sync(0xffffffffu, sB, 0);
+            const uint32_t uT = __shfl_sync(0xffffffffu, tmem_base, 0);
             for (int t = 0; t < T; ++t) {
                 const uint32_t ph = (uint32_t)t & 1u;
 #pragma unroll
                 for (int kb = 0; kb < REC_KB; ++kb) {
                     mbar_wait(smem_u32(&bars[kb]), ph);
                     tc_fence_after();
-                    const uint64_t a_hi = umma_desc_sw128(sA + kb * REC_A_TILE), a_lo = umma_desc_sw128(sA + (REC_KB + kb) * REC_A_TILE);
-                    const uint64_t b_hi = umma_desc_sw128(sB + kb * REC_B_TILE), b_lo = umma_desc_sw128(sB + (REC_KB + kb) * REC_B_TILE);
+                    const uint64_t a_hi = umma_desc_sw128(uA + kb * REC_A_TILE), a_lo = umma_desc_sw128(uA + (REC_KB + kb) * REC_A_TILE);
+                    const uint64_t b_hi = umma_desc_sw128(uB + kb * REC_B_TILE), b_lo = umma_desc_sw128(uB + (REC_KB + kb) * REC_B_TILE);
 #pragma unroll
                     for (int k = 0; k < UM_BK / 16; ++k) {
                         const uint64_t adv = (uint64_t)(k * 32 >> 4);
-                        uint32_t accum = (kb | k) ? 1u : 0u;
-                        if (want_lo) {
-                            umma_bf16(tmem_base, a_lo + adv, b_hi + adv, idesc, accum);
-                            umma_bf16(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
-                            accum = 1u;
+                        // consecutive MMAs go to different accumulators: a chain on ONE accumulator costs ~70 clk per
+                        // instruction (measured), independent ones pipeline at the 16-clk issue rate
+                        if (leader) {
+                            uint32_t accum = (kb | k) ? 1u : 0u;
+                            if (want_lo) {
+                                umma_bf16(uT, a_lo + adv, b_hi + adv, idesc, accum);
+                                umma_bf16(uT, a_hi + adv, b_lo + adv, idesc, 1u);
+                                accum = 1u;
+                            }
+                            umma_bf16(uT, a_hi + adv, b_hi + adv, idesc, accum);
                         }
-                        umma_bf16(tmem_base, a_hi + adv, b_hi + adv, idesc, accum);
                     }
                 }
-                umma_commit(smem_u32(&bars[REC_KB]));
+                if (leader) umma_commit(smem_u32(&bars[REC_KB]));
+                __syncwarp();
             }
         }
         __syncwarp();
@@ -218,7 +258,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) rec_fwd_kernel(const RecFwdPara
     __syncthreads();
     if (warp == UM_PRODUCERS / 32) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(32) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(REC_TMEM_COLS) : "memory");
     }
 }
 

@@ -231,31 +231,39 @@ umma2_kernel(const ASrcT a_, const BSrcT b_, const EpiT ep_, int K, int k_per_sp
         tc_fence_before();
     } else {
         // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        // The whole warp runs the loop (warp-uniform descriptor arithmetic -> uniform registers feed UTCHMMA); only the
+        // elected lane issues the MMAs and commits.
+        {
             constexpr uint32_t idesc = umma_idesc_bf16_major(BN, ASrc::kMN, BSrc::kMN);
             constexpr uint32_t kLboA = 64 * 128, kLboB = 64 * 128;
+            const bool leader = elect_one();
+            // bases broadcast through a shuffle: everything derived from them stays warp-uniform for the compiler
+            const uint32_t u_smem = __shfl_sync(0xffffffffu, smem_base, 0), u_tmem = __shfl_sync(0xffffffffu, tmem_base, 0);
             for (int kt = 0; kt < nk; ++kt) {
                 const int s = kt % kStages;
                 const uint32_t ph = (uint32_t)(kt / kStages) & 1u;
                 mbar_wait(smem_u32(&bars[s]), ph);
                 tc_fence_after();
-                const uint32_t st = smem_base + s * Cfg::kStageBytes;
+                const uint32_t st = u_smem + s * Cfg::kStageBytes;
                 auto mk_a = [&](uint32_t addr) { return ASrc::kMN ? umma_desc_sw128_mn(addr, kLboA) : umma_desc_sw128(addr); };
                 auto mk_b = [&](uint32_t addr) { return BSrc::kMN ? umma_desc_sw128_mn(addr, kLboB) : umma_desc_sw128(addr); };
                 const uint64_t a_hi = mk_a(st), a_lo = mk_a(st + kOffALo), b_hi = mk_b(st + kOffBHi), b_lo = mk_b(st + kOffBLo);
                 // per K=16 step: K-major +32 B inside the 128 B line; MN-major +16 lines = 2048 B
                 constexpr uint64_t kAdvA = (ASrc::kMN ? 2048 : 32) >> 4, kAdvB = (BSrc::kMN ? 2048 : 32) >> 4;
+                if (leader) {
 #pragma unroll
-                for (int k = 0; k < UM_BK / 16; ++k) {
-                    const uint64_t da = kAdvA * k, db = kAdvB * k;
-                    uint32_t acc = (kt | k) ? 1u : 0u;
-                    if (A_LO) { umma_bf16(tmem_base, a_lo + da, b_hi + db, idesc, acc); acc = 1u; }
-                    if (B_LO) { umma_bf16(tmem_base, a_hi + da, b_lo + db, idesc, acc); acc = 1u; }
-                    umma_bf16(tmem_base, a_hi + da, b_hi + db, idesc, acc);
+                    for (int k = 0; k < UM_BK / 16; ++k) {
+                        const uint64_t da = kAdvA * k, db = kAdvB * k;
+                        uint32_t acc = (kt | k) ? 1u : 0u;
+                        if (A_LO) { umma_bf16(u_tmem, a_lo + da, b_hi + db, idesc, acc); acc = 1u; }
+                        if (B_LO) { umma_bf16(u_tmem, a_hi + da, b_lo + db, idesc, acc); acc = 1u; }
+                        umma_bf16(u_tmem, a_hi + da, b_hi + db, idesc, acc);
+                    }
+                    umma_commit(smem_u32(&bars[kStages + s]));
                 }
-                umma_commit(smem_u32(&bars[kStages + s]));
+                __syncwarp();
             }
-            if (nk > 0) umma_commit(smem_u32(&bars[2 * kStages]));
+            if (nk > 0 && leader) umma_commit(smem_u32(&bars[2 * kStages]));
         }
         __syncwarp();
     }
