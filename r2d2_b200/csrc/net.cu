@@ -48,7 +48,7 @@ static void param_sizes(int A, int C, int64_t* n) {
 }
 
 struct Packed {
-    SplitW W1s, W2p, W3p, Wfcp, Wih_p, Whh_p, Wh0, W3d, W2d;   // W2d: [4][32][256]
+    SplitW W1s, W2p, W3p, Wfcp, Wih_p, Whh_p, WhhT_p, Wh0, W3d, W2d;   // W2d: [4][32][256]; WhhT_p: [512][2048] transpose
     float *bias_p, *bh0;
 };
 struct Acts {
@@ -72,7 +72,7 @@ struct r2d2_net {
     unsigned int* rec_bar;                            // [2] step counters of the persistent recurrence
     // backward scratch
     r2d2::SplitW dhid, DG, dlat, dpre3, dpre2, dpre1T;
-    float *dH, *dhrec, *dcrec, *dout16, *ws, *colws;
+    float *dH, *dhrec, *dcrec, *dout16, *ws, *colws, *rec_partial;
     size_t ws_floats;
     const float* hidden;             // last forward's stored state (caller-owned, alive until backward)
 };
@@ -122,7 +122,9 @@ __global__ void pack_kernel(const float* __restrict__ p, const int64_t* __restri
     }
     if (i < (int64_t)G4 * H) {
         const int np = i / H, k = i % H, g = np & 3, j = np >> 2;
-        put_split(pk.Whh_p, i, p[off[P_WHH] + (int64_t)(g * H + j) * H + k]);
+        const float w = p[off[P_WHH] + (int64_t)(g * H + j) * H + k];
+        put_split(pk.Whh_p, i, w);
+        put_split(pk.WhhT_p, (size_t)k * G4 + np, w);          // transposed copy for the persistent BPTT kernel
     }
     if (i < G4) {
         const int g = i & 3, j = i >> 2;
@@ -569,7 +571,7 @@ int r2d2_net_create(int B, int T, int C, int A, int Lmax, int max_forward, r2d2_
     for (int k = 0; k < 2 && !rc; ++k) {
         Packed& p = n->pk[k];
         rc |= alloc_s(&p.W1s, 32ull * 64 * C); rc |= alloc_s(&p.W2p, 64 * 512); rc |= alloc_s(&p.W3p, 64 * 576);
-        rc |= alloc_s(&p.Wfcp, 512ull * FLAT3); rc |= alloc_s(&p.Wih_p, (size_t)G4 * n->KU); rc |= alloc_s(&p.Whh_p, (size_t)G4 * H);
+        rc |= alloc_s(&p.Wfcp, 512ull * FLAT3); rc |= alloc_s(&p.Wih_p, (size_t)G4 * n->KU); rc |= alloc_s(&p.Whh_p, (size_t)G4 * H); rc |= alloc_s(&p.WhhT_p, (size_t)G4 * H);
         rc |= alloc_s(&p.Wh0, 2 * H * H); rc |= alloc_s(&p.W3d, 64 * 576); rc |= alloc_s(&p.W2d, 4 * 32 * 256);
         rc |= alloc_f(&p.bias_p, G4); rc |= alloc_f(&p.bh0, 2 * H);
         Acts& a = n->ac[k];
@@ -589,7 +591,7 @@ int r2d2_net_create(int B, int T, int C, int A, int Lmax, int max_forward, r2d2_
     rc |= alloc_s(&n->dhid, (size_t)n->Rmax * 2 * H); rc |= alloc_s(&n->DG, TB * G4); rc |= alloc_s(&n->dlat, NF * LATENT);
     rc |= alloc_s(&n->dpre3, NF * FLAT3); rc |= alloc_s(&n->dpre2, NF * 5184); rc |= alloc_s(&n->dpre1T, NF * 12800);
     rc |= alloc_f(&n->dH, TB * H); rc |= alloc_f(&n->dhrec, (size_t)kRecSplits * B * H); rc |= alloc_f(&n->dcrec, (size_t)B * H);
-    rc |= alloc_f(&n->dout16, (size_t)n->Rmax * 16);
+    rc |= alloc_f(&n->dout16, (size_t)n->Rmax * 16); rc |= alloc_f(&n->rec_partial, 2ull * 8 * 64 * H);
     n->ws_floats = 32ull << 20;                        // 128 MB split-K workspace
     rc |= alloc_f(&n->ws, n->ws_floats); rc |= alloc_f(&n->colws, (size_t)kColP * 4096);
     if (rc) return rc;
@@ -602,7 +604,7 @@ int r2d2_net_destroy(r2d2_net* n) {
     if (!n) return R2D2_OK;
     for (int k = 0; k < 2; ++k) {
         Packed& p = n->pk[k];
-        SplitW* ps[] = {&p.W1s, &p.W2p, &p.W3p, &p.Wfcp, &p.Wih_p, &p.Whh_p, &p.Wh0, &p.W3d, &p.W2d};
+        SplitW* ps[] = {&p.W1s, &p.W2p, &p.W3p, &p.Wfcp, &p.Wih_p, &p.Whh_p, &p.WhhT_p, &p.Wh0, &p.W3d, &p.W2d};
         for (SplitW* x : ps) free_s(*x);
         cudaFree(p.bias_p); cudaFree(p.bh0);
         Acts& a = n->ac[k];
@@ -612,7 +614,7 @@ int r2d2_net_destroy(r2d2_net* n) {
     }
     SplitW* ss[] = {&n->W1both, &n->dhid, &n->DG, &n->dlat, &n->dpre3, &n->dpre2, &n->dpre1T};
     for (SplitW* x : ss) free_s(*x);
-    float* fs[] = {n->dH, n->dhrec, n->dcrec, n->dout16, n->ws, n->colws};
+    float* fs[] = {n->dH, n->dhrec, n->dcrec, n->dout16, n->ws, n->colws, n->rec_partial};
     for (float* x : fs) cudaFree(x);
     cudaFree(n->rec_bar); cudaFree(n->s2d); cudaFree(n->row_src); cudaFree(n->len_full); cudaFree(n->len_learn); cudaFree(n->d_rows);
     cudaFree(g_doff[n]);
@@ -877,6 +879,13 @@ int r2d2_net_backward(r2d2_net* n, const float* params, const float* dq, float* 
         R2D2_CUDA_CHECK((launch_umma2<128>(a, b, e, Rmax, H, 2 * H, 1, s)));
     }
     // ---- BPTT through all b+l steps, burn-in included (no detach anywhere in model.py:122-150)
+    if (B <= 64 && g_persistent_recurrence) {            // one cooperative launch for all T steps (recurrence.cuh)
+        RecBwdParams P;
+        P.WThi = pk.WhhT_p.hi; P.WTlo = pk.WhhT_p.lo; P.dH = n->dH; P.Gs = ac.Gs; P.Cs = ac.Cs;
+        P.c0 = n->hidden + H; P.ld_c0 = 2 * H; P.len = n->len_learn; P.DGhi = n->DG.hi; P.DGlo = n->DG.lo;
+        P.partial = n->rec_partial; P.flags = n->rec_bar + 32; P.B = B; P.T = T; P.fast = g_fast_math == 1;
+        R2D2_CUDA_CHECK(launch_rec_bwd(P, s));
+    } else {
     R2D2_CUDA_CHECK(cudaMemsetAsync(n->dcrec, 0, (size_t)B * H * sizeof(float), s));
     for (int t = T - 1; t >= 0; --t) {
         const float* cprev = t ? ac.Cs + (size_t)(t - 1) * B * H : n->hidden + H;
@@ -890,6 +899,7 @@ int r2d2_net_backward(r2d2_net* n, const float* params, const float* dq, float* 
             Epi2Partial e{n->dhrec, B, H};
             R2D2_CUDA_CHECK((launch_umma2<64>(a, b, e, B, H, G4, kRecSplits, s)));
         }
+    }
     }
     R2D2_LAUNCH_CHECK();
     {   // recurrent weight gradients over all (t,b) rows

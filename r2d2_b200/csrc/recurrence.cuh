@@ -275,4 +275,237 @@ static inline cudaError_t launch_rec_fwd(const RecFwdParams& P, int nets, cudaSt
     return cudaLaunchCooperativeKernel((const void*)rec_fwd_kernel, dim3(nets * REC_CTAS_PER_NET), dim3(UM_THREADS), args, REC_SMEM, s);
 }
 
+// ================================================================================================
+// Persistent BPTT recurrence (backward): all T steps of  dgates_t -> dh_{t-1} = dgates_t . W_hh  in one
+// cooperative launch (online network only).
+//
+//   grid = 128 CTAs.  CTA c plays two roles every step:
+//   * pointwise role for hidden units [4c, 4c+4): thread (b, u) owns (sequence b, unit 4c+u) with dc carried in a
+//     register; dh_t = dH[t] + sum of the 8 K-slice partials of dgates_{t+1}.W_hh (fixed order: deterministic),
+//     LSTM cell backward -> d(pre-activation gates) DG_t (split) ;
+//   * GEMM role (ki = c / 16, ji = c % 16): partial[ki][b][32 ji + n] = DG_t[b][256 ki .. +256) . W_hh[256 ki.., 32 ji + n]
+//     with its W_hh^T block [32][256] (bf16 hi+lo, 32 KB) resident in shared memory, UMMA M=64, N=32, 48 MMAs.
+//   Dependencies are tracked with release/acquire counters per 64-unit K slice (flagDG[ki], 16 producers a step)
+//   and per 32-unit output slice (flagDH[ji], 8 producers a step); partial buffers alternate with the step parity.
+// ================================================================================================
+constexpr int RB_KB = 4;                               // k-blocks of 64 per K slice of 256
+constexpr int RB_A_TILE = 64 * UM_BK * 2;              // 8 KB
+constexpr int RB_B_TILE = 32 * UM_BK * 2;              // 4 KB
+constexpr int RB_SMEM = 2 * RB_KB * (RB_A_TILE + RB_B_TILE) + 1024 + 256;
+
+struct RecBwdParams {
+    const bf16* WThi; const bf16* WTlo;       // WhhT_p [512][2048]: row j, col n' (gate-interleaved)
+    const float* dH;                          // [T*B][512]   dLoss/dh_t from the head
+    const float* Gs; const float* Cs;         // saved gates [T*B][2048], cell states [T*B][512]
+    const float* c0; int ld_c0;               // stored cell state
+    const int* len;                           // [B] number of steps carrying gradient (burn-in + learning)
+    bf16* DGhi; bf16* DGlo;                   // [T*B][2048] out (split)
+    float* partial;                           // [2][8][64][512] fp32 scratch
+    unsigned int* flags;                      // [8] flagDG + [16] flagDH, zero before launch
+    int B, T, fast;
+};
+
+__global__ void __launch_bounds__(UM_THREADS, 1) rec_bwd_kernel(const RecBwdParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;
+    uint8_t* smem = smem_raw + pad;
+    const uint32_t sA = raw + pad;
+    const uint32_t sB = sA + 2 * RB_KB * RB_A_TILE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * RB_KB * (RB_A_TILE + RB_B_TILE));
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + RB_KB + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int c = blockIdx.x, ki = c >> 4, ji = c & 15;
+    const int B = P.B, T = P.T;
+    const bool want_lo = !P.fast;
+    unsigned int* flagDG = P.flags;          // [8]
+    unsigned int* flagDH = P.flags + 8;      // [16]
+
+    if (tid == 0) {
+        for (int kb = 0; kb < RB_KB; ++kb) mbar_init(smem_u32(&bars[kb]), UM_PRODUCERS / 32);
+        mbar_init(smem_u32(&bars[RB_KB]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == UM_PRODUCERS / 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(32) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < UM_PRODUCERS / 32) {
+        // ---- resident B: W_hh^T block rows j in [32 ji, +32), cols n' in [256 ki, +256)
+        for (int u = tid; u < 32 * 32; u += UM_PRODUCERS) {
+            const int row = u >> 5, ch = u & 31, kb = ch >> 3, j = ch & 7;
+            const uint32_t dst = (uint32_t)(kb * RB_B_TILE + (row >> 3) * 1024 + (row & 7) * 128 + ((j ^ (row & 7)) << 4));
+            const size_t src = (size_t)(32 * ji + row) * REC_G4 + 256 * ki + ch * 8;
+            cp_async16(sB + dst, P.WThi + src, true);
+            if (want_lo) cp_async16(sB + RB_KB * RB_B_TILE + dst, P.WTlo + src, true);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        fence_proxy_async_smem();
+
+        // pointwise ownership: (sequence pb, unit pj)
+        const int pb = tid >> 2, pj = 4 * c + (tid & 3);
+        const bool p_own = pb < B;
+        const int p_len = p_own ? P.len[pb] : 0;
+        float dcrec = 0.f;
+        // GEMM epilogue ownership (UMMA M=64 layout): row eb, 16 columns
+        const int eb = 16 * (warp & 3) + lane, ehalf = warp >> 2;
+        const bool e_own = lane < 16 && eb < B;
+        const int a_j = tid & 7, a_r0 = tid >> 3;           // A staging: rows a_r0, a_r0 + 32
+
+        for (int t = T - 1, step = 0; t >= 0; --t, ++step) {
+            // ================= pointwise role: DG_t for units [4c, 4c+4) =================
+            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+            float dh = 0.f, ct = 0.f, cp = 0.f;
+            const bool live = p_own && t < p_len;
+            if (live) {                                    // loads that do not depend on the previous step
+                const size_t row = (size_t)t * B + pb;
+                g = *reinterpret_cast<const float4*>(P.Gs + row * REC_G4 + 4 * pj);
+                dh = P.dH[row * REC_H + pj];
+                ct = P.Cs[row * REC_H + pj];
+                cp = t ? P.Cs[((size_t)(t - 1) * B + pb) * REC_H + pj] : P.c0[(size_t)pb * P.ld_c0 + pj];
+            }
+            if (step > 0) {                                // partials of dgates_{t+1}.W_hh for my output slice are complete
+                if (tid == 0) {
+                    const unsigned int target = 8u * (unsigned int)step;
+                    for (uint32_t spins = 0; ld_acquire_u32(flagDH + (c >> 3)) < target; ++spins)
+                        if (spins > (1u << 28)) __trap();
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(UM_PRODUCERS) : "memory");
+                if (live) {
+                    const float* pp = P.partial + (size_t)((t + 1) & 1) * 8 * 64 * REC_H + (size_t)pb * REC_H + pj;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) dh += __ldcg(pp + (size_t)q * 64 * REC_H);
+                }
+            }
+            {
+                float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+                if (live) {
+                    const float tc = fast_tanh(ct);
+                    const float dc = dcrec + dh * g.w * (1.f - tc * tc);
+                    o0 = dc * g.z * g.x * (1.f - g.x);
+                    o1 = dc * cp * g.y * (1.f - g.y);
+                    o2 = dc * g.x * (1.f - g.z * g.z);
+                    o3 = dh * tc * g.w * (1.f - g.w);
+                    dcrec = dc * g.y;
+                }
+                if (p_own) {
+                    uint32_t h[2], l[2];
+                    split2(o0, o1, h[0], l[0]);
+                    split2(o2, o3, h[1], l[1]);
+                    const size_t o = ((size_t)t * B + pb) * REC_G4 + 4 * pj;
+                    *reinterpret_cast<uint2*>(P.DGhi + o) = make_uint2(h[0], h[1]);
+                    *reinterpret_cast<uint2*>(P.DGlo + o) = make_uint2(l[0], l[1]);
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(UM_PRODUCERS) : "memory");
+            if (tid == 0) red_release_add(flagDG + (c >> 4), 1u);
+            if (t == 0) break;                              // dh_{-1} is not needed
+
+            // ================= GEMM role: partial[ki] of dgates_t . W_hh for output slice ji =================
+            if (tid == 0) {
+                const unsigned int target = 16u * (unsigned int)(step + 1);
+                for (uint32_t spins = 0; ld_acquire_u32(flagDG + ki) < target; ++spins)
+                    if (spins > (1u << 28)) __trap();
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(UM_PRODUCERS) : "memory");
+            {
+                const bf16* src_hi = P.DGhi + (size_t)t * B * REC_G4 + 256 * ki + a_j * 8;
+                const bf16* src_lo = P.DGlo + (size_t)t * B * REC_G4 + 256 * ki + a_j * 8;
+#pragma unroll
+                for (int kb = 0; kb < RB_KB; ++kb) {
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        const int row = a_r0 + 32 * r;
+                        const uint32_t dst = (uint32_t)(kb * RB_A_TILE + (row >> 3) * 1024 + (row & 7) * 128 + ((a_j ^ (row & 7)) << 4));
+                        const bool ok = row < B;
+                        const size_t so = ok ? (size_t)row * REC_G4 + kb * 64 : 0;
+                        cp_async16(sA + dst, src_hi + so, ok);
+                        if (want_lo) cp_async16(sA + RB_KB * RB_A_TILE + dst, src_lo + so, ok);
+                    }
+                    cp_async_commit();
+                }
+#pragma unroll
+                for (int kb = 0; kb < RB_KB; ++kb) {
+                    switch (RB_KB - 1 - kb) {
+                        case 3: cp_async_wait<3>(); break; case 2: cp_async_wait<2>(); break;
+                        case 1: cp_async_wait<1>(); break; default: cp_async_wait<0>(); break;
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&bars[kb]));
+                }
+            }
+            mbar_wait(smem_u32(&bars[RB_KB]), (uint32_t)step & 1u);
+            tc_fence_after();
+            float acc[16];
+            tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(16 * ehalf), acc);
+            if (e_own) {
+                float* dst = P.partial + ((size_t)(t & 1) * 8 + ki) * 64 * REC_H + (size_t)eb * REC_H + 32 * ji + 16 * ehalf;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    __stcg(reinterpret_cast<float4*>(dst) + q, make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]));
+            }
+            tc_fence_before();
+            asm volatile("bar.sync 1, %0;" ::"n"(UM_PRODUCERS) : "memory");
+            if (tid == 0) red_release_add(flagDH + ji, 1u);
+        }
+    } else {
+        // ---------------------------------------------------------------- MMA issuer (whole warp, elected lane issues)
+        const uint32_t idesc = umma_idesc_bf16_mn(64, 32);
+        const bool leader = elect_one();
+        const uint32_t uA = __shfl_sync(0xffffffffu, sA, 0), uB = __shfl_sync(0xffffffffu, sB, 0);
+        const uint32_t uT = __shfl_sync(0xffffffffu, tmem_base, 0);
+        for (int step = 0; step < T - 1; ++step) {
+            const uint32_t ph = (uint32_t)step & 1u;
+#pragma unroll
+            for (int kb = 0; kb < RB_KB; ++kb) {
+                mbar_wait(smem_u32(&bars[kb]), ph);
+                tc_fence_after();
+                const uint64_t a_hi = umma_desc_sw128(uA + kb * RB_A_TILE), a_lo = umma_desc_sw128(uA + (RB_KB + kb) * RB_A_TILE);
+                const uint64_t b_hi = umma_desc_sw128(uB + kb * RB_B_TILE), b_lo = umma_desc_sw128(uB + (RB_KB + kb) * RB_B_TILE);
+#pragma unroll
+                for (int k = 0; k < UM_BK / 16; ++k) {
+                    const uint64_t adv = (uint64_t)(k * 32 >> 4);
+                    if (leader) {
+                        uint32_t accum = (kb | k) ? 1u : 0u;
+                        if (want_lo) {
+                            umma_bf16(uT, a_lo + adv, b_hi + adv, idesc, accum);
+                            umma_bf16(uT, a_hi + adv, b_lo + adv, idesc, 1u);
+                            accum = 1u;
+                        }
+                        umma_bf16(uT, a_hi + adv, b_hi + adv, idesc, accum);
+                    }
+                }
+            }
+            if (leader) umma_commit(smem_u32(&bars[RB_KB]));
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    if (warp == UM_PRODUCERS / 32) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(32) : "memory");
+    }
+}
+
+static inline cudaError_t launch_rec_bwd(const RecBwdParams& P, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(rec_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RB_SMEM);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    cudaError_t e = cudaMemsetAsync(P.flags, 0, 24 * sizeof(unsigned int), s);
+    if (e != cudaSuccess) return e;
+    void* args[] = {(void*)&P};
+    return cudaLaunchCooperativeKernel((const void*)rec_bwd_kernel, dim3(128), dim3(UM_THREADS), args, RB_SMEM, s);
+}
+
 }  // namespace r2d2
