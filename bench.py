@@ -36,7 +36,7 @@ BURN, LEARN, FWD = 40, 40, 5
 T = BURN + LEARN + FWD
 BLOCK_LEN = 400
 TREE_CAPACITY = 1 << 20    # BASELINE config #3: sum tree over 2^20 sequence slots
-NUM_BLOCKS = 128           # frame store: 128 blocks x 441 frames (1.6 GB at C=4), far larger than L2
+NUM_BLOCKS = int(os.environ.get("R2D2_BENCH_BLOCKS", "128"))   # frame store: 128 blocks x 441 frames (1.6 GB at C=4), far larger than L2
 
 
 def flops_per_sequence(C: int) -> float:
@@ -232,8 +232,14 @@ def run_ours(args):
     def step_resident(i):
         learner.update_from_replay()
 
+    from collections import deque
+    staged = deque([learner.prefetch(tuples[0])])
+
     def step_e2e(i):
-        learner.update_from_batch(tuples[i % len(tuples)])     # H2D + update + D2H (synchronises on the result, like worker.py:357)
+        # every step moves one full batch host -> device inside the timed region; like the reference's prefetch thread
+        # (worker.py:309-316) the copy of batch i+1 is issued before batch i is trained on, on a copy stream
+        staged.append(learner.prefetch(tuples[(i + 1) % len(tuples)]))
+        learner.update_from_batch(staged.popleft())            # update + priorities/loss D2H, host synchronises on the result
 
     def timed(fn, steps, warmup):
         for w in range(warmup):

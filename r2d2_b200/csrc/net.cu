@@ -48,7 +48,7 @@ static void param_sizes(int A, int C, int64_t* n) {
 }
 
 struct Packed {
-    SplitW W1s, W2p, W3p, Wfcp, Wih_p, Whh_p, WhhT_p, Wh0, W3d, W2d;   // W2d: [4][32][256]; WhhT_p: [512][2048] transpose
+    SplitW W1s, W2p, W3p, Wfcp, Wih_p, Whh_p, WhhT_p, Wh0, W3d, W2d, W2q;   // W2d: [4][32][256]; WhhT_p: [512][2048] transpose
     float *bias_p, *bh0;
 };
 struct Acts {
@@ -105,7 +105,9 @@ __global__ void pack_kernel(const float* __restrict__ p, const int64_t* __restri
         // dgrad, 4 parity classes: W2d[cls][c_in][(jy*2+jx)*64 + c_out] = W2[c_out][c_in][py+2jy][px+2jx]
         const int cls = i / (32 * 256), r = i % (32 * 256), ci = r / 256, kk = r % 256, j = kk >> 6, co = kk & 63;
         const int py = cls >> 1, px = cls & 1, jy = j >> 1, jx = j & 1;
-        put_split(pk.W2d, i, p[off[P_C2W] + co * 512 + ci * 16 + (py + 2 * jy) * 4 + (px + 2 * jx)]);
+        const float wd = p[off[P_C2W] + co * 512 + ci * 16 + (py + 2 * jy) * 4 + (px + 2 * jx)];
+        put_split(pk.W2d, i, wd);
+        put_split(pk.W2q, (size_t)(ci * 4 + cls) * 256 + kk, wd);       // all four parity classes side by side (N = 128)
     }
     if (i < 64 * 576) {
         const int n = i / 576, k = i % 576, tap = k >> 6, c = k & 63;
@@ -398,6 +400,34 @@ struct Epi2DgradS2T {
         }
     }
 };
+// conv2 dgrad, all four output-parity classes in ONE contraction (they gather the same dpre2 taps; only the weights
+// differ): column n = 4*c + (2*py + px).  Row m = (f, y', x') on the 10x10 grid owns the 2x2 pixel block
+// (2y'+py, 2x'+px) of act1; 16 columns = 4 channels x 4 classes.  ReLU mask from act1, stored channel-major with the
+// two px neighbours written as one 4-byte pair.
+struct Epi2DgradS2Q {
+    SplitW out; SplitC act; int nframes; long long NP;
+    __device__ __forceinline__ void store16(int m, int n, const float (&v)[16], int) const {
+        if (m >= nframes * 100 || n >= 128) return;
+        const int f = m / 100, p = m - f * 100, yq = p / 10, xq = p - yq * 10;
+        const long long pix00 = ((long long)f * 20 + 2 * yq) * 20 + 2 * xq;       // (py, px) = (0, 0); even -> 4-byte aligned pairs
+        const int c0 = n >> 2;
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+            const int c = c0 + ci;
+#pragma unroll
+            for (int py = 0; py < 2; ++py) {
+                const long long pix = pix00 + 20 * py;
+                const bool on0 = (__bfloat16_as_ushort(act.hi[pix * 32 + c]) & 0x7FFFu) != 0;
+                const bool on1 = (__bfloat16_as_ushort(act.hi[(pix + 1) * 32 + c]) & 0x7FFFu) != 0;
+                uint32_t h, l;
+                split2(on0 ? v[ci * 4 + py * 2] : 0.f, on1 ? v[ci * 4 + py * 2 + 1] : 0.f, h, l);
+                const size_t o = (size_t)(c * NP + pix);
+                *reinterpret_cast<uint32_t*>(out.hi + o) = h;
+                *reinterpret_cast<uint32_t*>(out.lo + o) = l;
+            }
+        }
+    }
+};
 // scatter rows of d(hidden rows) to dH[t][b] (fp32) through the row map
 struct Epi2ScatterRows {
     float* dH; const int* src; const int* d_rows; int Rmax;
@@ -572,7 +602,7 @@ int r2d2_net_create(int B, int T, int C, int A, int Lmax, int max_forward, r2d2_
         Packed& p = n->pk[k];
         rc |= alloc_s(&p.W1s, 32ull * 64 * C); rc |= alloc_s(&p.W2p, 64 * 512); rc |= alloc_s(&p.W3p, 64 * 576);
         rc |= alloc_s(&p.Wfcp, 512ull * FLAT3); rc |= alloc_s(&p.Wih_p, (size_t)G4 * n->KU); rc |= alloc_s(&p.Whh_p, (size_t)G4 * H); rc |= alloc_s(&p.WhhT_p, (size_t)G4 * H);
-        rc |= alloc_s(&p.Wh0, 2 * H * H); rc |= alloc_s(&p.W3d, 64 * 576); rc |= alloc_s(&p.W2d, 4 * 32 * 256);
+        rc |= alloc_s(&p.Wh0, 2 * H * H); rc |= alloc_s(&p.W3d, 64 * 576); rc |= alloc_s(&p.W2d, 4 * 32 * 256); rc |= alloc_s(&p.W2q, 128 * 256);
         rc |= alloc_f(&p.bias_p, G4); rc |= alloc_f(&p.bh0, 2 * H);
         Acts& a = n->ac[k];
         rc |= alloc_s(&a.act1, NF * 12800); rc |= alloc_s(&a.act2, NF * 5184); rc |= alloc_s(&a.act3, NF * FLAT3);
@@ -604,7 +634,7 @@ int r2d2_net_destroy(r2d2_net* n) {
     if (!n) return R2D2_OK;
     for (int k = 0; k < 2; ++k) {
         Packed& p = n->pk[k];
-        SplitW* ps[] = {&p.W1s, &p.W2p, &p.W3p, &p.Wfcp, &p.Wih_p, &p.Whh_p, &p.WhhT_p, &p.Wh0, &p.W3d, &p.W2d};
+        SplitW* ps[] = {&p.W1s, &p.W2p, &p.W3p, &p.Wfcp, &p.Wih_p, &p.Whh_p, &p.WhhT_p, &p.Wh0, &p.W3d, &p.W2d, &p.W2q};
         for (SplitW* x : ps) free_s(*x);
         cudaFree(p.bias_p); cudaFree(p.bh0);
         Acts& a = n->ac[k];
@@ -944,17 +974,12 @@ int r2d2_net_backward(r2d2_net* n, const float* params, const float* dq, float* 
         SrcConvMN<20, 20, 32, 9, 9, 4, 4, 2> b{ac.act1.hi, ac.act1.lo, NF};
         R2D2_CUDA_CHECK((wgrad2<64, LO_NO_WEIGHT>(a, b, 64, 512, K2, (K2 + 4095) / 4096, R_C2, n, grads, d_off, 1.f, s)));
         R2D2_CUDA_CHECK(colsum_split(ro(n->dpre2), K2, 64, B_PLAIN, grads, off[P_C2B], 0, A, n->colws, s));
-        {   // stride-2 dgrad as four stride-1 problems (output parity classes), ONE launch: blockIdx.x = class, so the
-            // CTAs that write interleaved pixels of the same dpre1T sectors run together and merge in L2
+        {   // stride-2 dgrad: the four output-parity classes read the SAME 2x2 taps of dpre2 -> one contraction with the
+            // four weight sets side by side (N = 4 x 32), the gathered tile is staged once instead of four times
             SrcDgradK<10, 10, 9, 9, 64, 2, 2> a2{n->dpre2.hi, n->dpre2.lo, NF};
-            Multi<SrcMatK, 4> b2;
-            Multi<Epi2DgradS2T, 4> e;
-            for (int cls = 0; cls < 4; ++cls) {
-                const size_t wo = (size_t)cls * 32 * 256;
-                b2.f[cls] = SrcMatK{pk.W2d.hi + wo, pk.W2d.lo + wo, 32, 256, 256};
-                e.f[cls] = Epi2DgradS2T{n->dpre1T, ro(ac.act1), NF, cls >> 1, cls & 1, (long long)NF * 400};
-            }
-            R2D2_CUDA_CHECK((launch_umma2_multi<32, 4, LO_WEIGHT_B>(a2, b2, e, NF * 100, 256, s)));
+            SrcMatK b2{pk.W2q.hi, pk.W2q.lo, 128, 256, 256};
+            Epi2DgradS2Q e{n->dpre1T, ro(ac.act1), NF, (long long)NF * 400};
+            R2D2_CUDA_CHECK((launch_umma2<128, LO_WEIGHT_B>(a2, b2, e, NF * 100, 128, 256, 1, s)));
         }
     }
     {   // conv1 (weights only; frames need no gradient)

@@ -66,6 +66,74 @@ class FlatParams:
         return {k: (v.detach().clone() if device is None else v.detach().to(device)) for k, v in self.views.items()}
 
 
+class BatchStager:
+    """Double-buffered host -> device staging of reference-format batches on a copy stream.
+
+    The reference learner prefetches batches from its queue in a background thread (worker.py:309-316) and then
+    moves each one to the device synchronously (worker.py:331-334).  Here the move of batch k+1 (pinned host memory,
+    one cudaMemcpyAsync per field into preallocated device slots) runs on a side stream while batch k is being
+    trained on; events hand slots back and forth between the two streams."""
+
+    def __init__(self, core: "DeviceLearner", slots: int = 2):
+        d, B, T, A, R = core.device, core.B, core.T, core.A, core.rows_cap
+        self.core = core
+        self.stream = torch.cuda.Stream(device=d)
+        self.slots = []
+        for _ in range(slots):
+            buf = dict(obs=torch.zeros(B, T, core.C, 84, 84, dtype=torch.uint8, device=d),
+                       last_action=torch.zeros(B, T, A, dtype=torch.uint8, device=d), last_reward=torch.zeros(B, T, device=d),
+                       hidden=torch.zeros(B, 2, HIDDEN, device=d), action=torch.zeros(R, dtype=torch.uint8, device=d),
+                       n_step_reward=torch.zeros(R, device=d), gamma=torch.zeros(R, device=d),
+                       burn_in=torch.zeros(B, dtype=torch.uint8, device=d), learning=torch.zeros(B, dtype=torch.uint8, device=d),
+                       forward=torch.zeros(B, dtype=torch.uint8, device=d), is_weights=torch.zeros(R, device=d))
+            self.slots.append(dict(buf=buf, ready=torch.cuda.Event(), free=None, tmax=T))
+        self._next = 0
+
+    @staticmethod
+    def _as_u8(t):
+        return t.view(torch.uint8) if t.dtype == torch.bool else (t if t.dtype == torch.uint8 else (t != 0).to(torch.uint8))
+
+    def stage(self, fields: dict) -> int:
+        """Enqueue the copies of one batch (dict with the 14-tuple's learner-visible fields); returns a slot handle."""
+        i = self._next
+        self._next = (i + 1) % len(self.slots)
+        slot = self.slots[i]
+        buf, core = slot["buf"], self.core
+        with torch.cuda.stream(self.stream):
+            if slot["free"] is not None:
+                self.stream.wait_event(slot["free"])            # the update that last used this slot has finished
+            Tb = fields["obs"].shape[1]
+            assert Tb <= core.T
+            buf["obs"][:, :Tb].copy_(fields["obs"], non_blocking=True)
+            buf["last_action"][:, :Tb].copy_(self._as_u8(fields["last_action"]), non_blocking=True)
+            buf["last_reward"][:, :Tb].copy_(fields["last_reward"], non_blocking=True)
+            if Tb < slot["tmax"] or Tb < core.T:                  # pad_sequence-style zero padding at the END of time
+                buf["obs"][:, Tb:].zero_(); buf["last_action"][:, Tb:].zero_(); buf["last_reward"][:, Tb:].zero_()
+            slot["tmax"] = Tb
+            h = fields["hidden"]
+            if h.shape[0] == 2 and h.shape[1] == core.B and h.shape[0] != core.B:
+                h = h.transpose(0, 1)                              # (2,B,H) view of the stacked (B,2,H) array, worker.py:223
+            buf["hidden"].copy_(h, non_blocking=True)
+            rows = fields["action"].numel()
+            buf["action"][:rows].copy_(fields["action"].reshape(-1), non_blocking=True)
+            buf["n_step_reward"][:rows].copy_(fields["n_step_reward"], non_blocking=True)
+            buf["gamma"][:rows].copy_(fields["gamma"], non_blocking=True)
+            buf["is_weights"][:rows].copy_(fields["is_weights"], non_blocking=True)
+            for k in ("burn_in", "learning", "forward"):
+                buf[k].copy_(fields[k], non_blocking=True)
+            slot["ready"].record(self.stream)
+        return i
+
+    def acquire(self, handle: int) -> dict:
+        torch.cuda.current_stream(self.core.device).wait_event(self.slots[handle]["ready"])
+        return self.slots[handle]["buf"]
+
+    def release(self, handle: int) -> None:
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.core.device))
+        self.slots[handle]["free"] = ev
+
+
 class DeviceLearner:
     def __init__(self, action_dim: int, batch_size: int, seq_frames: int, in_channels: int = 1, max_learning: int = 40,
                  max_forward: int = 5, lr: float = 1e-4, eps: float = 1e-3, grad_norm: float = 40.0,

@@ -238,6 +238,7 @@ class Learner:
         self._loss_host = torch.empty(2, dtype=torch.float32).pin_memory()
         self._sum_loss = 0.0
         self.env_steps = 0
+        self._stager = None
 
     # -- parameters ---------------------------------------------------------------------------------------------
     def state_dict(self):
@@ -247,15 +248,27 @@ class Learner:
         self.shared_model.load_state_dict(self.core.online.state_dict(device='cpu'))
 
     # -- one update from a reference-format host/device 14-tuple (worker.py:330-369) -----------------------------
-    def update_from_batch(self, data):
+    def prefetch(self, data):
+        """Start moving a 14-tuple to the device on the copy stream (the reference prefetches from its queue in a thread,
+        worker.py:309-316).  Returns a staged handle accepted by update_from_batch."""
+        from .learner_core import BatchStager
+        if self._stager is None:
+            self._stager = BatchStager(self.core)
         (batch_obs, batch_last_action, batch_last_reward, batch_hidden, batch_action, batch_n_step_reward, batch_n_step_gamma,
          burn_in_steps, learning_steps, forward_steps, idxes, is_weights, old_ptr, env_steps) = data
-        hidden = batch_hidden.transpose(0, 1) if batch_hidden.shape[0] == 2 and batch_hidden.shape[1] == self.batch_size \
-            else batch_hidden                                                       # (2,B,H) view of (B,2,H), worker.py:223
-        b = self.core.prepare(dict(obs=batch_obs, last_action=batch_last_action, last_reward=batch_last_reward, hidden=hidden,
-                                   action=batch_action, n_step_reward=batch_n_step_reward, gamma=batch_n_step_gamma,
-                                   burn_in=burn_in_steps, learning=learning_steps, forward=forward_steps, is_weights=is_weights))
+        handle = self._stager.stage(dict(obs=batch_obs, last_action=batch_last_action, last_reward=batch_last_reward,
+                                         hidden=batch_hidden, action=batch_action, n_step_reward=batch_n_step_reward,
+                                         gamma=batch_n_step_gamma, burn_in=burn_in_steps, learning=learning_steps,
+                                         forward=forward_steps, is_weights=is_weights))
+        return ("staged", handle, idxes, old_ptr, env_steps)
+
+    def update_from_batch(self, data):
+        if not (isinstance(data, tuple) and len(data) == 5 and isinstance(data[0], str) and data[0] == "staged"):
+            data = self.prefetch(data)
+        _, handle, idxes, old_ptr, env_steps = data
+        b = self._stager.acquire(handle)
         self.core.update(b)
+        self._stager.release(handle)
         self._prio_host.copy_(self.core.prio, non_blocking=True)                   # worker.py:357: priorities back to the host
         self._loss_host[0:1].copy_(self.core.loss_sum, non_blocking=True)
         self._loss_host[1:2].copy_(self.core.rows.float(), non_blocking=True)
@@ -315,7 +328,10 @@ class Learner:
                 if isinstance(data, tuple) and len(data) == 4 and isinstance(data[0], str) and data[0] == BLOCK_MSG:
                     self._ingest(data)
                 else:                                                              # reference-format 14-tuple
-                    self.priority_queue.put(self.update_from_batch(data))
+                    staged = data if (isinstance(data[0], str) and data[0] == "staged") else self.prefetch(data)
+                    if self.batched_data and not isinstance(self.batched_data[0][0], str):
+                        self.batched_data[0] = self.prefetch(self.batched_data[0])   # H2D of the next batch overlaps this update
+                    self.priority_queue.put(self.update_from_batch(staged))
                     break
             if self.replay is not None and len(self.replay) >= config.learning_starts:
                 self.update_from_replay()
