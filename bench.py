@@ -299,8 +299,13 @@ def run_ours(args):
         if ms_unroll is not None:
             fl = flops_per_sequence(C) * B
             ach = fl / (ms_unroll * 1e-3) / 1e12
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "r01_unroll_traffic.json")
+            if os.path.exists(tpath) and C == 4 and args.precision == "strict":
+                with open(tpath) as f:
+                    traffic = json.load(f)["bytes"]        # dram bytes of the same launches from the committed ncu pass
             line["roofline"] = {"bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                                "frac": ach / peaks["tflops"], "traffic": None, "peak_source": peaks["source"],
+                                "frac": ach / peaks["tflops"], "traffic": traffic, "peak_source": peaks["source"],
                                 "kernel": "K1+K1b unroll group (forward online+target, BPTT backward): umma2_kernel launches",
                                 "ms": ms_unroll, "algorithmic_gflop_per_launch": fl / 1e9}
         if world == 1 and not args.no_cpu_baseline:
