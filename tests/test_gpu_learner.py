@@ -190,3 +190,27 @@ def test_full_size_batch_td_parity(mode):
         assert err.max() < 1e-4 and e_pr < 1e-4
     finally:
         _lib.lib().r2d2_set_fast_math(prev)
+
+
+@pytest.mark.parametrize("B,C,A_,burn,learn,fwd", [(72, 1, 9, 4, 3, 2), (5, 4, 9, 6, 5, 3), (6, 1, 4, 5, 4, 2), (6, 1, 15, 5, 4, 2)])
+def test_shape_sweep_vs_oracle(B, C, A_, burn, learn, fwd):
+    """Other shapes of the same kernels: B > 64 (per-step recurrence path, several M tiles), 4-channel frames
+    (BASELINE.json's 84x84x4), smallest / largest supported action counts."""
+    torch.set_num_threads(min(32, os.cpu_count() or 8))
+    from r2d2_b200.learner_core import DeviceLearner
+    params = init_params(A_, in_channels=C, seed=11)
+    tparams = init_params(A_, in_channels=C, seed=12)
+    d = synth.synthetic_batch(B, A_, burn_in=burn, learning=learn, forward=fwd, channels=C, seed=31, ragged=True)
+    st = LearnerState(online={k: v.clone() for k, v in params.items()}, target=tparams)
+    out = learner_update(st, synth.to_torch_batch(d), max_forward=fwd)
+    dl = DeviceLearner(A_, B, d["obs"].shape[1], in_channels=C, max_learning=learn, max_forward=fwd)
+    dl.load_state_dict(params, tparams)
+    dl.update(dl.prepare(_torch_batch(d)))
+    torch.cuda.synchronize()
+    rows = int(dl.rows.item())
+    e_q = (dl.q[:rows].cpu() - out["q"]).abs().max().item()
+    e_td = np.abs(dl.td[:rows].cpu().numpy() - out["td"]).max()
+    e_pr = np.abs(dl.prio.cpu().numpy() - out["priorities"]).max()
+    e_p = max((dl.online.views[k].cpu() - st.online[k]).abs().max().item() for k in st.online)
+    _diag(f"shape B={B} C={C} A={A_} b/l/f={burn}/{learn}/{fwd}: q {e_q:.3e} td {e_td:.3e} prio {e_pr:.3e} params {e_p:.3e}")
+    assert e_q < 2e-5 and e_td < 1e-4 and e_pr < 1e-4 and e_p < 2e-5

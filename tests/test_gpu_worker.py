@@ -95,3 +95,26 @@ def test_learner_loop_on_hbm_replay(monkeypatch):
     assert changed > 0                                               # weights were published to the shared model (every 4 updates)
     leaves = learner.replay.tree.ptree[learner.replay.tree.num_nodes // 2:]
     assert np.isfinite(leaves).all() and (leaves >= 0).all()
+
+
+def test_learner_run_consumes_reference_tuples(golden_dir, monkeypatch):
+    """Learner.run() fed reference-format 14-tuples through its batch queue (the topology where a CPU-side sampler
+    produces host batches): priorities come back on the priority queue in the reference's (idxes, priorities, old_ptr,
+    loss) format and match the recorded reference outputs."""
+    from r2d2_b200 import config
+    from r2d2_b200.worker import Learner
+    g = np.load(os.path.join(golden_dir, "learner_ragged.npz"))
+    batch_size, K, bl, ls, bi, fs, seed0, num_blocks = (int(x) for x in g["meta"])
+    monkeypatch.setattr(config, "batch_size", batch_size)
+    monkeypatch.setattr(config, "training_steps", K)
+    rb, _ = build_oracle_replay(synth.RAGGED_SCRIPT, num_blocks, batch_size)
+    bq, pq = queue.Queue(), queue.Queue()
+    for k in range(K):
+        bq.put(_tuple14(sample_with_seed(rb, seed0 + k)))
+    learner = Learner(bq, pq, _network(init_params(A, seed=3)), save_interval=10 ** 9)
+    learner.run()
+    for k in range(K):
+        idxes, prio, old_ptr, loss = pq.get(timeout=5)
+        np.testing.assert_array_equal(idxes, g[f"k{k}_out_idxes"])
+        np.testing.assert_allclose(prio, g[f"k{k}_out_priorities"], atol=1e-4, rtol=0)
+        assert abs(loss - float(g[f"k{k}_out_loss"])) < 2e-5
