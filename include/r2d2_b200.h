@@ -105,6 +105,8 @@ int r2d2_net_destroy(r2d2_net* n);
 /* Row capacity of the Q outputs ([rows_capacity][A], >= B*Lmax). */
 int r2d2_net_rows_capacity(const r2d2_net* n);
 int r2d2_net_ku(const r2d2_net* n);
+/* Device pointer of the frame staging buffer conv1 reads: bf16 [B*T][21][21][16*C] (frames after space-to-depth by 4). */
+void* r2d2_net_s2d_buffer(r2d2_net* n);
 /* Re-lay out `params` for slot `which` (0 = online, 1 = target).  Call after every change of that
  * slot's parameters (optimizer step, target sync; worker.py:365,376-377). */
 int r2d2_net_pack(r2d2_net* n, int which, const float* params, void* stream);
@@ -121,6 +123,7 @@ int r2d2_net_forward(r2d2_net* n, int which, const float* params, const uint8_t*
                      const uint8_t* fwd, float* q_learn_out, float* q_shift_out, void* stream);
 /* The three Q tensors of one learner update (worker.py:346,347,352) in one call: both slots are unrolled on the
  * same batch and the two recurrences advance together in shared launches. */
+/* obs may be NULL when the frames were already staged by r2d2_replay_gather_s2d. */
 int r2d2_net_forward_pair(r2d2_net* n, const float* params_online, const float* params_target, const uint8_t* obs,
                           const uint8_t* last_action, const float* last_reward, const float* hidden, const uint8_t* burn,
                           const uint8_t* learn, const uint8_t* fwd, float* q_learn_out, float* qn_online_out,
@@ -161,6 +164,12 @@ int r2d2_replay_ingest(r2d2_replay* r, int block_idx, const void* host_blob, int
 int r2d2_replay_gather(r2d2_replay* r, const int64_t* idx, const float* isw, int B, int T, uint8_t* obs, uint8_t* last_action,
                        float* last_reward, float* hidden, uint8_t* action, float* n_step_reward, float* gamma, uint8_t* burn,
                        uint8_t* learn, uint8_t* fwd, float* is_weights_rows, int32_t* rows_out, void* stream);
+
+/* The same gather writing the frames straight into the network's space-to-depth bf16 staging buffer
+ * (s2d_out = r2d2_net_s2d_buffer(net)); r2d2_net_forward_pair is then called with obs == NULL. */
+int r2d2_replay_gather_s2d(r2d2_replay* r, const int64_t* idx, const float* isw, int B, int T, void* s2d_out, uint8_t* last_action,
+                           float* last_reward, float* hidden, uint8_t* action, float* n_step_reward, float* gamma, uint8_t* burn,
+                           uint8_t* learn, uint8_t* fwd, float* is_weights_rows, int32_t* rows_out, void* stream);
 
 /* GEMM backend of every contraction in K1/K1b: 0 = fp32 CUDA-core FFMA (on-device numerical
  * reference), 1 = tcgen05 bf16x3 split (hi*hi + hi*lo + lo*hi, fp32 accumulate in TMEM: parity mode,

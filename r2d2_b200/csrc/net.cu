@@ -467,21 +467,52 @@ __global__ void reduce_route_kernel(const float* __restrict__ ws, int splits, in
     }
 }
 
-// deterministic column sums of a (split or fp32) [M][N] tensor: partial[p][n] over row chunk p, then final routing
+// deterministic column sums of a (split or fp32) [M][N] tensor: partial[p][n] over row chunk p, then final routing.
+// Split tensors are read 8 columns (16 bytes per plane) at a time: N % 8 == 0.
 template <bool kSplit>
-__global__ void colsum_partial_kernel(const float* __restrict__ X, SplitC S, int M, int N, int chunk, float* __restrict__ part) {
-    __shared__ float s[8][33];
-    const int col = blockIdx.x * 32 + threadIdx.x, p = blockIdx.y;
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ X, SplitC S, int M, int N, int chunk,
+                                                             float* __restrict__ part) {
+    const int p = blockIdx.y;
     const int r0 = p * chunk, r1 = min(M, r0 + chunk);
-    float acc = 0.f;
-    if (col < N)
-        for (int r = r0 + threadIdx.y; r < r1; r += 8) acc += kSplit ? split_load(S.hi, S.lo, (size_t)r * N + col) : X[(size_t)r * N + col];
-    s[threadIdx.y][threadIdx.x] = acc;
-    __syncthreads();
-    if (threadIdx.y == 0 && col < N) {
-        float t = 0.f;
-        for (int y = 0; y < 8; ++y) t += s[y][threadIdx.x];
-        part[(size_t)p * N + col] = t;
+    if constexpr (kSplit) {
+        __shared__ float s[256][9];
+        const int groups = N >> 3;                               // 8-column groups per row
+        const int gpb = min(groups, 32);                         // groups handled by one block (x dimension)
+        const int g = blockIdx.x * gpb + (threadIdx.x % gpb);
+        const int rl = threadIdx.x / gpb, rstep = 256 / gpb;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (g < groups)
+            for (int r = r0 + rl; r < r1; r += rstep) {
+                float v[8];
+                split_load8(S.hi, S.lo, (size_t)r * N + g * 8, v);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] += v[i];
+            }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[threadIdx.x][i] = acc[i];
+        __syncthreads();
+        if (rl == 0 && g < groups) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float t = 0.f;
+                for (int y = 0; y < rstep; ++y) t += s[y * gpb + (threadIdx.x % gpb)][i];
+                part[(size_t)p * N + g * 8 + i] = t;
+            }
+        }
+    } else {
+        __shared__ float s[8][33];
+        const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+        const int col = blockIdx.x * 32 + tx;
+        float acc = 0.f;
+        if (col < N)
+            for (int r = r0 + ty; r < r1; r += 8) acc += X[(size_t)r * N + col];
+        s[ty][tx] = acc;
+        __syncthreads();
+        if (ty == 0 && col < N) {
+            float t = 0.f;
+            for (int y = 0; y < 8; ++y) t += s[y][tx];
+            part[(size_t)p * N + col] = t;
+        }
     }
 }
 // row sums of a split [R][N] tensor (bias gradient of the channel-major dpre1T): partial[p][r]
@@ -519,15 +550,16 @@ __global__ void colsum_final_kernel(const float* __restrict__ part, int P, int N
 constexpr int kColP = 128;
 static cudaError_t colsum_split(SplitC S, int M, int N, int kind, float* g, int64_t o0, int64_t o1, int A, float* colws, cudaStream_t s) {
     const int chunk = (M + kColP - 1) / kColP;
-    dim3 grid((N + 31) / 32, kColP), block(32, 8);
-    colsum_partial_kernel<true><<<grid, block, 0, s>>>(nullptr, S, M, N, chunk, colws);
+    const int groups = N / 8, gpb = groups < 32 ? groups : 32;
+    dim3 grid((groups + gpb - 1) / gpb, kColP);
+    colsum_partial_kernel<true><<<grid, 256, 0, s>>>(nullptr, S, M, N, chunk, colws);
     colsum_final_kernel<<<(N + 127) / 128, 128, 0, s>>>(colws, kColP, N, kind, g, o0, o1, A);
     return cudaGetLastError();
 }
 static cudaError_t colsum_f32(const float* X, int M, int N, int kind, float* g, int64_t o0, int64_t o1, int A, float* colws, cudaStream_t s) {
     const int chunk = (M + kColP - 1) / kColP;
-    dim3 grid((N + 31) / 32, kColP), block(32, 8);
-    colsum_partial_kernel<false><<<grid, block, 0, s>>>(X, SplitC{nullptr, nullptr}, M, N, chunk, colws);
+    dim3 grid((N + 31) / 32, kColP);
+    colsum_partial_kernel<false><<<grid, 256, 0, s>>>(X, SplitC{nullptr, nullptr}, M, N, chunk, colws);
     colsum_final_kernel<<<(N + 127) / 128, 128, 0, s>>>(colws, kColP, N, kind, g, o0, o1, A);
     return cudaGetLastError();
 }
@@ -654,6 +686,8 @@ int r2d2_net_destroy(r2d2_net* n) {
 }
 
 int r2d2_net_rows_capacity(const r2d2_net* n) { return n ? n->Rmax : -1; }
+/* device pointer of the space-to-depth frame staging buffer, bf16 [B*T][21][21][16*C] */
+void* r2d2_net_s2d_buffer(r2d2_net* n) { return n ? (void*)n->s2d : nullptr; }
 int r2d2_net_ku(const r2d2_net* n) { return n ? n->KU : -1; }
 
 /* re-lay out the caller's flat parameter buffer (reference state_dict layout) for slot `which` */
@@ -717,8 +751,10 @@ static int net_prep(r2d2_net* n, const uint8_t* obs, const float* hidden, const 
                     const uint8_t* fwd, cudaStream_t s) {
     prep_rows_kernel<<<1, 256, (n->B + 1) * sizeof(int), s>>>(burn, learn, fwd, hidden, n->ac[0].HsX, n->ac[1].HsX, n->B, n->F, n->Rmax, n->row_src,
                                                              n->len_full, n->len_learn, n->d_rows);
-    const int64_t total = (int64_t)n->NF * n->C * 84 * 21;
-    s2d_kernel<<<cdiv(total, 256), 256, 0, s>>>(obs, n->s2d, n->C, total);
+    if (obs) {                                             // obs == NULL: the frames were staged by r2d2_replay_gather_s2d
+        const int64_t total = (int64_t)n->NF * n->C * 84 * 21;
+        s2d_kernel<<<cdiv(total, 256), 256, 0, s>>>(obs, n->s2d, n->C, total);
+    }
     R2D2_LAUNCH_CHECK();
     return R2D2_OK;
 }
@@ -852,7 +888,7 @@ int r2d2_net_forward_pair(r2d2_net* n, const float* params_online, const float* 
                           const uint8_t* last_action, const float* last_reward, const float* hidden, const uint8_t* burn,
                           const uint8_t* learn, const uint8_t* fwd, float* q_learn_out, float* qn_online_out,
                           float* qn_target_out, void* stream) {
-    R2D2_REQUIRE(n && params_online && params_target && obs && last_action && last_reward && hidden && burn && learn && fwd &&
+    R2D2_REQUIRE(n && params_online && params_target && last_action && last_reward && hidden && burn && learn && fwd &&
                      q_learn_out && qn_online_out && qn_target_out,
                  "bad arguments");
     cudaStream_t s = as_stream(stream);

@@ -8,6 +8,8 @@
 //   * gather is two launches: a one-CTA metadata pass (window bounds, ragged row offsets) and a
 //     (T x B)-CTA copy pass moving 16-byte chunks (a C x 84 x 84 u8 frame is 441*C chunks).
 // Bound: HBM.  Algorithmic bytes per sampled sequence: 2 * (b+l+f) * 7056 * C  (read + write) + ~10 KB side data.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace r2d2 {
@@ -74,7 +76,8 @@ __global__ void replay_meta_kernel(const uint8_t* __restrict__ store, ReplayLayo
 
 __global__ void __launch_bounds__(256) replay_copy_kernel(const uint8_t* __restrict__ store, ReplayLayout lay, const SeqDesc* __restrict__ desc,
                                                           const float* __restrict__ isw, int T, int C, int A, int H, int64_t frame_bytes,
-                                                          uint8_t* __restrict__ obs, uint8_t* __restrict__ last_action,
+                                                          uint8_t* __restrict__ obs, __nv_bfloat16* __restrict__ s2d,
+                                                          uint8_t* __restrict__ last_action,
                                                           float* __restrict__ last_reward, float* __restrict__ hidden,
                                                           uint8_t* __restrict__ action, float* __restrict__ nsr, float* __restrict__ gam,
                                                           float* __restrict__ isw_rows) {
@@ -83,16 +86,32 @@ __global__ void __launch_bounds__(256) replay_copy_kernel(const uint8_t* __restr
     const uint8_t* blob = store + d.blob;
     const int len = d.b + d.l + d.f;
     const int64_t chunks = frame_bytes / 16;
-    uint4* dst = reinterpret_cast<uint4*>(obs + ((int64_t)n * T + t) * frame_bytes);
+    uint4* dst = obs ? reinterpret_cast<uint4*>(obs + ((int64_t)n * T + t) * frame_bytes) : nullptr;
+    // fused space-to-depth output (the layout conv1 consumes, net.cu): [Y][X][c*16 + r*4 + q] bf16, pixel (c, 4Y+r, 4X+q)
+    __nv_bfloat16* sdst = s2d ? s2d + ((int64_t)n * T + t) * (441 * 16 * C) : nullptr;
+    if (sdst) {
+        const int words = C * 84 * 21;
+        const uint32_t* wsrc = reinterpret_cast<const uint32_t*>(blob + lay.obs + (int64_t)(d.start + (t < len ? t : 0)) * frame_bytes);
+        for (int i = threadIdx.x; i < words; i += blockDim.x) {
+            const int X = i % 21, y = (i / 21) % 84, c = i / (21 * 84);
+            const uint32_t w = (t < len) ? __ldg(wsrc + i) : 0u;
+            const __nv_bfloat162 p0 = __floats2bfloat162_rn((float)(w & 255u), (float)((w >> 8) & 255u));
+            const __nv_bfloat162 p1 = __floats2bfloat162_rn((float)((w >> 16) & 255u), (float)(w >> 24));
+            uint2 o;
+            o.x = *reinterpret_cast<const uint32_t*>(&p0);
+            o.y = *reinterpret_cast<const uint32_t*>(&p1);
+            *reinterpret_cast<uint2*>(sdst + (((y >> 2) * 21 + X) * 16 * C + c * 16 + (y & 3) * 4)) = o;
+        }
+    }
     if (t < len) {
         const uint4* src = reinterpret_cast<const uint4*>(blob + lay.obs + (int64_t)(d.start + t) * frame_bytes);
-        for (int64_t i = threadIdx.x; i < chunks; i += blockDim.x) dst[i] = __ldg(src + i);
+        if (dst) for (int64_t i = threadIdx.x; i < chunks; i += blockDim.x) dst[i] = __ldg(src + i);
         if (threadIdx.x < A) last_action[((int64_t)n * T + t) * A + threadIdx.x] = blob[lay.last_action + (int64_t)(d.start + t) * A + threadIdx.x];
         if (threadIdx.x == 0)
             last_reward[(int64_t)n * T + t] = reinterpret_cast<const float*>(blob + lay.last_reward)[d.start + t];
     } else {                                           // pad_sequence zero padding at the END (worker.py:212-214)
         const uint4 z = make_uint4(0, 0, 0, 0);
-        for (int64_t i = threadIdx.x; i < chunks; i += blockDim.x) dst[i] = z;
+        if (dst) for (int64_t i = threadIdx.x; i < chunks; i += blockDim.x) dst[i] = z;
         if (threadIdx.x < A) last_action[((int64_t)n * T + t) * A + threadIdx.x] = 0;
         if (threadIdx.x == 0) last_reward[(int64_t)n * T + t] = 0.f;
     }
@@ -183,10 +202,11 @@ int r2d2_replay_ingest(r2d2_replay* r, int block_idx, const void* host_blob, int
  * action u8 [rows], n_step_reward f32 [rows], gamma f32 [rows], burn/learn/fwd u8 [B], is_weights f32 [rows] (per-sequence
  * weight repeated over its learning steps), rows_out i32[1].  T >= burn_in+learning+forward; ragged arrays need capacity
  * B*learning. */
-int r2d2_replay_gather(r2d2_replay* r, const int64_t* idx, const float* isw, int B, int T, uint8_t* obs, uint8_t* last_action,
-                       float* last_reward, float* hidden, uint8_t* action, float* n_step_reward, float* gamma, uint8_t* burn,
-                       uint8_t* learn, uint8_t* fwd, float* is_weights_rows, int32_t* rows_out, void* stream) {
-    R2D2_REQUIRE(r && idx && isw && obs && last_action && last_reward && hidden && action && n_step_reward && gamma && burn && learn &&
+static int replay_gather_impl(r2d2_replay* r, const int64_t* idx, const float* isw, int B, int T, uint8_t* obs, void* s2d,
+                              uint8_t* last_action, float* last_reward, float* hidden, uint8_t* action, float* n_step_reward,
+                              float* gamma, uint8_t* burn, uint8_t* learn, uint8_t* fwd, float* is_weights_rows, int32_t* rows_out,
+                              void* stream) {
+    R2D2_REQUIRE(r && idx && isw && (obs || s2d) && last_action && last_reward && hidden && action && n_step_reward && gamma && burn && learn &&
                      fwd && is_weights_rows && rows_out && B >= 1 && T >= r->burn_in + r->learning + r->forward,
                  "bad arguments");
     if (B > r->desc_cap) {
@@ -196,10 +216,29 @@ int r2d2_replay_gather(r2d2_replay* r, const int64_t* idx, const float* isw, int
     }
     cudaStream_t s = as_stream(stream);
     replay_meta_kernel<<<1, 256, B * sizeof(int), s>>>(r->store, r->lay, r->spb, idx, B, r->desc, burn, learn, fwd, rows_out);
-    replay_copy_kernel<<<dim3(T, B), 256, 0, s>>>(r->store, r->lay, r->desc, isw, T, r->C, r->A, r->H, r->frame_bytes, obs, last_action,
+    replay_copy_kernel<<<dim3(T, B), 256, 0, s>>>(r->store, r->lay, r->desc, isw, T, r->C, r->A, r->H, r->frame_bytes, obs,
+                                                  (__nv_bfloat16*)s2d, last_action,
                                                   last_reward, hidden, action, n_step_reward, gamma, is_weights_rows);
     R2D2_LAUNCH_CHECK();
     return R2D2_OK;
+}
+
+int r2d2_replay_gather(r2d2_replay* r, const int64_t* idx, const float* isw, int B, int T, uint8_t* obs, uint8_t* last_action,
+                       float* last_reward, float* hidden, uint8_t* action, float* n_step_reward, float* gamma, uint8_t* burn,
+                       uint8_t* learn, uint8_t* fwd, float* is_weights_rows, int32_t* rows_out, void* stream) {
+    return replay_gather_impl(r, idx, isw, B, T, obs, nullptr, last_action, last_reward, hidden, action, n_step_reward, gamma, burn,
+                              learn, fwd, is_weights_rows, rows_out, stream);
+}
+
+/* Same gather with the frames written directly in the network's space-to-depth bf16 staging layout
+ * (s2d_out = r2d2_net_s2d_buffer(net), [B*T][21][21][16C]) instead of as raw u8 frames: the learner then calls
+ * r2d2_net_forward_pair with obs == NULL and one 2 x 85 x 7056 x C byte round trip through HBM per sequence disappears. */
+int r2d2_replay_gather_s2d(r2d2_replay* r, const int64_t* idx, const float* isw, int B, int T, void* s2d_out, uint8_t* last_action,
+                           float* last_reward, float* hidden, uint8_t* action, float* n_step_reward, float* gamma, uint8_t* burn,
+                           uint8_t* learn, uint8_t* fwd, float* is_weights_rows, int32_t* rows_out, void* stream) {
+    R2D2_REQUIRE(s2d_out, "null s2d buffer");
+    return replay_gather_impl(r, idx, isw, B, T, nullptr, s2d_out, last_action, last_reward, hidden, action, n_step_reward, gamma,
+                              burn, learn, fwd, is_weights_rows, rows_out, stream);
 }
 
 }  // extern "C"

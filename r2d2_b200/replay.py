@@ -138,10 +138,25 @@ class DeviceReplay:
             self.num_episodes += 1
 
     # ------------------------------------------------------------------ sample_batch (worker.py:163-240), on device
-    def sample(self, unit_uniforms: Optional[torch.Tensor] = None):
-        """Returns (batch dict of device tensors, idxes int64 device, old_ptr)."""
+    def sample(self, unit_uniforms: Optional[torch.Tensor] = None, fuse_into=None):
+        """Returns (batch dict of device tensors, idxes int64 device, old_ptr).  With fuse_into = a DeviceLearner whose
+        shape matches, frames are written straight into its space-to-depth staging buffer and batch["obs"] is None."""
         idx, isw = self.tree.sample_device(self.batch_size, unit_uniforms)
+        if fuse_into is not None:
+            return self.gather_fused(idx, isw, fuse_into), idx, self.block_ptr
         return self.gather(idx, isw), idx, self.block_ptr
+
+    def gather_fused(self, idx: torch.Tensor, isw: torch.Tensor, core) -> dict:
+        assert core.B == self.batch_size and core.T == self.T and core.C == self.C
+        b, p = self.batch, _lib.ptr
+        s2d = _lib.lib().r2d2_net_s2d_buffer(core._h)
+        _lib.check(_lib.lib().r2d2_replay_gather_s2d(self._h, p(idx), p(isw), self.batch_size, self.T, s2d, p(b["last_action"]),
+                                                     p(b["last_reward"]), p(b["hidden"]), p(b["action"]), p(b["n_step_reward"]),
+                                                     p(b["gamma"]), p(b["burn_in"]), p(b["learning"]), p(b["forward"]),
+                                                     p(b["is_weights"]), p(b["rows"]), _lib.stream_ptr()))
+        out = dict(b)
+        out["obs"] = None
+        return out
 
     def gather(self, idx: torch.Tensor, isw: torch.Tensor) -> dict:
         b, p = self.batch, _lib.ptr

@@ -280,7 +280,7 @@ class Learner:
 
     # -- one update from the HBM-resident replay (sample -> update -> priority update, no host round trip) --------
     def update_from_replay(self):
-        batch, idx, old_ptr = self.replay.sample()
+        batch, idx, old_ptr = self.replay.sample(fuse_into=self.core)     # frames go straight into conv1's staging layout
         self.core.update(batch)
         self.replay.update_priorities(idx, self.core.prio, old_ptr)
         self.env_steps = self.replay.env_steps

@@ -102,3 +102,23 @@ def test_replay_buffer_surface_reproduces_reference_sample(golden_dir):
     rb.update_priorities(g["upd_idx"], g["upd_td"], int(g["upd_gt_old_ptr"]), 0.5)
     np.testing.assert_allclose(rb.priority_tree.ptree, g["upd_gt_tree"], rtol=1e-6)
     assert rb.training_steps == 1 and rb.sum_loss == 0.5
+
+
+def test_fused_gather_into_s2d_staging_matches_unfused():
+    """r2d2_replay_gather_s2d (frames written straight into conv1's space-to-depth staging buffer, obs == NULL in the
+    forward call) must give bit-identical learner outputs to gather -> raw frames -> s2d pass."""
+    from oracle.learner import init_params
+    from r2d2_b200.learner_core import DeviceLearner
+    dev, cpu = _build_device_replay(synth.RAGGED_SCRIPT, 8, 8)
+    core = DeviceLearner(A, 8, 85)
+    core.load_state_dict(init_params(A, seed=3))
+    r = torch.from_numpy(np.random.RandomState(5).random_sample(8)).cuda()
+    b1, idx1, _ = dev.sample(r)
+    core.compute_forward(b1)
+    q1, td1 = core.q.clone(), core.td.clone()
+    b1["obs"].zero_()                                          # make sure the fused path cannot read stale raw frames
+    b2, idx2, _ = dev.sample(r, fuse_into=core)
+    assert b2["obs"] is None and torch.equal(idx1, idx2)
+    core.compute_forward(b2)
+    torch.cuda.synchronize()
+    assert torch.equal(core.q, q1) and torch.equal(core.td, td1)
