@@ -136,22 +136,26 @@ __global__ void pack_kernel(const float* __restrict__ p, const int64_t* __restri
     if (i < 2 * H) pk.bh0[i] = (i < H) ? p[off[P_A0B] + i] : p[off[P_V0B] + i - H];
 }
 
-// u8 frames (C,84,84) -> space-to-depth bf16 [f][Y][X][c*16 + r*4 + q],  pixel (c, 4Y+r, 4X+q)
-__global__ void s2d_kernel(const uint8_t* __restrict__ obs, bf16* __restrict__ s2d, int C, int64_t total /* NF*C*84*21 */) {
+// u8 frames (C,84,84) -> space-to-depth bf16 [f][Y][X][c*16 + r*4 + q],  pixel (c, 4Y+r, 4X+q).
+// item = (f, c, Y, X): four coalesced 32-bit reads -> one 32-byte sector of bf16
+__global__ void s2d_kernel(const uint8_t* __restrict__ obs, bf16* __restrict__ s2d, int C, int64_t total /* NF*C*441 */) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= total) return;
-    const int X = i % 21;
-    const int y = (i / 21) % 84;
-    const int c = (i / (21 * 84)) % C;
-    const int64_t f = i / (21 * 84 * (int64_t)C);
-    const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(obs) + i);     // 4 consecutive x of one row
-    const int Y = y >> 2, r = y & 3;
-    const __nv_bfloat162 p0 = __floats2bfloat162_rn((float)(w & 255u), (float)((w >> 8) & 255u));
-    const __nv_bfloat162 p1 = __floats2bfloat162_rn((float)((w >> 16) & 255u), (float)(w >> 24));
-    uint2 o;
-    o.x = *reinterpret_cast<const uint32_t*>(&p0);
-    o.y = *reinterpret_cast<const uint32_t*>(&p1);
-    *reinterpret_cast<uint2*>(s2d + ((f * 21 + Y) * 21 + X) * (16 * C) + c * 16 + r * 4) = o;
+    const int X = i % 21, Y = (i / 21) % 21, c = (i / 441) % C;
+    const int64_t f = i / (441 * (int64_t)C);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(obs) + ((f * C + c) * 84 + 4 * Y) * 21 + X;
+    uint32_t o[8];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const uint32_t w = __ldg(src + r * 21);
+        const __nv_bfloat162 p0 = __floats2bfloat162_rn((float)(w & 255u), (float)((w >> 8) & 255u));
+        const __nv_bfloat162 p1 = __floats2bfloat162_rn((float)((w >> 16) & 255u), (float)(w >> 24));
+        o[2 * r] = *reinterpret_cast<const uint32_t*>(&p0);
+        o[2 * r + 1] = *reinterpret_cast<const uint32_t*>(&p1);
+    }
+    uint4* q = reinterpret_cast<uint4*>(s2d + ((f * 21 + Y) * 21 + X) * (16 * C) + c * 16);
+    q[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    q[1] = make_uint4(o[4], o[5], o[6], o[7]);
 }
 
 // row maps + sequence lengths + split copy of h0.  One CTA.  model.py:102-111 (shifted rows) and model.py:143.
@@ -752,7 +756,7 @@ static int net_prep(r2d2_net* n, const uint8_t* obs, const float* hidden, const 
     prep_rows_kernel<<<1, 256, (n->B + 1) * sizeof(int), s>>>(burn, learn, fwd, hidden, n->ac[0].HsX, n->ac[1].HsX, n->B, n->F, n->Rmax, n->row_src,
                                                              n->len_full, n->len_learn, n->d_rows);
     if (obs) {                                             // obs == NULL: the frames were staged by r2d2_replay_gather_s2d
-        const int64_t total = (int64_t)n->NF * n->C * 84 * 21;
+        const int64_t total = (int64_t)n->NF * n->C * 441;
         s2d_kernel<<<cdiv(total, 256), 256, 0, s>>>(obs, n->s2d, n->C, total);
     }
     R2D2_LAUNCH_CHECK();

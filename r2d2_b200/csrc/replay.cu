@@ -90,17 +90,23 @@ __global__ void __launch_bounds__(256) replay_copy_kernel(const uint8_t* __restr
     // fused space-to-depth output (the layout conv1 consumes, net.cu): [Y][X][c*16 + r*4 + q] bf16, pixel (c, 4Y+r, 4X+q)
     __nv_bfloat16* sdst = s2d ? s2d + ((int64_t)n * T + t) * (441 * 16 * C) : nullptr;
     if (sdst) {
-        const int words = C * 84 * 21;
+        // item = (c, Y, X): four coalesced 32-bit reads (rows 4Y..4Y+3, pixels 4X..4X+3) -> one 32-byte sector of bf16
+        const int items = C * 441;
         const uint32_t* wsrc = reinterpret_cast<const uint32_t*>(blob + lay.obs + (int64_t)(d.start + (t < len ? t : 0)) * frame_bytes);
-        for (int i = threadIdx.x; i < words; i += blockDim.x) {
-            const int X = i % 21, y = (i / 21) % 84, c = i / (21 * 84);
-            const uint32_t w = (t < len) ? __ldg(wsrc + i) : 0u;
-            const __nv_bfloat162 p0 = __floats2bfloat162_rn((float)(w & 255u), (float)((w >> 8) & 255u));
-            const __nv_bfloat162 p1 = __floats2bfloat162_rn((float)((w >> 16) & 255u), (float)(w >> 24));
-            uint2 o;
-            o.x = *reinterpret_cast<const uint32_t*>(&p0);
-            o.y = *reinterpret_cast<const uint32_t*>(&p1);
-            *reinterpret_cast<uint2*>(sdst + (((y >> 2) * 21 + X) * 16 * C + c * 16 + (y & 3) * 4)) = o;
+        for (int i = threadIdx.x; i < items; i += blockDim.x) {
+            const int X = i % 21, Y = (i / 21) % 21, c = i / 441;
+            uint32_t o[8];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const uint32_t w = (t < len) ? __ldg(wsrc + (c * 84 + 4 * Y + r) * 21 + X) : 0u;
+                const __nv_bfloat162 p0 = __floats2bfloat162_rn((float)(w & 255u), (float)((w >> 8) & 255u));
+                const __nv_bfloat162 p1 = __floats2bfloat162_rn((float)((w >> 16) & 255u), (float)(w >> 24));
+                o[2 * r] = *reinterpret_cast<const uint32_t*>(&p0);
+                o[2 * r + 1] = *reinterpret_cast<const uint32_t*>(&p1);
+            }
+            uint4* q = reinterpret_cast<uint4*>(sdst + ((Y * 21 + X) * 16 * C + c * 16));
+            q[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            q[1] = make_uint4(o[4], o[5], o[6], o[7]);
         }
     }
     if (t < len) {
