@@ -189,6 +189,11 @@ int r2d2_set_fast_math(int mode);
 int r2d2_debug_gemm2(int ubn, int a_major, int b_major, int M, int N, int K, const void* a_hi, const void* a_lo,
                      const void* b_hi, const void* b_lo, float* C, int splits, void* stream);
 
+/* Hardware probe (tests/tools only): D[128][32] = A[shift .. shift+128)[64] . B[32][64]^T with a K-major
+ * SWIZZLE_128B descriptor whose start address is shifted by `shift` rows inside one staged buffer (A bf16 [144][64]);
+ * mode 1 also sets the descriptor's base_offset field to shift & 7. */
+int r2d2_debug_shift_probe(const void* A, const void* B, float* D, int shift, int mode, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * K5  clip_grad_norm_(max_norm) + Adam(lr, eps).step()  (worker.py:289,364-365) on the flat
  * buffers.  grad_scale: optional device float multiplied into the gradients first;

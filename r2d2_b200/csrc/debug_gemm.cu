@@ -103,3 +103,70 @@ int r2d2_debug_gemm(int backend, int ubn, int a_major, int b_major, int M, int N
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Experiment: can a K-major SWIZZLE_128B operand be addressed at a ROW-SHIFTED start (start + 128*s bytes) so that
+// several im2col taps read overlapping windows of ONE staged activation buffer?  mode 0: base_offset field = 0,
+// mode 1: base_offset = s & 7.  Data is stored with the absolute-address swizzle (chunk ^= physical_row & 7).
+// D[128][32] = A[s .. s+128)[64] . B[32][64]^T, bf16 hi only.
+// ------------------------------------------------------------------------------------------------
+namespace r2d2 {
+__global__ void __launch_bounds__(128) shift_probe_kernel(const bf16* __restrict__ A /*[144][64]*/, const bf16* __restrict__ Bm /*[32][64]*/,
+                                                          float* __restrict__ D /*[128][32]*/, int shift, int mode) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;
+    uint8_t* smem = smem_raw + pad;
+    const uint32_t sA = raw + pad, sB = sA + 144 * 128;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 144 * 128 + 32 * 128);
+    uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int u = tid; u < 144 * 8; u += 128) {
+        const int row = u >> 3, j = u & 7;
+        *reinterpret_cast<uint4*>(smem + (row >> 3) * 1024 + (row & 7) * 128 + ((j ^ (row & 7)) << 4)) =
+            *reinterpret_cast<const uint4*>(A + row * 64 + j * 8);
+    }
+    for (int u = tid; u < 32 * 8; u += 128) {
+        const int row = u >> 3, j = u & 7;
+        *reinterpret_cast<uint4*>(smem + 144 * 128 + (row >> 3) * 1024 + (row & 7) * 128 + ((j ^ (row & 7)) << 4)) =
+            *reinterpret_cast<const uint4*>(Bm + row * 64 + j * 8);
+    }
+    if (tid == 0) { mbar_init(smem_u32(bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(32) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *slot;
+    if (tid == 0) {
+        const uint32_t start = sA + 128u * (uint32_t)shift;
+        uint64_t adesc = umma_desc_sw128(start);
+        if (mode == 1) adesc |= (uint64_t)(shift & 7) << 49;                  // base_offset, bits [49,52)
+        const uint64_t bdesc = umma_desc_sw128(sB);
+        const uint32_t idesc = umma_idesc_bf16(32);
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, k ? 1u : 0u);
+        umma_commit(smem_u32(bar));
+    }
+    mbar_wait(smem_u32(bar), 0);
+    tc_fence_after();
+    for (int c = 0; c < 32; c += 16) {
+        float v[16];
+        tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, v);
+        for (int i = 0; i < 16; ++i) D[(warp * 32 + (tid & 31)) * 32 + c + i] = v[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(32) : "memory");
+}
+}  // namespace r2d2
+
+extern "C" int r2d2_debug_shift_probe(const void* A, const void* B, float* D, int shift, int mode, void* stream) {
+    R2D2_REQUIRE(A && B && D && shift >= 0 && shift <= 16, "bad arguments");
+    const int smem = 144 * 128 + 32 * 128 + 1024 + 64;
+    r2d2::shift_probe_kernel<<<1, 128, smem, r2d2::as_stream(stream)>>>((const r2d2::bf16*)A, (const r2d2::bf16*)B, D, shift, mode);
+    R2D2_LAUNCH_CHECK();
+    return R2D2_OK;
+}

@@ -25,6 +25,7 @@
 #include <map>
 
 #include "recurrence.cuh"
+#include "winconv.cuh"
 
 namespace r2d2 {
 
@@ -705,6 +706,44 @@ int r2d2_net_pack(r2d2_net* n, int which, const float* params, void* stream) {
 
 }  // extern "C"
 
+// Window-convolution epilogues (winconv.cuh): p is a pixel of the GW x GH INPUT grid; only the OW x OH pixels whose
+// window stays inside the frame are stored (row = f*OH*OW + gy*OW + gx of the usual NHWC activation matrix).
+static const bool g_window_conv = [] { const char* e = getenv("R2D2_WINDOW_CONV"); return !(e && e[0] == '0'); }();
+template <int GW, int GH, int OW, int OH>
+struct EpiWinBiasSplit {        // out(split)[row*64 + n] = relu(v + bias[n])
+    SplitW out; const float* bias;
+    __device__ __forceinline__ void store16(long long p, int n, const float (&v)[16]) const {
+        const int r = (int)(p % (GW * GH)), gy = r / GW, gx = r - gy * GW;
+        if (gy >= OH || gx >= OW) return;
+        const size_t row = (size_t)(p / (GW * GH)) * (OH * OW) + gy * OW + gx;
+#pragma unroll
+        for (int j = 0; j < 16; j += 8) {
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = fmaxf(v[j + i] + __ldg(bias + n + j + i), 0.f);
+            split_store8(out.hi, out.lo, row * 64 + n + j, o);
+        }
+    }
+};
+struct EpiWinConv1Pair {        // 21x21 s2d grid -> 20x20; columns 0-31 online act1, 32-63 target act1
+    SplitW out0, out1; const float* bias0; const float* bias1; float scale;
+    __device__ __forceinline__ void store16(long long p, int n, const float (&v)[16]) const {
+        const int r = (int)(p % 441), gy = r / 21, gx = r - gy * 21;
+        if (gy >= 20 || gx >= 20) return;
+        const size_t row = (size_t)(p / 441) * 400 + gy * 20 + gx;
+        const SplitW& o = n < 32 ? out0 : out1;
+        const float* b = n < 32 ? bias0 : bias1;
+        const int c = n & 31;
+#pragma unroll
+        for (int j = 0; j < 16; j += 8) {
+            float q[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) q[i] = fmaxf(v[j + i] * scale + __ldg(b + c + j + i), 0.f);
+            split_store8(o.hi, o.lo, row * 32 + c + j, q);
+        }
+    }
+};
+
 struct FwdArgs {
     const float* params; const uint8_t* obs; const uint8_t* last_action; const float* last_reward; const float* hidden;
 };
@@ -736,6 +775,12 @@ struct Epi2Conv1Pair {
 };
 template <int CH>
 static cudaError_t conv1_forward_pair(r2d2_net* n, const float* p0, const float* p1, cudaStream_t s) {
+    if constexpr (CH == 4) {
+        if (g_window_conv) {
+            EpiWinConv1Pair we{n->ac[0].act1, n->ac[1].act1, p0 + n->off[P_C1B], p1 + n->off[P_C1B], 1.f / 255.f};
+            return launch_winconv<21, 64, 2, 2, 64, false>(SplitC{n->s2d, nullptr}, (long long)n->NF * 441, SplitC{n->W1both.hi, n->W1both.lo}, we, s);
+        }
+    }
     SrcConvK<21, 21, 16 * CH, 20, 20, 2, 2, 1, false> a{n->s2d, nullptr, n->NF};
     SrcMatK b{n->W1both.hi, n->W1both.lo, 64, 64 * CH, 64 * CH};
     Epi2Conv1Pair e{n->ac[0].act1, n->ac[1].act1, p0 + n->off[P_C1B], p1 + n->off[P_C1B], n->NF * 400, 1.f / 255.f};
@@ -779,7 +824,10 @@ static int net_encode(r2d2_net* n, int which, const FwdArgs& fa, cudaStream_t s,
         Epi2BiasSplit<true> e{ac.act2, params + off[P_C2B], NF * 81, 64, 64, 1.f};
         R2D2_CUDA_CHECK((launch_umma2<64, LO_WEIGHT_B>(a, b, e, NF * 81, 64, 512, 1, s)));
     }
-    {
+    if (g_window_conv) {
+        EpiWinBiasSplit<9, 9, 7, 7> e{ac.act3, params + off[P_C3B]};
+        R2D2_CUDA_CHECK((launch_winconv<9, 64, 3, 3, 64, true>(SplitC{ac.act2.hi, ac.act2.lo}, (long long)NF * 81, SplitC{pk.W3p.hi, pk.W3p.lo}, e, s)));
+    } else {
         SrcConvK<9, 9, 64, 7, 7, 3, 3, 1> a{ac.act2.hi, ac.act2.lo, NF};
         SrcMatK b{pk.W3p.hi, pk.W3p.lo, 64, 576, 576};
         Epi2BiasSplit<true> e{ac.act3, params + off[P_C3B], NF * 49, 64, 64, 1.f};

@@ -1,0 +1,20 @@
+"""Does a row-shifted UMMA descriptor read the right rows of a swizzled smem buffer? (planning experiment for
+halo-reusing 'window' convolutions)"""
+import sys
+import torch
+sys.path.insert(0, ".")
+from r2d2_b200 import _lib
+_lib.require_device()
+torch.manual_seed(0)
+A = torch.randn(144, 64, device="cuda").bfloat16().contiguous()
+B = torch.randn(32, 64, device="cuda").bfloat16().contiguous()
+for mode in (0, 1):
+    line = []
+    for s in range(0, 12):
+        D = torch.zeros(128, 32, device="cuda")
+        _lib.check(_lib.lib().r2d2_debug_shift_probe(_lib.ptr(A), _lib.ptr(B), _lib.ptr(D), s, mode, _lib.stream_ptr()))
+        torch.cuda.synchronize()
+        ref = A[s:s + 128].float() @ B.float().t()
+        err = (D - ref).abs().max().item() / ref.abs().max().item()
+        line.append(f"{s}:{'ok' if err < 1e-2 else f'{err:.1e}'}")
+    print(f"base_offset mode {mode}: " + " ".join(line))
