@@ -143,11 +143,18 @@ __global__ void __launch_bounds__(128) shift_probe_kernel(const bf16* __restrict
     const uint32_t tmem = *slot;
     if (tid == 0) {
         const uint32_t start = sA + 128u * (uint32_t)shift;
-        uint64_t adesc = umma_desc_sw128(start);
-        if (mode == 1) adesc |= (uint64_t)(shift & 7) << 49;                  // base_offset, bits [49,52)
         const uint64_t bdesc = umma_desc_sw128(sB);
-        const uint32_t idesc = umma_idesc_bf16(32);
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, k ? 1u : 0u);
+        if (mode == 2) {
+            // A read MN-major: smem rows are the REDUCTION index (64 + shift lines of 64 M-elements), M = 64
+            const uint64_t adesc = umma_desc_sw128_mn(start, 8192);
+            const uint32_t idesc = ((1u << 4) | (1u << 7) | (1u << 10) | ((32u >> 3) << 17) | ((64u >> 4) << 24)) | (1u << 15);
+            for (int k = 0; k < 4; ++k) umma_bf16(tmem, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 2), idesc, k ? 1u : 0u);
+        } else {
+            uint64_t adesc = umma_desc_sw128(start);
+            if (mode == 1) adesc |= (uint64_t)(shift & 7) << 49;                  // base_offset, bits [49,52)
+            const uint32_t idesc = umma_idesc_bf16(32);
+            for (int k = 0; k < 4; ++k) umma_bf16(tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, k ? 1u : 0u);
+        }
         umma_commit(smem_u32(bar));
     }
     mbar_wait(smem_u32(bar), 0);

@@ -100,9 +100,12 @@ __global__ void pack_kernel(const float* __restrict__ p, const int64_t* __restri
         put_split(pk.W1s, i, w);
         put_split(w1both, (size_t)which * 32 * K1 + i, w);
     }
-    if (i < 64 * 512) {                          // conv2: [n][c][ky][kx] -> [n][(ky*4+kx)*32 + c]
-        const int n = i / 512, k = i % 512, tap = k >> 5, c = k & 31;
-        put_split(pk.W2p, i, p[off[P_C2W] + n * 512 + c * 16 + tap]);
+    if (i < 64 * 512) {                          // conv2 as a 2x2 stride-1 conv over act1 in space-to-depth-by-2 form:
+        {                                        // k = (dy*2+dx)*128 + (ry*2+rx)*32 + c  <->  W2[n][c][2dy+ry][2dx+rx]
+            const int n = i / 512, k = i % 512, tap = k >> 7, sub = (k >> 5) & 3, c = k & 31;
+            const int ky = 2 * (tap >> 1) + (sub >> 1), kx = 2 * (tap & 1) + (sub & 1);
+            put_split(pk.W2p, i, p[off[P_C2W] + n * 512 + c * 16 + ky * 4 + kx]);
+        }
         // dgrad, 4 parity classes: W2d[cls][c_in][(jy*2+jx)*64 + c_out] = W2[c_out][c_in][py+2jy][px+2jx]
         const int cls = i / (32 * 256), r = i % (32 * 256), ci = r / 256, kk = r % 256, j = kk >> 6, co = kk & 63;
         const int py = cls >> 1, px = cls & 1, jy = j >> 1, jx = j & 1;
@@ -400,7 +403,7 @@ struct Epi2DgradS2T {
         const long long pix = ((long long)f * 20 + 2 * yq + py) * 20 + 2 * xq + px;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-            const bool on = (__bfloat16_as_ushort(act.hi[pix * 32 + n + j]) & 0x7FFFu) != 0;
+            const bool on = (__bfloat16_as_ushort(act.hi[(size_t)m * 128 + (py * 2 + px) * 32 + n + j]) & 0x7FFFu) != 0;
             put_split(out, (size_t)((n + j) * NP + pix), on ? v[j] : 0.f);
         }
     }
@@ -422,8 +425,8 @@ struct Epi2DgradS2Q {
 #pragma unroll
             for (int py = 0; py < 2; ++py) {
                 const long long pix = pix00 + 20 * py;
-                const bool on0 = (__bfloat16_as_ushort(act.hi[pix * 32 + c]) & 0x7FFFu) != 0;
-                const bool on1 = (__bfloat16_as_ushort(act.hi[(pix + 1) * 32 + c]) & 0x7FFFu) != 0;
+                const bool on0 = (__bfloat16_as_ushort(act.hi[(size_t)m * 128 + (py * 2) * 32 + c]) & 0x7FFFu) != 0;      // act1 is s2d-by-2
+                const bool on1 = (__bfloat16_as_ushort(act.hi[(size_t)m * 128 + (py * 2 + 1) * 32 + c]) & 0x7FFFu) != 0;
                 uint32_t h, l;
                 split2(on0 ? v[ci * 4 + py * 2] : 0.f, on1 ? v[ci * 4 + py * 2 + 1] : 0.f, h, l);
                 const size_t o = (size_t)(c * NP + pix);
@@ -462,7 +465,10 @@ __global__ void reduce_route_kernel(const float* __restrict__ ws, int splits, in
             const int tap = n / (16 * C), ch = n % (16 * C), dy = tap >> 1, dx = tap & 1, c = ch >> 4, r = (ch >> 2) & 3, q = ch & 3;
             g[off[P_C1W] + (int64_t)m * 64 * C + c * 64 + (4 * dy + r) * 8 + 4 * dx + q] = s;
         } break;
-        case R_C2: { const int tap = n >> 5, c = n & 31; g[off[P_C2W] + m * 512 + c * 16 + tap] = s; } break;
+        case R_C2: {   // n = (dy*2+dx)*128 + (ry*2+rx)*32 + c  ->  [m][c][2dy+ry][2dx+rx]
+            const int tap = n >> 7, sub = (n >> 5) & 3, c = n & 31, ky = 2 * (tap >> 1) + (sub >> 1), kx = 2 * (tap & 1) + (sub & 1);
+            g[off[P_C2W] + m * 512 + c * 16 + ky * 4 + kx] = s;
+        } break;
         case R_C3: { const int tap = n >> 6, c = n & 63; g[off[P_C3W] + m * 576 + c * 9 + tap] = s; } break;
         case R_FC: { const int hw = n >> 6, c = n & 63; g[off[P_FCW] + (int64_t)m * FLAT3 + c * 49 + hw] = s; } break;
         case R_WIH: { const int row = (m & 3) * H + (m >> 2); if (n < KIH) g[off[P_WIH] + (int64_t)row * KIH + n] = s; } break;
@@ -730,7 +736,7 @@ struct EpiWinConv1Pair {        // 21x21 s2d grid -> 20x20; columns 0-31 online 
     __device__ __forceinline__ void store16(long long p, int n, const float (&v)[16]) const {
         const int r = (int)(p % 441), gy = r / 21, gx = r - gy * 21;
         if (gy >= 20 || gx >= 20) return;
-        const size_t row = (size_t)(p / 441) * 400 + gy * 20 + gx;
+        const size_t o1 = ((size_t)(p / 441) * 100 + (gy >> 1) * 10 + (gx >> 1)) * 128 + ((gy & 1) * 2 + (gx & 1)) * 32;   // act1: s2d-by-2
         const SplitW& o = n < 32 ? out0 : out1;
         const float* b = n < 32 ? bias0 : bias1;
         const int c = n & 31;
@@ -739,7 +745,7 @@ struct EpiWinConv1Pair {        // 21x21 s2d grid -> 20x20; columns 0-31 online 
             float q[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) q[i] = fmaxf(v[j + i] * scale + __ldg(b + c + j + i), 0.f);
-            split_store8(o.hi, o.lo, row * 32 + c + j, q);
+            split_store8(o.hi, o.lo, o1 + c + j, q);
         }
     }
 };
@@ -748,14 +754,6 @@ struct FwdArgs {
     const float* params; const uint8_t* obs; const uint8_t* last_action; const float* last_reward; const float* hidden;
 };
 
-template <int CH>
-static cudaError_t conv1_forward(r2d2_net* n, int which, const float* params, cudaStream_t s) {
-    SrcConvK<21, 21, 16 * CH, 20, 20, 2, 2, 1, false> a{n->s2d, nullptr, n->NF};
-    const Packed& pk = n->pk[which];
-    SrcMatK b{pk.W1s.hi, pk.W1s.lo, 32, 64 * CH, 64 * CH};
-    Epi2BiasSplit<true> e{n->ac[which].act1, params + n->off[P_C1B], n->NF * 400, 32, 32, 1.f / 255.f};
-    return launch_umma2<32, LO_WEIGHT_B>(a, b, e, n->NF * 400, 32, 64 * CH, 1, s);
-}
 // conv1 of BOTH slots in one launch: columns 0-31 -> online act1, 32-63 -> target act1 (same frames, stacked weights)
 struct Epi2Conv1Pair {
     SplitW out0, out1; const float* bias0; const float* bias1; int M; float scale;
@@ -764,15 +762,25 @@ struct Epi2Conv1Pair {
         const SplitW& o = n < 32 ? out0 : out1;
         const float* b = n < 32 ? bias0 : bias1;
         const int c = n & 31;
+        const int f = m / 400, pp = m - f * 400, gy = pp / 20, gx = pp - gy * 20;
+        const size_t o1 = ((size_t)f * 100 + (gy >> 1) * 10 + (gx >> 1)) * 128 + ((gy & 1) * 2 + (gx & 1)) * 32;      // act1: s2d-by-2
 #pragma unroll
         for (int j = 0; j < 16; j += 8) {
             float r[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) r[i] = fmaxf(v[j + i] * scale + __ldg(b + c + j + i), 0.f);
-            split_store8(o.hi, o.lo, (size_t)m * 32 + c + j, r);
+            split_store8(o.hi, o.lo, o1 + c + j, r);
         }
     }
 };
+template <int CH>
+static cudaError_t conv1_forward(r2d2_net* n, int which, const float* params, cudaStream_t s) {
+    SrcConvK<21, 21, 16 * CH, 20, 20, 2, 2, 1, false> a{n->s2d, nullptr, n->NF};
+    const Packed& pk = n->pk[which];
+    SrcMatK b{pk.W1s.hi, pk.W1s.lo, 32, 64 * CH, 64 * CH};
+    Epi2Conv1Pair e{n->ac[which].act1, n->ac[which].act1, params + n->off[P_C1B], params + n->off[P_C1B], n->NF * 400, 1.f / 255.f};
+    return launch_umma2<32, LO_WEIGHT_B>(a, b, e, n->NF * 400, 32, 64 * CH, 1, s);
+}
 template <int CH>
 static cudaError_t conv1_forward_pair(r2d2_net* n, const float* p0, const float* p1, cudaStream_t s) {
     if constexpr (CH == 4) {
@@ -818,8 +826,11 @@ static int net_encode(r2d2_net* n, int which, const FwdArgs& fa, cudaStream_t s,
     side_columns_kernel<<<T * B, 32, 0, s>>>(ac.U, fa.last_action, fa.last_reward, B, T, A, KU);
     R2D2_LAUNCH_CHECK();
     if (!conv1_done) R2D2_CUDA_CHECK(n->C == 1 ? conv1_forward<1>(n, which, params, s) : conv1_forward<4>(n, which, params, s));
-    {
-        SrcConvK<20, 20, 32, 9, 9, 4, 4, 2> a{ac.act1.hi, ac.act1.lo, NF};
+    if (g_window_conv) {   // conv2 = 2x2 stride-1 window conv over the 10x10 s2d-by-2 grid of act1 (128 channels)
+        EpiWinBiasSplit<10, 10, 9, 9> e{ac.act2, params + off[P_C2B]};
+        R2D2_CUDA_CHECK((launch_winconv<10, 128, 2, 2, 64, true>(SplitC{ac.act1.hi, ac.act1.lo}, (long long)NF * 100, SplitC{pk.W2p.hi, pk.W2p.lo}, e, s)));
+    } else {
+        SrcConvK<10, 10, 128, 9, 9, 2, 2, 1> a{ac.act1.hi, ac.act1.lo, NF};
         SrcMatK b{pk.W2p.hi, pk.W2p.lo, 64, 512, 512};
         Epi2BiasSplit<true> e{ac.act2, params + off[P_C2B], NF * 81, 64, 64, 1.f};
         R2D2_CUDA_CHECK((launch_umma2<64, LO_WEIGHT_B>(a, b, e, NF * 81, 64, 512, 1, s)));
@@ -1059,7 +1070,7 @@ int r2d2_net_backward(r2d2_net* n, const float* params, const float* dq, float* 
     {   // conv2
         const int K2 = NF * 81;
         SrcMatMN a{n->dpre2.hi, n->dpre2.lo, 64, K2, 64};
-        SrcConvMN<20, 20, 32, 9, 9, 4, 4, 2> b{ac.act1.hi, ac.act1.lo, NF};
+        SrcConvMN<10, 10, 128, 9, 9, 2, 2, 1> b{ac.act1.hi, ac.act1.lo, NF};
         R2D2_CUDA_CHECK((wgrad2<64, LO_NO_WEIGHT>(a, b, 64, 512, K2, (K2 + 4095) / 4096, R_C2, n, grads, d_off, 1.f, s)));
         R2D2_CUDA_CHECK(colsum_split(ro(n->dpre2), K2, 64, B_PLAIN, grads, off[P_C2B], 0, A, n->colws, s));
         {   // stride-2 dgrad: the four output-parity classes read the SAME 2x2 taps of dpre2 -> one contraction with the

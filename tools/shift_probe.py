@@ -18,3 +18,15 @@ for mode in (0, 1):
         err = (D - ref).abs().max().item() / ref.abs().max().item()
         line.append(f"{s}:{'ok' if err < 1e-2 else f'{err:.1e}'}")
     print(f"base_offset mode {mode}: " + " ".join(line))
+
+# mode 2: A consumed MN-major (rows of the smem buffer are the reduction index), M = 64, K = 64, N = 32
+line = []
+for s in range(0, 12):
+    D = torch.zeros(128, 32, device="cuda")
+    _lib.check(_lib.lib().r2d2_debug_shift_probe(_lib.ptr(A), _lib.ptr(B), _lib.ptr(D), s, 2, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    ref = A[s:s + 64].float().t() @ B.float().t()                       # [64 m][32 n]
+    lanes = torch.tensor([(m & 15) + 32 * (m >> 4) for m in range(64)], device="cuda")
+    err = (D[lanes] - ref).abs().max().item() / ref.abs().max().item()
+    line.append(f"{s}:{'ok' if err < 1e-2 else f'{err:.1e}'}")
+print("MN-major shifted (mode 2): " + " ".join(line))
