@@ -49,7 +49,7 @@ static void param_sizes(int A, int C, int64_t* n) {
 }
 
 struct Packed {
-    SplitW W1s, W2p, W3p, Wfcp, Wih_p, Whh_p, WhhT_p, Wh0, W3d, W2d, W2q;   // W2d: [4][32][256]; WhhT_p: [512][2048] transpose
+    SplitW W1s, W2p, W3p, Wfcp, Wih_p, Whh_p, WhhT_p, Wh0, W3d, W2q;   // W2q: [128][256] conv2 dgrad; WhhT_p: [512][2048] transpose
     float *bias_p, *bh0;
 };
 struct Acts {
@@ -72,7 +72,7 @@ struct r2d2_net {
     int *row_src, *len_full, *len_learn, *d_rows;     // row_src: [2*Rmax]  (q rows | shifted rows)
     unsigned int* rec_bar;                            // [2] step counters of the persistent recurrence
     // backward scratch
-    r2d2::SplitW dhid, DG, dlat, dpre3, dpre2, dpre1T;
+    r2d2::SplitW dhid, DG, dlat, dpre3, dpre2, dpre1g;   // dpre*: pre-activation grads on the layer's INPUT grid (9x9x64, 10x10x64, 21x21x32), junk pixels stay 0
     float *dH, *dhrec, *dcrec, *dout16, *ws, *colws, *rec_partial;
     size_t ws_floats;
     const float* hidden;             // last forward's stored state (caller-owned, alive until backward)
@@ -106,12 +106,11 @@ __global__ void pack_kernel(const float* __restrict__ p, const int64_t* __restri
             const int ky = 2 * (tap >> 1) + (sub >> 1), kx = 2 * (tap & 1) + (sub & 1);
             put_split(pk.W2p, i, p[off[P_C2W] + n * 512 + c * 16 + ky * 4 + kx]);
         }
-        // dgrad, 4 parity classes: W2d[cls][c_in][(jy*2+jx)*64 + c_out] = W2[c_out][c_in][py+2jy][px+2jx]
+        // dgrad, 4 parity classes (= s2d-by-2 sub-pixels): W2q[cls*32 + c_in][(jy*2+jx)*64 + c_out] = W2[c_out][c_in][py+2jy][px+2jx]
         const int cls = i / (32 * 256), r = i % (32 * 256), ci = r / 256, kk = r % 256, j = kk >> 6, co = kk & 63;
         const int py = cls >> 1, px = cls & 1, jy = j >> 1, jx = j & 1;
         const float wd = p[off[P_C2W] + co * 512 + ci * 16 + (py + 2 * jy) * 4 + (px + 2 * jx)];
-        put_split(pk.W2d, i, wd);
-        put_split(pk.W2q, (size_t)(ci * 4 + cls) * 256 + kk, wd);       // all four parity classes side by side (N = 128)
+        put_split(pk.W2q, (size_t)(cls * 32 + ci) * 256 + kk, wd);      // all four parity classes side by side (N = 128 = s2d-by-2 channel)
     }
     if (i < 64 * 576) {
         const int n = i / 576, k = i % 576, tap = k >> 6, c = k & 63;
@@ -393,46 +392,25 @@ struct Epi2DLatent {
         }
     }
 };
-// conv2 dgrad epilogue for parity class (py,px): rows (f, y', x') on the 10x10 grid -> act1 pixel (2y'+py, 2x'+px);
-// ReLU mask from act1; stored CHANNEL-major (dpre1T[c][pixel]) so that conv1's wgrad reads it as a K-major operand
-struct Epi2DgradS2T {
-    SplitW out; SplitC act; int nframes, py, px; long long NP;
+// FC data gradient -> dpre3 on conv3's INPUT grid (9x9, the 7x7 valid outputs at gy,gx < 7; the rest stays zero), masked
+// by act3 > 0.  Column n = hw*64 + c of frame m.
+struct Epi2MaskedToGrid3 {
+    SplitW out; SplitC act; int M;
     __device__ __forceinline__ void store16(int m, int n, const float (&v)[16], int) const {
-        if (m >= nframes * 100 || n >= 32) return;
-        const int f = m / 100, p = m - f * 100, yq = p / 10, xq = p - yq * 10;
-        const long long pix = ((long long)f * 20 + 2 * yq + py) * 20 + 2 * xq + px;
+        if (m >= M || n >= FLAT3) return;
+        const int hw = n >> 6, c = n & 63, oy = hw / 7, ox = hw - oy * 7;
+        const size_t o = ((size_t)m * 81 + oy * 9 + ox) * 64 + c, a = (size_t)m * FLAT3 + n;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const bool on = (__bfloat16_as_ushort(act.hi[(size_t)m * 128 + (py * 2 + px) * 32 + n + j]) & 0x7FFFu) != 0;
-            put_split(out, (size_t)((n + j) * NP + pix), on ? v[j] : 0.f);
-        }
-    }
-};
-// conv2 dgrad, all four output-parity classes in ONE contraction (they gather the same dpre2 taps; only the weights
-// differ): column n = 4*c + (2*py + px).  Row m = (f, y', x') on the 10x10 grid owns the 2x2 pixel block
-// (2y'+py, 2x'+px) of act1; 16 columns = 4 channels x 4 classes.  ReLU mask from act1, stored channel-major with the
-// two px neighbours written as one 4-byte pair.
-struct Epi2DgradS2Q {
-    SplitW out; SplitC act; int nframes; long long NP;
-    __device__ __forceinline__ void store16(int m, int n, const float (&v)[16], int) const {
-        if (m >= nframes * 100 || n >= 128) return;
-        const int f = m / 100, p = m - f * 100, yq = p / 10, xq = p - yq * 10;
-        const long long pix00 = ((long long)f * 20 + 2 * yq) * 20 + 2 * xq;       // (py, px) = (0, 0); even -> 4-byte aligned pairs
-        const int c0 = n >> 2;
+        for (int j = 0; j < 16; j += 8) {
+            const uint4 h = *reinterpret_cast<const uint4*>(act.hi + a + j);
+            const uint32_t hw4[4] = {h.x, h.y, h.z, h.w};
+            float r[8];
 #pragma unroll
-        for (int ci = 0; ci < 4; ++ci) {
-            const int c = c0 + ci;
-#pragma unroll
-            for (int py = 0; py < 2; ++py) {
-                const long long pix = pix00 + 20 * py;
-                const bool on0 = (__bfloat16_as_ushort(act.hi[(size_t)m * 128 + (py * 2) * 32 + c]) & 0x7FFFu) != 0;      // act1 is s2d-by-2
-                const bool on1 = (__bfloat16_as_ushort(act.hi[(size_t)m * 128 + (py * 2 + 1) * 32 + c]) & 0x7FFFu) != 0;
-                uint32_t h, l;
-                split2(on0 ? v[ci * 4 + py * 2] : 0.f, on1 ? v[ci * 4 + py * 2 + 1] : 0.f, h, l);
-                const size_t o = (size_t)(c * NP + pix);
-                *reinterpret_cast<uint32_t*>(out.hi + o) = h;
-                *reinterpret_cast<uint32_t*>(out.lo + o) = l;
+            for (int i = 0; i < 4; ++i) {
+                r[2 * i] = (hw4[i] & 0x7FFFu) ? v[j + 2 * i] : 0.f;
+                r[2 * i + 1] = (hw4[i] & 0x7FFF0000u) ? v[j + 2 * i + 1] : 0.f;
             }
+            split_store8(out.hi, out.lo, o + j, r);
         }
     }
 };
@@ -450,15 +428,16 @@ struct Epi2ScatterRows {
 };
 
 // split-K reduce + routing of a weight gradient into the reference's parameter layout
-enum RouteKind { R_C1, R_C2, R_C3, R_FC, R_WIH, R_WHH, R_H0, R_H2 };
+enum RouteKind { R_C1, R_C2, R_C3, R_FC, R_WIH, R_WHH, R_H0, R_H2, R_C1W, R_C2W, R_C3W };   // R_C*W: window wgrad partials [tap*IC + c][out channel]
 __global__ void reduce_route_kernel(const float* __restrict__ ws, int splits, int M, int N, int kind, float* __restrict__ g,
                                     const int64_t* __restrict__ off, int A, int C, float scale) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= (int64_t)M * N) return;
-    const int m = i / N, n = i % N;
+    int m = i / N, n = i % N;
     float s = 0.f;
     for (int z = 0; z < splits; ++z) s += ws[(size_t)z * M * N + i];
     s *= scale;
+    if (kind >= R_C1W) { const int t = m; m = n; n = t; kind = kind == R_C1W ? R_C1 : kind == R_C2W ? R_C2 : R_C3; }   // (k, out) -> (out, k)
     const int KIH = LATENT + A + 1;
     switch (kind) {
         case R_C1: {   // n = (dy*2+dx)*16C + c*16 + r*4 + q  ->  [m][c][4dy+r][4dx+q]
@@ -645,7 +624,7 @@ int r2d2_net_create(int B, int T, int C, int A, int Lmax, int max_forward, r2d2_
         Packed& p = n->pk[k];
         rc |= alloc_s(&p.W1s, 32ull * 64 * C); rc |= alloc_s(&p.W2p, 64 * 512); rc |= alloc_s(&p.W3p, 64 * 576);
         rc |= alloc_s(&p.Wfcp, 512ull * FLAT3); rc |= alloc_s(&p.Wih_p, (size_t)G4 * n->KU); rc |= alloc_s(&p.Whh_p, (size_t)G4 * H); rc |= alloc_s(&p.WhhT_p, (size_t)G4 * H);
-        rc |= alloc_s(&p.Wh0, 2 * H * H); rc |= alloc_s(&p.W3d, 64 * 576); rc |= alloc_s(&p.W2d, 4 * 32 * 256); rc |= alloc_s(&p.W2q, 128 * 256);
+        rc |= alloc_s(&p.Wh0, 2 * H * H); rc |= alloc_s(&p.W3d, 64 * 576); rc |= alloc_s(&p.W2q, 128 * 256);
         rc |= alloc_f(&p.bias_p, G4); rc |= alloc_f(&p.bh0, 2 * H);
         Acts& a = n->ac[k];
         rc |= alloc_s(&a.act1, NF * 12800); rc |= alloc_s(&a.act2, NF * 5184); rc |= alloc_s(&a.act3, NF * FLAT3);
@@ -654,7 +633,8 @@ int r2d2_net_create(int B, int T, int C, int A, int Lmax, int max_forward, r2d2_
         rc |= alloc_f(&a.XP, TB * G4); rc |= alloc_f(&a.Cs, TB * H); rc |= alloc_f(&a.Gs, k == 0 ? TB * G4 : 4);
     }
     if (rc) return rc;
-    R2D2_CUDA_CHECK(cudaMalloc(&n->s2d, NF * 441 * 16 * C * sizeof(bf16)));
+    R2D2_CUDA_CHECK(cudaMalloc(&n->s2d, (NF * 441 + 32) * 16 * C * sizeof(bf16)));     // + slack rows: the C = 1 wgrad reads taps of junk pixels
+    R2D2_CUDA_CHECK(cudaMemset(n->s2d, 0, (NF * 441 + 32) * 16 * C * sizeof(bf16)));
     rc |= alloc_s(&n->W1both, 64ull * 64 * C);
     R2D2_CUDA_CHECK(cudaMalloc(&n->row_src, 2 * n->Rmax * sizeof(int)));
     R2D2_CUDA_CHECK(cudaMalloc(&n->len_full, B * sizeof(int)));
@@ -662,7 +642,7 @@ int r2d2_net_create(int B, int T, int C, int A, int Lmax, int max_forward, r2d2_
     R2D2_CUDA_CHECK(cudaMalloc(&n->d_rows, sizeof(int)));
     R2D2_CUDA_CHECK(cudaMalloc(&n->rec_bar, 64 * sizeof(unsigned int)));
     rc |= alloc_s(&n->dhid, (size_t)n->Rmax * 2 * H); rc |= alloc_s(&n->DG, TB * G4); rc |= alloc_s(&n->dlat, NF * LATENT);
-    rc |= alloc_s(&n->dpre3, NF * FLAT3); rc |= alloc_s(&n->dpre2, NF * 5184); rc |= alloc_s(&n->dpre1T, NF * 12800);
+    rc |= alloc_s(&n->dpre3, NF * 5184); rc |= alloc_s(&n->dpre2, NF * 6400); rc |= alloc_s(&n->dpre1g, NF * 14112);   // gradient grids (see struct)
     rc |= alloc_f(&n->dH, TB * H); rc |= alloc_f(&n->dhrec, (size_t)kRecSplits * B * H); rc |= alloc_f(&n->dcrec, (size_t)B * H);
     rc |= alloc_f(&n->dout16, (size_t)n->Rmax * 16); rc |= alloc_f(&n->rec_partial, 2ull * 8 * 64 * H);
     n->ws_floats = 32ull << 20;                        // 128 MB split-K workspace
@@ -677,7 +657,7 @@ int r2d2_net_destroy(r2d2_net* n) {
     if (!n) return R2D2_OK;
     for (int k = 0; k < 2; ++k) {
         Packed& p = n->pk[k];
-        SplitW* ps[] = {&p.W1s, &p.W2p, &p.W3p, &p.Wfcp, &p.Wih_p, &p.Whh_p, &p.WhhT_p, &p.Wh0, &p.W3d, &p.W2d, &p.W2q};
+        SplitW* ps[] = {&p.W1s, &p.W2p, &p.W3p, &p.Wfcp, &p.Wih_p, &p.Whh_p, &p.WhhT_p, &p.Wh0, &p.W3d, &p.W2q};
         for (SplitW* x : ps) free_s(*x);
         cudaFree(p.bias_p); cudaFree(p.bh0);
         Acts& a = n->ac[k];
@@ -685,7 +665,7 @@ int r2d2_net_destroy(r2d2_net* n) {
         for (SplitW* x : as) free_s(*x);
         cudaFree(a.XP); cudaFree(a.Cs); cudaFree(a.Gs);
     }
-    SplitW* ss[] = {&n->W1both, &n->dhid, &n->DG, &n->dlat, &n->dpre3, &n->dpre2, &n->dpre1T};
+    SplitW* ss[] = {&n->W1both, &n->dhid, &n->DG, &n->dlat, &n->dpre3, &n->dpre2, &n->dpre1g};
     for (SplitW* x : ss) free_s(*x);
     float* fs[] = {n->dH, n->dhrec, n->dcrec, n->dout16, n->ws, n->colws, n->rec_partial};
     for (float* x : fs) cudaFree(x);
@@ -750,6 +730,61 @@ struct EpiWinConv1Pair {        // 21x21 s2d grid -> 20x20; columns 0-31 online 
     }
 };
 
+// conv3 data gradient: all 81 pixels of the 9x9 grid are real act2 pixels; ReLU mask from act2 (same rows), result on
+// conv2's 10x10 gradient grid (row f*100 + y*10 + x; gy == 9 / gx == 9 stay zero)
+struct EpiWinDgrad3 {
+    SplitW out; SplitC act;
+    __device__ __forceinline__ void store16(long long p, int n, const float (&v)[16]) const {
+        const int r = (int)(p % 81), y = r / 9, x = r - y * 9;
+        const size_t o = ((size_t)(p / 81) * 100 + y * 10 + x) * 64 + n, a = (size_t)p * 64 + n;
+#pragma unroll
+        for (int j = 0; j < 16; j += 8) {
+            const uint4 h = *reinterpret_cast<const uint4*>(act.hi + a + j);
+            const uint32_t hw4[4] = {h.x, h.y, h.z, h.w};
+            float q[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                q[2 * i] = (hw4[i] & 0x7FFFu) ? v[j + 2 * i] : 0.f;
+                q[2 * i + 1] = (hw4[i] & 0x7FFF0000u) ? v[j + 2 * i + 1] : 0.f;
+            }
+            split_store8(out.hi, out.lo, o + j, q);
+        }
+    }
+};
+// conv2 data gradient: row p = (f, Y, X) of the 10x10 s2d-by-2 grid, column n = (ry*2+rx)*32 + c = act1 pixel
+// (2Y+ry, 2X+rx); ReLU mask from act1 (same layout); result on conv1's 21x21 gradient grid, 32 channels per pixel
+struct EpiWinDgrad2 {
+    SplitW out; SplitC act;
+    __device__ __forceinline__ void store16(long long p, int n, const float (&v)[16]) const {
+        const int r = (int)(p % 100), Y = r / 10, X = r - Y * 10, sub = n >> 5, c = n & 31;
+        const size_t o = ((size_t)(p / 100) * 441 + (2 * Y + (sub >> 1)) * 21 + 2 * X + (sub & 1)) * 32 + c, a = (size_t)p * 128 + n;
+#pragma unroll
+        for (int j = 0; j < 16; j += 8) {
+            const uint4 h = *reinterpret_cast<const uint4*>(act.hi + a + j);
+            const uint32_t hw4[4] = {h.x, h.y, h.z, h.w};
+            float q[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                q[2 * i] = (hw4[i] & 0x7FFFu) ? v[j + 2 * i] : 0.f;
+                q[2 * i + 1] = (hw4[i] & 0x7FFF0000u) ? v[j + 2 * i + 1] : 0.f;
+            }
+            split_store8(out.hi, out.lo, o + j, q);
+        }
+    }
+};
+// window weight gradient + split reduction into the reference layout
+template <int GW, int IC, int KH, int KW, int TG, int NO, bool X_HAS_LO, int KP>
+static cudaError_t winwgrad(SplitC X, SplitC G, long long R, int chunk, int kind, r2d2_net* net, float* grads, const int64_t* d_off,
+                            float scale, cudaStream_t s) {
+    constexpr int M = KH * KW * IC;
+    const int splits = (int)((R + chunk - 1) / chunk);
+    if ((size_t)splits * M * NO > net->ws_floats || chunk % KP) return cudaErrorInvalidValue;
+    cudaError_t e = launch_winwgrad<GW, IC, KH, KW, TG, NO, X_HAS_LO, KP>(X, G, R, chunk, net->ws, s);
+    if (e != cudaSuccess) return e;
+    reduce_route_kernel<<<cdiv((int64_t)M * NO, 256), 256, 0, s>>>(net->ws, splits, M, NO, kind, grads, d_off, net->A, net->C, scale);
+    return cudaGetLastError();
+}
+
 struct FwdArgs {
     const float* params; const uint8_t* obs; const uint8_t* last_action; const float* last_reward; const float* hidden;
 };
@@ -796,11 +831,15 @@ static cudaError_t conv1_forward_pair(r2d2_net* n, const float* p0, const float*
 }
 template <int CH>
 static cudaError_t conv1_wgrad(r2d2_net* n, float* grads, cudaStream_t s) {
-    const int NP = n->NF * 400;
-    SrcMatK a{n->dpre1T.hi, n->dpre1T.lo, 32, NP, NP};
-    SrcConvMN<21, 21, 16 * CH, 20, 20, 2, 2, 1, false> b{n->s2d, nullptr, n->NF};
-    const int splits = (NP + 4095) / 4096;
-    return wgrad2<(CH == 4 ? 256 : 64), LO_NO_WEIGHT>(a, b, 32, 64 * CH, NP, splits, R_C1, n, grads, g_doff[n], 1.f / 255.f, s);
+    const long long NP = (long long)n->NF * 441;               // dpre1g lives on the 21x21 s2d grid (junk row/column are zero)
+    if constexpr (CH == 4) {
+        return winwgrad<21, 64, 2, 2, 4, 32, false, 128>(SplitC{n->s2d, nullptr}, ro(n->dpre1g), NP, 4096, R_C1W, n, grads, g_doff[n], 1.f / 255.f, s);
+    } else {
+        SrcMatMN a{n->dpre1g.hi, n->dpre1g.lo, 32, (int)NP, 32};
+        SrcConvMN<21, 21, 16 * CH, 21, 21, 2, 2, 1, false> b{n->s2d, nullptr, n->NF};       // junk pixels read the slack rows: finite x 0
+        const int splits = (int)((NP + 4095) / 4096);
+        return wgrad2<64, LO_NO_WEIGHT>(a, b, 32, 64 * CH, (int)NP, splits, R_C1, n, grads, g_doff[n], 1.f / 255.f, s);
+    }
 }
 
 // frames -> space-to-depth bf16 (once per batch, shared by both slots) + row maps + h0 split
@@ -1053,41 +1092,27 @@ int r2d2_net_backward(r2d2_net* n, const float* params, const float* dq, float* 
         R2D2_CUDA_CHECK(colsum_split(ro(n->dlat), NF, LATENT, B_PLAIN, grads, off[P_FCB], 0, A, n->colws, s));
         SrcMatK a2{n->dlat.hi, n->dlat.lo, NF, LATENT, LATENT};
         SrcMatMN b2{pk.Wfcp.hi, pk.Wfcp.lo, FLAT3, LATENT, FLAT3};
-        Epi2MaskedSplit e{n->dpre3, ro(ac.act3), NF, FLAT3, FLAT3};
+        Epi2MaskedToGrid3 e{n->dpre3, ro(ac.act3), NF};
         R2D2_CUDA_CHECK((launch_umma2<128, LO_WEIGHT_B>(a2, b2, e, NF, FLAT3, LATENT, 1, s)));
     }
-    {   // conv3
-        const int K3 = NF * 49;
-        SrcMatMN a{n->dpre3.hi, n->dpre3.lo, 64, K3, 64};
-        SrcConvMN<9, 9, 64, 7, 7, 3, 3, 1> b{ac.act2.hi, ac.act2.lo, NF};
-        R2D2_CUDA_CHECK((wgrad2<64, LO_NO_WEIGHT>(a, b, 64, 576, K3, (K3 + 4095) / 4096, R_C3, n, grads, d_off, 1.f, s)));
-        R2D2_CUDA_CHECK(colsum_split(ro(n->dpre3), K3, 64, B_PLAIN, grads, off[P_C3B], 0, A, n->colws, s));
-        SrcDgradK<9, 9, 7, 7, 64, 3, 3> a2{n->dpre3.hi, n->dpre3.lo, NF};
-        SrcMatK b2{pk.W3d.hi, pk.W3d.lo, 64, 576, 576};
-        Epi2MaskedSplit e{n->dpre2, ro(ac.act2), NF * 81, 64, 64};
-        R2D2_CUDA_CHECK((launch_umma2<64, LO_WEIGHT_B>(a2, b2, e, NF * 81, 64, 576, 1, s)));
+    // The conv layers run as window convolutions (winconv.cuh): gradients live on each layer's input grid.
+    {   // conv3: weights from act2 (9x9 grid) x dpre3 (same grid); data gradient = 3x3 window conv of dpre3 with flipped taps
+        const long long R3 = (long long)NF * 81;
+        R2D2_CUDA_CHECK((winwgrad<9, 64, 3, 3, 3, 64, true, 64>(ro(ac.act2), ro(n->dpre3), R3, 3072, R_C3W, n, grads, d_off, 1.f, s)));
+        R2D2_CUDA_CHECK(colsum_split(ro(n->dpre3), (int)R3, 64, B_PLAIN, grads, off[P_C3B], 0, A, n->colws, s));
+        EpiWinDgrad3 e{n->dpre2, ro(ac.act2)};
+        R2D2_CUDA_CHECK((launch_winconv<9, 64, 3, 3, 64, true, true>(ro(n->dpre3), R3, SplitC{pk.W3d.hi, pk.W3d.lo}, e, s)));
     }
-    {   // conv2
-        const int K2 = NF * 81;
-        SrcMatMN a{n->dpre2.hi, n->dpre2.lo, 64, K2, 64};
-        SrcConvMN<10, 10, 128, 9, 9, 2, 2, 1> b{ac.act1.hi, ac.act1.lo, NF};
-        R2D2_CUDA_CHECK((wgrad2<64, LO_NO_WEIGHT>(a, b, 64, 512, K2, (K2 + 4095) / 4096, R_C2, n, grads, d_off, 1.f, s)));
-        R2D2_CUDA_CHECK(colsum_split(ro(n->dpre2), K2, 64, B_PLAIN, grads, off[P_C2B], 0, A, n->colws, s));
-        {   // stride-2 dgrad: the four output-parity classes read the SAME 2x2 taps of dpre2 -> one contraction with the
-            // four weight sets side by side (N = 4 x 32), the gathered tile is staged once instead of four times
-            SrcDgradK<10, 10, 9, 9, 64, 2, 2> a2{n->dpre2.hi, n->dpre2.lo, NF};
-            SrcMatK b2{pk.W2q.hi, pk.W2q.lo, 128, 256, 256};
-            Epi2DgradS2Q e{n->dpre1T, ro(ac.act1), NF, (long long)NF * 400};
-            R2D2_CUDA_CHECK((launch_umma2<128, LO_WEIGHT_B>(a2, b2, e, NF * 100, 128, 256, 1, s)));
-        }
+    {   // conv2 on the 10x10 s2d-by-2 grid of act1
+        const long long R2 = (long long)NF * 100;
+        R2D2_CUDA_CHECK((winwgrad<10, 128, 2, 2, 4, 64, true, 64>(ro(ac.act1), ro(n->dpre2), R2, 3712, R_C2W, n, grads, d_off, 1.f, s)));
+        R2D2_CUDA_CHECK(colsum_split(ro(n->dpre2), (int)R2, 64, B_PLAIN, grads, off[P_C2B], 0, A, n->colws, s));
+        EpiWinDgrad2 e{n->dpre1g, ro(ac.act1)};
+        R2D2_CUDA_CHECK((launch_winconv<10, 64, 2, 2, 128, true, true>(ro(n->dpre2), R2, SplitC{pk.W2q.hi, pk.W2q.lo}, e, s)));
     }
     {   // conv1 (weights only; frames need no gradient)
         R2D2_CUDA_CHECK(n->C == 1 ? conv1_wgrad<1>(n, grads, s) : conv1_wgrad<4>(n, grads, s));
-        const long long NP = (long long)NF * 400;
-        const int P = 64;
-        rowsum_partial_kernel<<<dim3(32, P), 256, 0, s>>>(ro(n->dpre1T), 32, NP, (NP + P - 1) / P, n->colws);
-        colsum_final_kernel<<<1, 128, 0, s>>>(n->colws, P, 32, B_PLAIN, grads, off[P_C1B], 0, A);
-        R2D2_LAUNCH_CHECK();
+        R2D2_CUDA_CHECK(colsum_split(ro(n->dpre1g), NF * 441, 32, B_PLAIN, grads, off[P_C1B], 0, A, n->colws, s));
     }
     return R2D2_OK;
 }

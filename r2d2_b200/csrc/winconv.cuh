@@ -37,7 +37,7 @@ struct WinCfg {
 
 // Epilogue contract: store_row(p, acc-chunk) style functor with  void store16(long long p, int n, const float (&v)[16]) const
 // where p is the GRID pixel index (frame * GW*GH + gy * GW + gx); the functor drops junk pixels itself.
-template <int GW, int IC, int KH, int KW, int N, bool A_LO, bool B_LO, class Epi>
+template <int GW, int IC, int KH, int KW, int N, bool A_LO, bool B_LO, bool BACK, class Epi>
 __global__ void __launch_bounds__(UM_THREADS, 1)
 winconv_kernel(const bf16* __restrict__ Xhi, const bf16* __restrict__ Xlo, long long R /* total grid pixels */,
                const bf16* __restrict__ Whi, const bf16* __restrict__ Wlo /* [N][taps*IC], k = tap*IC + c */, const Epi ep) {
@@ -93,8 +93,8 @@ winconv_kernel(const bf16* __restrict__ Xhi, const bf16* __restrict__ Xlo, long 
                 const uint32_t st = sA + s * Cfg::kAStage;
                 for (int u = tid; u < Cfg::kWinRows * 8; u += 128) {
                     const int row = u >> 3, j = u & 7;
-                    const long long p = p0 + row;
-                    const bool ok = p < R;
+                    const long long p = p0 + row - (BACK ? Cfg::kHalo : 0);
+                    const bool ok = p >= 0 && p < R;
                     const size_t src = ok ? (size_t)p * IC + kb * 64 + j * 8 : 0;
                     const uint32_t dst = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((j ^ (row & 7)) << 4));
                     cp_async16(st + dst, Xhi + src, ok);
@@ -146,7 +146,8 @@ winconv_kernel(const bf16* __restrict__ Xhi, const bf16* __restrict__ Xlo, long 
                 if (leader) {
 #pragma unroll
                     for (int t = 0; t < TAPS; ++t) {
-                        const uint32_t shift = (uint32_t)((t / KW) * GW + (t % KW)) * 128u;          // row-shifted view of the window
+                        const int off_t = (t / KW) * GW + (t % KW);
+                        const uint32_t shift = (uint32_t)(BACK ? Cfg::kHalo - off_t : off_t) * 128u;  // row-shifted view of the window
                         const uint64_t a_hi = umma_desc_sw128(st + shift), a_lo = umma_desc_sw128(st + Cfg::kWinBytes + shift);
                         const uint32_t bt = uB + (t * KB + kb) * Cfg::kBTile;
                         const uint64_t b_hi = umma_desc_sw128(bt), b_lo = umma_desc_sw128(bt + TAPS * KB * Cfg::kBTile);
@@ -173,10 +174,10 @@ winconv_kernel(const bf16* __restrict__ Xhi, const bf16* __restrict__ Xlo, long 
     }
 }
 
-template <int GW, int IC, int KH, int KW, int N, bool A_LO, bool B_LO, class Epi>
+template <int GW, int IC, int KH, int KW, int N, bool A_LO, bool B_LO, bool BACK, class Epi>
 static inline cudaError_t launch_winconv_inst(SplitC X, long long R, SplitC W, const Epi& ep, cudaStream_t s) {
     using Cfg = WinCfg<GW, IC, KH, KW, N, A_LO, B_LO>;
-    auto kern = winconv_kernel<GW, IC, KH, KW, N, A_LO, B_LO, Epi>;
+    auto kern = winconv_kernel<GW, IC, KH, KW, N, A_LO, B_LO, BACK, Epi>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
@@ -190,14 +191,220 @@ static inline cudaError_t launch_winconv_inst(SplitC X, long long R, SplitC W, c
 }
 
 // A_HAS_LO: whether X has a lo plane at all (u8 frames do not).  Precision policy as in launch_umma2 (weights are B).
-template <int GW, int IC, int KH, int KW, int N, bool A_HAS_LO, class Epi>
+// BACK = true is the data gradient: out[q] = sum_taps X[q - off(tap)] . W[tap] with X the (zero-junk) gradient grid.
+template <int GW, int IC, int KH, int KW, int N, bool A_HAS_LO, bool BACK = false, class Epi>
 static inline cudaError_t launch_winconv(SplitC X, long long R, SplitC W, const Epi& ep, cudaStream_t s) {
-    if (g_fast_math == 1) return launch_winconv_inst<GW, IC, KH, KW, N, false, false>(X, R, W, ep, s);
+    if (g_fast_math == 1) return launch_winconv_inst<GW, IC, KH, KW, N, false, false, BACK>(X, R, W, ep, s);
     if constexpr (!A_HAS_LO) {
-        return launch_winconv_inst<GW, IC, KH, KW, N, false, true>(X, R, W, ep, s);
+        return launch_winconv_inst<GW, IC, KH, KW, N, false, true, BACK>(X, R, W, ep, s);
     } else {
-        if (g_fast_math == 2) return launch_winconv_inst<GW, IC, KH, KW, N, false, true>(X, R, W, ep, s);
-        return launch_winconv_inst<GW, IC, KH, KW, N, true, true>(X, R, W, ep, s);
+        if (g_fast_math == 2) return launch_winconv_inst<GW, IC, KH, KW, N, false, true, BACK>(X, R, W, ep, s);
+        return launch_winconv_inst<GW, IC, KH, KW, N, true, true, BACK>(X, R, W, ep, s);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Window weight gradient:  dW[tap][c][n] = sum_p X[p + off(tap)][c] * G[p][n]
+// X: activations on the input grid ([R][IC]); G: output gradient on the SAME grid ([R][NO], junk pixels are zero).
+// Both operands are consumed MN-major (smem lines are pixels = the reduction index), so the staged bytes are the plain
+// rows of X and G; tap t multiplies the X window shifted by off(t) lines.  M = IC (64, or 128 as two 64-channel atoms),
+// N = NO, one TMEM accumulator per tap.  A work item is (pixel chunk, tap group); chunks are <= 4096 pixels because
+// the TMEM accumulation truncates -- partials go to the split-K workspace [chunk][taps*IC][NO].
+// PACK_G (NO = 32, X without lo plane): the hi and lo planes of a G row share one 128-byte line, a single N = 64 MMA
+// yields X.G_hi | X.G_lo side by side and the epilogue adds the halves.
+template <int GW, int IC, int KH, int KW, int TG, int NO, bool X_LO, bool G_LO, bool PACK_G, int KP>
+struct WinWgradCfg {
+    static constexpr int kTaps = KH * KW;
+    static_assert(TG == kTaps || TG == KW, "tap groups are the whole kernel or one kernel row");
+    static constexpr int kGroups = kTaps / TG;
+    static constexpr int kHG = (TG == kTaps) ? (KH - 1) * GW + (KW - 1) : (KW - 1);       // halo inside one group
+    static constexpr int kAtoms = IC / 64;
+    static constexpr int kWinRows = (KP + kHG + 7) / 8 * 8;
+    static constexpr int kWinBytes = kWinRows * 128;
+    static constexpr int kXBytes = (X_LO ? 2 : 1) * kAtoms * kWinBytes;
+    static constexpr int kGPlane = KP * 128;
+    static constexpr int kGBytes = (PACK_G ? 1 : (G_LO ? 2 : 1)) * kGPlane;
+    static constexpr int kStage = kXBytes + kGBytes;
+    static constexpr int kNMMA = PACK_G ? 64 : NO;
+    static constexpr int kCols = TG * kNMMA <= 32 ? 32 : TG * kNMMA <= 64 ? 64 : TG * kNMMA <= 128 ? 128 : TG * kNMMA <= 256 ? 256 : 512;
+    static constexpr int kStagesRaw = (227 * 1024 - 2048) / kStage;
+    // three stages when that lets two CTAs share an SM (prologue/epilogue of one hides behind the other), else up to four
+    static constexpr int kStages = (2 * (3 * kStage + 1280) <= 227 * 1024) ? 3 : (kStagesRaw > 4 ? 4 : kStagesRaw);
+    static constexpr int kSmem = kStages * kStage + 1024 + 256;
+    static_assert(IC % 64 == 0 && IC <= 128 && (NO == 32 || NO == 64) && KP % 16 == 0 && TG * kNMMA <= 512, "window wgrad shape");
+    static_assert(!PACK_G || (NO == 32 && !X_LO), "PACK_G packs hi|lo of a 32-channel gradient row");
+    static_assert(kStages >= 2, "not enough shared memory");
+};
+
+template <int GW, int IC, int KH, int KW, int TG, int NO, bool X_LO, bool G_LO, bool PACK_G, int KP>
+__global__ void __launch_bounds__(UM_THREADS, 1)
+winwgrad_kernel(const bf16* __restrict__ Xhi, const bf16* __restrict__ Xlo, const bf16* __restrict__ Ghi, const bf16* __restrict__ Glo,
+                long long R, int chunk /* pixels per item, multiple of KP */, float* __restrict__ ws) {
+    using Cfg = WinWgradCfg<GW, IC, KH, KW, TG, NO, X_LO, G_LO, PACK_G, KP>;
+    constexpr int S = Cfg::kStages, ATOMS = Cfg::kAtoms, NMMA = Cfg::kNMMA;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;
+    uint8_t* smem = smem_raw + pad;
+    const uint32_t sbase = raw + pad;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStage);       // full[S] | empty[S] | acc
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int group = blockIdx.y;
+    const int tap0 = group * TG;
+    const int wbase = (tap0 / KW) * GW + (tap0 % KW);                           // first line of this group's window
+    const long long c0 = (long long)blockIdx.x * chunk;
+    const long long c1 = (c0 + chunk < R) ? c0 + chunk : R;
+    const int nst = (int)((c1 - c0 + KP - 1) / KP);
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) { mbar_init(smem_u32(&bars[s]), 8); mbar_init(smem_u32(&bars[S + s]), 1); }
+        mbar_init(smem_u32(&bars[2 * S]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::kCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 8) {
+        // ------------------------------------------------------------------ producers
+        for (int it = 0; it < nst; ++it) {
+            const int s = it % S;
+            const uint32_t ph = (uint32_t)(it / S) & 1u;
+            mbar_wait(smem_u32(&bars[S + s]), ph ^ 1u);
+            const uint32_t st = sbase + s * Cfg::kStage;
+            const long long p0 = c0 + (long long)it * KP;
+            for (int u = tid; u < Cfg::kWinRows * 8 * ATOMS; u += UM_PRODUCERS) {
+                const int j = u & 7, row = (u >> 3) % Cfg::kWinRows, atom = (u >> 3) / Cfg::kWinRows;
+                const long long p = p0 + wbase + row;
+                const bool ok = p < R;
+                const size_t src = ok ? (size_t)p * IC + atom * 64 + j * 8 : 0;
+                const uint32_t dst = (uint32_t)(atom * Cfg::kWinBytes + (row >> 3) * 1024 + (row & 7) * 128 + ((j ^ (row & 7)) << 4));
+                cp_async16(st + dst, Xhi + src, ok);
+                if (X_LO) cp_async16(st + ATOMS * Cfg::kWinBytes + dst, Xlo + src, ok);
+            }
+            const uint32_t sg = st + Cfg::kXBytes;
+            if (PACK_G) {
+                for (int u = tid; u < KP * 8; u += UM_PRODUCERS) {
+                    const int j = u & 7, row = u >> 3;
+                    const long long p = p0 + row;
+                    const bool ok = p < c1;
+                    const size_t src = ok ? (size_t)p * NO + (j & 3) * 8 : 0;
+                    cp_async16(sg + (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((j ^ (row & 7)) << 4)), (j < 4 ? Ghi : Glo) + src, ok);
+                }
+            } else {
+                constexpr int CH = NO / 8;                                       // 16-byte chunks per gradient row
+                for (int u = tid; u < KP * CH; u += UM_PRODUCERS) {
+                    const int j = u % CH, row = u / CH;
+                    const long long p = p0 + row;
+                    const bool ok = p < c1;
+                    const size_t src = ok ? (size_t)p * NO + j * 8 : 0;
+                    const uint32_t dst = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((j ^ (row & 7)) << 4));
+                    cp_async16(sg + dst, Ghi + src, ok);
+                    if (G_LO) cp_async16(sg + Cfg::kGPlane + dst, Glo + src, ok);
+                }
+            }
+            cp_async_commit();
+            cp_async_wait<0>();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars[s]));
+        }
+        // ------------------------------------------------------------------ epilogue: TMEM -> partial [chunk][taps*IC][NO]
+        mbar_wait(smem_u32(&bars[2 * S]), 0);
+        tc_fence_after();
+        const int q = warp & 3, half = warp >> 2;
+        const bool lane_ok = (IC == 128) || lane < 16;                          // M = 64: rows live in lanes 32q + (0..15)
+        const int m = (IC == 128) ? q * 32 + lane : q * 16 + lane;
+        float* out = ws + (size_t)blockIdx.x * (Cfg::kTaps * IC * NO);
+        constexpr int NCH = NO / 16;                                            // 16-column chunks per tap
+        for (int u = half; u < TG * NCH; u += 2) {
+            const int t = u / NCH, c = (u % NCH) * 16;
+            float v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * NMMA + c), v);
+            if (PACK_G) {
+                float w[16];
+                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * NMMA + 32 + c), w);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] += w[i];
+            }
+            if (lane_ok) {
+                float* o = out + ((size_t)(tap0 + t) * IC + m) * NO + c;
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
+        }
+        tc_fence_before();
+    } else {
+        // ------------------------------------------------------------------ MMA issue
+        constexpr uint32_t idesc = ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NMMA >> 3) << 17) | ((uint32_t)(IC >> 4) << 24)) | (1u << 15) | (1u << 16);
+        const bool leader = elect_one();
+        const uint32_t uS = __shfl_sync(0xffffffffu, sbase, 0), uT = __shfl_sync(0xffffffffu, tmem_base, 0);
+        for (int it = 0; it < nst; ++it) {
+            const int s = it % S;
+            const uint32_t ph = (uint32_t)(it / S) & 1u;
+            mbar_wait(smem_u32(&bars[s]), ph);
+            tc_fence_after();
+            const uint32_t st = uS + s * Cfg::kStage;
+            if (leader) {
+#pragma unroll
+                for (int t = 0; t < TG; ++t) {
+                    const int tap = tap0 + t;                                    // (ky, kx); tap0 is a multiple of KW or 0
+                    const uint32_t shift = (uint32_t)(((tap / KW) * GW + (tap % KW)) - wbase) * 128u;
+                    const uint64_t x_hi = umma_desc_sw128_mn(st + shift, Cfg::kWinBytes);
+                    const uint64_t x_lo = umma_desc_sw128_mn(st + ATOMS * Cfg::kWinBytes + shift, Cfg::kWinBytes);
+                    const uint64_t g_hi = umma_desc_sw128_mn(st + Cfg::kXBytes, 8192), g_lo = umma_desc_sw128_mn(st + Cfg::kXBytes + Cfg::kGPlane, 8192);
+                    const uint32_t acc = uT + t * NMMA;
+#pragma unroll
+                    for (int k = 0; k < KP / 16; ++k) {
+                        const uint64_t adv = (uint64_t)(k * 128);                // 16 lines x 128 B, >> 4
+                        uint32_t accum = (it | k) ? 1u : 0u;
+                        if (X_LO) { umma_bf16(acc, x_lo + adv, g_hi + adv, idesc, accum); accum = 1u; }
+                        if (G_LO && !PACK_G) { umma_bf16(acc, x_hi + adv, g_lo + adv, idesc, accum); accum = 1u; }
+                        umma_bf16(acc, x_hi + adv, g_hi + adv, idesc, accum);
+                    }
+                }
+                umma_commit(smem_u32(&bars[S + s]));
+                if (it == nst - 1) umma_commit(smem_u32(&bars[2 * S]));
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kCols) : "memory");
+    }
+}
+
+template <int GW, int IC, int KH, int KW, int TG, int NO, bool X_LO, bool G_LO, bool PACK_G, int KP>
+static inline cudaError_t launch_winwgrad_inst(SplitC X, SplitC G, long long R, int chunk, float* ws, cudaStream_t s) {
+    using Cfg = WinWgradCfg<GW, IC, KH, KW, TG, NO, X_LO, G_LO, PACK_G, KP>;
+    auto kern = winwgrad_kernel<GW, IC, KH, KW, TG, NO, X_LO, G_LO, PACK_G, KP>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const int nchunks = (int)((R + chunk - 1) / chunk);
+    kern<<<dim3(nchunks, Cfg::kGroups), UM_THREADS, Cfg::kSmem, s>>>(X.hi, X.lo, G.hi, G.lo, R, chunk, ws);
+    return cudaGetLastError();
+}
+
+// Precision policy of the other weight gradients (LO_NO_WEIGHT): strict = all three split products, otherwise hi.hi.
+template <int GW, int IC, int KH, int KW, int TG, int NO, bool X_HAS_LO, int KP>
+static inline cudaError_t launch_winwgrad(SplitC X, SplitC G, long long R, int chunk, float* ws, cudaStream_t s) {
+    if (g_fast_math != 0) return launch_winwgrad_inst<GW, IC, KH, KW, TG, NO, false, false, false, KP>(X, G, R, chunk, ws, s);
+    if constexpr (!X_HAS_LO && NO == 32) {
+        return launch_winwgrad_inst<GW, IC, KH, KW, TG, NO, false, true, true, KP>(X, G, R, chunk, ws, s);
+    } else {
+        return launch_winwgrad_inst<GW, IC, KH, KW, TG, NO, X_HAS_LO, true, false, KP>(X, G, R, chunk, ws, s);
     }
 }
 
