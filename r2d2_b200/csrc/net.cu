@@ -161,18 +161,21 @@ __global__ void s2d_kernel(const uint8_t* __restrict__ obs, bf16* __restrict__ s
     q[1] = make_uint4(o[4], o[5], o[6], o[7]);
 }
 
-// row maps + sequence lengths + split copy of h0.  One CTA.  model.py:102-111 (shifted rows) and model.py:143.
+// row maps + sequence lengths (block 0) + split copy of h0 (other blocks).  model.py:102-111 (shifted rows) and model.py:143.
 __global__ void prep_rows_kernel(const uint8_t* __restrict__ burn, const uint8_t* __restrict__ learn,
                                  const uint8_t* __restrict__ fwd, const float* __restrict__ hidden, SplitW h0a, SplitW h0b, int B, int F,
                                  int Rmax, int* __restrict__ row_src, int* __restrict__ len_full, int* __restrict__ len_learn,
                                  int* __restrict__ d_rows) {
     extern __shared__ int s_off[];
-    for (int i = threadIdx.x; i < 2 * Rmax; i += blockDim.x) row_src[i] = -1;
-    for (int i = threadIdx.x; i < B * H; i += blockDim.x) {          // h0 (split) in front of both slots' state arrays
-        const float x = hidden[(size_t)(i / H) * 2 * H + (i % H)];
-        put_split(h0a, i, x);
-        put_split(h0b, i, x);
+    if (blockIdx.x > 0) {                                            // blocks 1..: h0 (split) in front of both slots' state arrays
+        for (int i = (blockIdx.x - 1) * blockDim.x + threadIdx.x; i < B * H; i += (gridDim.x - 1) * blockDim.x) {
+            const float x = hidden[(size_t)(i / H) * 2 * H + (i % H)];
+            put_split(h0a, i, x);
+            put_split(h0b, i, x);
+        }
+        return;
     }
+    for (int i = threadIdx.x; i < 2 * Rmax; i += blockDim.x) row_src[i] = -1;
     if (threadIdx.x == 0) {
         int run = 0;
         for (int n = 0; n < B; ++n) { s_off[n] = run; run += learn[n]; }
@@ -431,11 +434,21 @@ struct Epi2ScatterRows {
 enum RouteKind { R_C1, R_C2, R_C3, R_FC, R_WIH, R_WHH, R_H0, R_H2, R_C1W, R_C2W, R_C3W };   // R_C*W: window wgrad partials [tap*IC + c][out channel]
 __global__ void reduce_route_kernel(const float* __restrict__ ws, int splits, int M, int N, int kind, float* __restrict__ g,
                                     const int64_t* __restrict__ off, int A, int C, float scale) {
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= (int64_t)M * N) return;
+    // block = 32 consecutive outputs x 8 slices of the split index, summed in a fixed order
+    __shared__ float sm[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t i = blockIdx.x * 32ll + tx;
+    const bool in = i < (int64_t)M * N;
+    float acc = 0.f;
+    if (in)
+        for (int z = ty; z < splits; z += 8) acc += ws[(size_t)z * M * N + i];
+    sm[ty][tx] = acc;
+    __syncthreads();
+    if (ty != 0 || !in) return;
     int m = i / N, n = i % N;
     float s = 0.f;
-    for (int z = 0; z < splits; ++z) s += ws[(size_t)z * M * N + i];
+#pragma unroll
+    for (int y = 0; y < 8; ++y) s += sm[y][tx];
     s *= scale;
     if (kind >= R_C1W) { const int t = m; m = n; n = t; kind = kind == R_C1W ? R_C1 : kind == R_C2W ? R_C2 : R_C3; }   // (k, out) -> (out, k)
     const int KIH = LATENT + A + 1;
@@ -523,12 +536,21 @@ __global__ void rowsum_partial_kernel(SplitC S, int R, long long N, long long ch
     }
 }
 enum BiasKind { B_PLAIN, B_LSTM, B_H0, B_H2 };
-__global__ void colsum_final_kernel(const float* __restrict__ part, int P, int N, int kind, float* __restrict__ g,
-                                    int64_t o0, int64_t o1, int A) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
+// final fixed-order reduction of P partial rows; block = 32 columns x 8 slices of the partial index
+__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ part, int P, int N, int kind, float* __restrict__ g,
+                                                           int64_t o0, int64_t o1, int A) {
+    __shared__ float sm[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int n = blockIdx.x * 32 + tx;
+    float acc = 0.f;
+    if (n < N)
+        for (int p = ty; p < P; p += 8) acc += part[(size_t)p * N + n];
+    sm[ty][tx] = acc;
+    __syncthreads();
+    if (ty != 0 || n >= N) return;
     float s = 0.f;
-    for (int p = 0; p < P; ++p) s += part[(size_t)p * N + n];
+#pragma unroll
+    for (int y = 0; y < 8; ++y) s += sm[y][tx];
     switch (kind) {
         case B_PLAIN: g[o0 + n] = s; break;
         case B_LSTM: { const int row = (n & 3) * H + (n >> 2); g[o0 + row] = s; g[o1 + row] = s; } break;   // b_ih and b_hh
@@ -543,14 +565,14 @@ static cudaError_t colsum_split(SplitC S, int M, int N, int kind, float* g, int6
     const int groups = N / 8, gpb = groups < 32 ? groups : 32;
     dim3 grid((groups + gpb - 1) / gpb, kColP);
     colsum_partial_kernel<true><<<grid, 256, 0, s>>>(nullptr, S, M, N, chunk, colws);
-    colsum_final_kernel<<<(N + 127) / 128, 128, 0, s>>>(colws, kColP, N, kind, g, o0, o1, A);
+    colsum_final_kernel<<<(N + 31) / 32, 256, 0, s>>>(colws, kColP, N, kind, g, o0, o1, A);
     return cudaGetLastError();
 }
 static cudaError_t colsum_f32(const float* X, int M, int N, int kind, float* g, int64_t o0, int64_t o1, int A, float* colws, cudaStream_t s) {
     const int chunk = (M + kColP - 1) / kColP;
     dim3 grid((N + 31) / 32, kColP);
     colsum_partial_kernel<false><<<grid, 256, 0, s>>>(X, SplitC{nullptr, nullptr}, M, N, chunk, colws);
-    colsum_final_kernel<<<(N + 127) / 128, 128, 0, s>>>(colws, kColP, N, kind, g, o0, o1, A);
+    colsum_final_kernel<<<(N + 31) / 32, 256, 0, s>>>(colws, kColP, N, kind, g, o0, o1, A);
     return cudaGetLastError();
 }
 
@@ -566,7 +588,7 @@ static cudaError_t wgrad2(const AS& a, const BS& b, int M, int N, int K, int spl
     cudaError_t e = launch_umma2<UBN, POL>(a, b, ep, M, N, K, splits, s);
     if (e != cudaSuccess) return e;
     const int64_t tot = (int64_t)M * N;
-    reduce_route_kernel<<<cdiv(tot, 256), 256, 0, s>>>(net->ws, splits, M, N, kind, grads, d_off, net->A, net->C, scale);
+    reduce_route_kernel<<<cdiv(tot, 32), 256, 0, s>>>(net->ws, splits, M, N, kind, grads, d_off, net->A, net->C, scale);
     return cudaGetLastError();
 }
 
@@ -773,15 +795,17 @@ struct EpiWinDgrad2 {
     }
 };
 // window weight gradient + split reduction into the reference layout
+// (+ the layer's bias gradient = column sums of G, from the same kernel)
 template <int GW, int IC, int KH, int KW, int TG, int NO, bool X_HAS_LO, int KP>
-static cudaError_t winwgrad(SplitC X, SplitC G, long long R, int chunk, int kind, r2d2_net* net, float* grads, const int64_t* d_off,
-                            float scale, cudaStream_t s) {
+static cudaError_t winwgrad(SplitC X, SplitC G, long long R, int chunk, int kind, int64_t bias_off, r2d2_net* net, float* grads,
+                            const int64_t* d_off, float scale, cudaStream_t s) {
     constexpr int M = KH * KW * IC;
     const int splits = (int)((R + chunk - 1) / chunk);
-    if ((size_t)splits * M * NO > net->ws_floats || chunk % KP) return cudaErrorInvalidValue;
-    cudaError_t e = launch_winwgrad<GW, IC, KH, KW, TG, NO, X_HAS_LO, KP>(X, G, R, chunk, net->ws, s);
+    if ((size_t)splits * M * NO > net->ws_floats || (size_t)splits * NO > (size_t)kColP * 4096 || chunk % KP) return cudaErrorInvalidValue;
+    cudaError_t e = launch_winwgrad<GW, IC, KH, KW, TG, NO, X_HAS_LO, KP, true>(X, G, R, chunk, net->ws, net->colws, s);
     if (e != cudaSuccess) return e;
-    reduce_route_kernel<<<cdiv((int64_t)M * NO, 256), 256, 0, s>>>(net->ws, splits, M, NO, kind, grads, d_off, net->A, net->C, scale);
+    reduce_route_kernel<<<cdiv((int64_t)M * NO, 32), 256, 0, s>>>(net->ws, splits, M, NO, kind, grads, d_off, net->A, net->C, scale);
+    colsum_final_kernel<<<(NO + 31) / 32, 256, 0, s>>>(net->colws, splits, NO, B_PLAIN, grads, bias_off, 0, net->A);
     return cudaGetLastError();
 }
 
@@ -833,19 +857,21 @@ template <int CH>
 static cudaError_t conv1_wgrad(r2d2_net* n, float* grads, cudaStream_t s) {
     const long long NP = (long long)n->NF * 441;               // dpre1g lives on the 21x21 s2d grid (junk row/column are zero)
     if constexpr (CH == 4) {
-        return winwgrad<21, 64, 2, 2, 4, 32, false, 128>(SplitC{n->s2d, nullptr}, ro(n->dpre1g), NP, 4096, R_C1W, n, grads, g_doff[n], 1.f / 255.f, s);
+        return winwgrad<21, 64, 2, 2, 4, 32, false, 128>(SplitC{n->s2d, nullptr}, ro(n->dpre1g), NP, 4096, R_C1W, n->off[P_C1B], n, grads, g_doff[n], 1.f / 255.f, s);
     } else {
         SrcMatMN a{n->dpre1g.hi, n->dpre1g.lo, 32, (int)NP, 32};
         SrcConvMN<21, 21, 16 * CH, 21, 21, 2, 2, 1, false> b{n->s2d, nullptr, n->NF};       // junk pixels read the slack rows: finite x 0
         const int splits = (int)((NP + 4095) / 4096);
-        return wgrad2<64, LO_NO_WEIGHT>(a, b, 32, 64 * CH, (int)NP, splits, R_C1, n, grads, g_doff[n], 1.f / 255.f, s);
+        cudaError_t e = wgrad2<64, LO_NO_WEIGHT>(a, b, 32, 64 * CH, (int)NP, splits, R_C1, n, grads, g_doff[n], 1.f / 255.f, s);
+        if (e != cudaSuccess) return e;
+        return colsum_split(ro(n->dpre1g), (int)NP, 32, B_PLAIN, grads, n->off[P_C1B], 0, n->A, n->colws, s);
     }
 }
 
 // frames -> space-to-depth bf16 (once per batch, shared by both slots) + row maps + h0 split
 static int net_prep(r2d2_net* n, const uint8_t* obs, const float* hidden, const uint8_t* burn, const uint8_t* learn,
                     const uint8_t* fwd, cudaStream_t s) {
-    prep_rows_kernel<<<1, 256, (n->B + 1) * sizeof(int), s>>>(burn, learn, fwd, hidden, n->ac[0].HsX, n->ac[1].HsX, n->B, n->F, n->Rmax, n->row_src,
+    prep_rows_kernel<<<1 + 32, 256, (n->B + 1) * sizeof(int), s>>>(burn, learn, fwd, hidden, n->ac[0].HsX, n->ac[1].HsX, n->B, n->F, n->Rmax, n->row_src,
                                                              n->len_full, n->len_learn, n->d_rows);
     if (obs) {                                             // obs == NULL: the frames were staged by r2d2_replay_gather_s2d
         const int64_t total = (int64_t)n->NF * n->C * 441;
@@ -1030,7 +1056,7 @@ int r2d2_net_backward(r2d2_net* n, const float* params, const float* dq, float* 
     {   // layer-2 weights: [A+1 (pad 16)] x [1024] = dout16^T . hid   (tiny: CUDA cores)
         const int P = 16, chunk = (Rmax + P - 1) / P;
         head_w2_grad_kernel<<<dim3(2 * H / 128, P), 128, 0, s>>>(n->dout16, ro(ac.hid), Rmax, chunk, n->ws);
-        reduce_route_kernel<<<cdiv(16 * 2 * H, 256), 256, 0, s>>>(n->ws, P, 16, 2 * H, R_H2, grads, d_off, A, n->C, 1.f);
+        reduce_route_kernel<<<cdiv(16 * 2 * H, 32), 256, 0, s>>>(n->ws, P, 16, 2 * H, R_H2, grads, d_off, A, n->C, 1.f);
         R2D2_CUDA_CHECK(colsum_f32(n->dout16, Rmax, 16, B_H2, grads, off[P_A2B], off[P_V2B], A, n->colws, s));
     }
     {   // layer-0 weights: [1024] x [512] = dhid^T . Hsel
@@ -1098,21 +1124,18 @@ int r2d2_net_backward(r2d2_net* n, const float* params, const float* dq, float* 
     // The conv layers run as window convolutions (winconv.cuh): gradients live on each layer's input grid.
     {   // conv3: weights from act2 (9x9 grid) x dpre3 (same grid); data gradient = 3x3 window conv of dpre3 with flipped taps
         const long long R3 = (long long)NF * 81;
-        R2D2_CUDA_CHECK((winwgrad<9, 64, 3, 3, 3, 64, true, 64>(ro(ac.act2), ro(n->dpre3), R3, 3072, R_C3W, n, grads, d_off, 1.f, s)));
-        R2D2_CUDA_CHECK(colsum_split(ro(n->dpre3), (int)R3, 64, B_PLAIN, grads, off[P_C3B], 0, A, n->colws, s));
+        R2D2_CUDA_CHECK((winwgrad<9, 64, 3, 3, 3, 64, true, 64>(ro(ac.act2), ro(n->dpre3), R3, 3072, R_C3W, off[P_C3B], n, grads, d_off, 1.f, s)));
         EpiWinDgrad3 e{n->dpre2, ro(ac.act2)};
         R2D2_CUDA_CHECK((launch_winconv<9, 64, 3, 3, 64, true, true>(ro(n->dpre3), R3, SplitC{pk.W3d.hi, pk.W3d.lo}, e, s)));
     }
     {   // conv2 on the 10x10 s2d-by-2 grid of act1
         const long long R2 = (long long)NF * 100;
-        R2D2_CUDA_CHECK((winwgrad<10, 128, 2, 2, 4, 64, true, 64>(ro(ac.act1), ro(n->dpre2), R2, 3712, R_C2W, n, grads, d_off, 1.f, s)));
-        R2D2_CUDA_CHECK(colsum_split(ro(n->dpre2), (int)R2, 64, B_PLAIN, grads, off[P_C2B], 0, A, n->colws, s));
+        R2D2_CUDA_CHECK((winwgrad<10, 128, 2, 2, 4, 64, true, 64>(ro(ac.act1), ro(n->dpre2), R2, 3712, R_C2W, off[P_C2B], n, grads, d_off, 1.f, s)));
         EpiWinDgrad2 e{n->dpre1g, ro(ac.act1)};
         R2D2_CUDA_CHECK((launch_winconv<10, 64, 2, 2, 128, true, true>(ro(n->dpre2), R2, SplitC{pk.W2q.hi, pk.W2q.lo}, e, s)));
     }
     {   // conv1 (weights only; frames need no gradient)
         R2D2_CUDA_CHECK(n->C == 1 ? conv1_wgrad<1>(n, grads, s) : conv1_wgrad<4>(n, grads, s));
-        R2D2_CUDA_CHECK(colsum_split(ro(n->dpre1g), NF * 441, 32, B_PLAIN, grads, off[P_C1B], 0, A, n->colws, s));
     }
     return R2D2_OK;
 }

@@ -212,7 +212,7 @@ static inline cudaError_t launch_winconv(SplitC X, long long R, SplitC W, const 
 // the TMEM accumulation truncates -- partials go to the split-K workspace [chunk][taps*IC][NO].
 // PACK_G (NO = 32, X without lo plane): the hi and lo planes of a G row share one 128-byte line, a single N = 64 MMA
 // yields X.G_hi | X.G_lo side by side and the epilogue adds the halves.
-template <int GW, int IC, int KH, int KW, int TG, int NO, bool X_LO, bool G_LO, bool PACK_G, int KP>
+template <int GW, int IC, int KH, int KW, int TG, int NO, bool X_LO, bool G_LO, bool PACK_G, int KP, bool BIAS>
 struct WinWgradCfg {
     static constexpr int kTaps = KH * KW;
     static_assert(TG == kTaps || TG == KW, "tap groups are the whole kernel or one kernel row");
@@ -226,28 +226,32 @@ struct WinWgradCfg {
     static constexpr int kGBytes = (PACK_G ? 1 : (G_LO ? 2 : 1)) * kGPlane;
     static constexpr int kStage = kXBytes + kGBytes;
     static constexpr int kNMMA = PACK_G ? 64 : NO;
-    static constexpr int kCols = TG * kNMMA <= 32 ? 32 : TG * kNMMA <= 64 ? 64 : TG * kNMMA <= 128 ? 128 : TG * kNMMA <= 256 ? 256 : 512;
-    static constexpr int kStagesRaw = (227 * 1024 - 2048) / kStage;
-    // three stages when that lets two CTAs share an SM (prologue/epilogue of one hides behind the other), else up to four
-    static constexpr int kStages = (2 * (3 * kStage + 1280) <= 227 * 1024) ? 3 : (kStagesRaw > 4 ? 4 : kStagesRaw);
-    static constexpr int kSmem = kStages * kStage + 1024 + 256;
-    static_assert(IC % 64 == 0 && IC <= 128 && (NO == 32 || NO == 64) && KP % 16 == 0 && TG * kNMMA <= 512, "window wgrad shape");
+    static constexpr int kUsedCols = (TG + (BIAS ? 1 : 0)) * kNMMA;             // BIAS: one more accumulator, ones^T . G
+    static constexpr int kCols = kUsedCols <= 32 ? 32 : kUsedCols <= 64 ? 64 : kUsedCols <= 128 ? 128 : kUsedCols <= 256 ? 256 : 512;
+    static constexpr int kOnesBytes = 4096;                                     // two 16-line atoms of bf16 1.0
+    static constexpr int kStagesRaw = (227 * 1024 - 2048 - kOnesBytes) / kStage;
+    // three stages when that lets two CTAs share an SM (prologue/epilogue of one hides behind the other), else up to five
+    static constexpr bool kTwoCtas = kCols <= 256 && (2 * (3 * kStage + kOnesBytes + 1280) <= 227 * 1024);
+    static constexpr int kStages = kTwoCtas ? 3 : (kStagesRaw > 5 ? 5 : kStagesRaw);
+    static constexpr int kSmem = kStages * kStage + kOnesBytes + 1024 + 256;
+    static_assert(IC % 64 == 0 && IC <= 128 && (NO == 32 || NO == 64) && KP % 16 == 0 && kUsedCols <= 512, "window wgrad shape");
     static_assert(!PACK_G || (NO == 32 && !X_LO), "PACK_G packs hi|lo of a 32-channel gradient row");
     static_assert(kStages >= 2, "not enough shared memory");
 };
 
-template <int GW, int IC, int KH, int KW, int TG, int NO, bool X_LO, bool G_LO, bool PACK_G, int KP>
+template <int GW, int IC, int KH, int KW, int TG, int NO, bool X_LO, bool G_LO, bool PACK_G, int KP, bool BIAS>
 __global__ void __launch_bounds__(UM_THREADS, 1)
 winwgrad_kernel(const bf16* __restrict__ Xhi, const bf16* __restrict__ Xlo, const bf16* __restrict__ Ghi, const bf16* __restrict__ Glo,
-                long long R, int chunk /* pixels per item, multiple of KP */, float* __restrict__ ws) {
-    using Cfg = WinWgradCfg<GW, IC, KH, KW, TG, NO, X_LO, G_LO, PACK_G, KP>;
+                long long R, int chunk /* pixels per item, multiple of KP */, float* __restrict__ ws, float* __restrict__ bias_ws /* [chunks][NO] */) {
+    using Cfg = WinWgradCfg<GW, IC, KH, KW, TG, NO, X_LO, G_LO, PACK_G, KP, BIAS>;
     constexpr int S = Cfg::kStages, ATOMS = Cfg::kAtoms, NMMA = Cfg::kNMMA;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;
     uint8_t* smem = smem_raw + pad;
     const uint32_t sbase = raw + pad;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStage);       // full[S] | empty[S] | acc
+    const uint32_t sOnes = sbase + S * Cfg::kStage;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStage + Cfg::kOnesBytes);       // full[S] | empty[S] | acc
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int group = blockIdx.y;
@@ -265,6 +269,11 @@ winwgrad_kernel(const bf16* __restrict__ Xhi, const bf16* __restrict__ Xlo, cons
     if (warp == 8) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::kCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    const bool do_bias = BIAS && group == 0;
+    if (BIAS) {
+        for (int u = tid; u < Cfg::kOnesBytes / 4; u += UM_THREADS) reinterpret_cast<uint32_t*>(smem + S * Cfg::kStage)[u] = 0x3F803F80u;
+        fence_proxy_async_smem();
     }
     tc_fence_before();
     __syncthreads();
@@ -339,6 +348,22 @@ winwgrad_kernel(const bf16* __restrict__ Xhi, const bf16* __restrict__ Xlo, cons
                 for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
             }
         }
+        if (do_bias && warp == 0) {                                              // row 0 of the ones^T . G accumulator = column sums
+            for (int c = 0; c < NO; c += 16) {
+                float v[16];
+                tmem_ld16(tmem_base + (uint32_t)(TG * NMMA + c), v);
+                if (PACK_G) {
+                    float w[16];
+                    tmem_ld16(tmem_base + (uint32_t)(TG * NMMA + 32 + c), w);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] += w[i];
+                }
+                if (lane == 0) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) bias_ws[(size_t)blockIdx.x * NO + c + i] = v[i];
+                }
+            }
+        }
         tc_fence_before();
     } else {
         // ------------------------------------------------------------------ MMA issue
@@ -369,6 +394,18 @@ winwgrad_kernel(const bf16* __restrict__ Xhi, const bf16* __restrict__ Xlo, cons
                         umma_bf16(acc, x_hi + adv, g_hi + adv, idesc, accum);
                     }
                 }
+                if (do_bias) {
+                    const uint64_t ones = umma_desc_sw128_mn(sOnes, 2048);
+                    const uint64_t g_hi = umma_desc_sw128_mn(st + Cfg::kXBytes, 8192), g_lo = umma_desc_sw128_mn(st + Cfg::kXBytes + Cfg::kGPlane, 8192);
+                    const uint32_t acc = uT + TG * NMMA;
+#pragma unroll
+                    for (int k = 0; k < KP / 16; ++k) {
+                        const uint64_t adv = (uint64_t)(k * 128);
+                        uint32_t accum = (it | k) ? 1u : 0u;
+                        if (G_LO && !PACK_G) { umma_bf16(acc, ones, g_lo + adv, idesc, accum); accum = 1u; }
+                        umma_bf16(acc, ones, g_hi + adv, idesc, accum);
+                    }
+                }
                 umma_commit(smem_u32(&bars[S + s]));
                 if (it == nst - 1) umma_commit(smem_u32(&bars[2 * S]));
             }
@@ -382,10 +419,10 @@ winwgrad_kernel(const bf16* __restrict__ Xhi, const bf16* __restrict__ Xlo, cons
     }
 }
 
-template <int GW, int IC, int KH, int KW, int TG, int NO, bool X_LO, bool G_LO, bool PACK_G, int KP>
-static inline cudaError_t launch_winwgrad_inst(SplitC X, SplitC G, long long R, int chunk, float* ws, cudaStream_t s) {
-    using Cfg = WinWgradCfg<GW, IC, KH, KW, TG, NO, X_LO, G_LO, PACK_G, KP>;
-    auto kern = winwgrad_kernel<GW, IC, KH, KW, TG, NO, X_LO, G_LO, PACK_G, KP>;
+template <int GW, int IC, int KH, int KW, int TG, int NO, bool X_LO, bool G_LO, bool PACK_G, int KP, bool BIAS>
+static inline cudaError_t launch_winwgrad_inst(SplitC X, SplitC G, long long R, int chunk, float* ws, float* bias_ws, cudaStream_t s) {
+    using Cfg = WinWgradCfg<GW, IC, KH, KW, TG, NO, X_LO, G_LO, PACK_G, KP, BIAS>;
+    auto kern = winwgrad_kernel<GW, IC, KH, KW, TG, NO, X_LO, G_LO, PACK_G, KP, BIAS>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
@@ -393,18 +430,19 @@ static inline cudaError_t launch_winwgrad_inst(SplitC X, SplitC G, long long R, 
         configured = true;
     }
     const int nchunks = (int)((R + chunk - 1) / chunk);
-    kern<<<dim3(nchunks, Cfg::kGroups), UM_THREADS, Cfg::kSmem, s>>>(X.hi, X.lo, G.hi, G.lo, R, chunk, ws);
+    kern<<<dim3(nchunks, Cfg::kGroups), UM_THREADS, Cfg::kSmem, s>>>(X.hi, X.lo, G.hi, G.lo, R, chunk, ws, bias_ws);
     return cudaGetLastError();
 }
 
 // Precision policy of the other weight gradients (LO_NO_WEIGHT): strict = all three split products, otherwise hi.hi.
-template <int GW, int IC, int KH, int KW, int TG, int NO, bool X_HAS_LO, int KP>
-static inline cudaError_t launch_winwgrad(SplitC X, SplitC G, long long R, int chunk, float* ws, cudaStream_t s) {
-    if (g_fast_math != 0) return launch_winwgrad_inst<GW, IC, KH, KW, TG, NO, false, false, false, KP>(X, G, R, chunk, ws, s);
+// BIAS: also emit per-chunk column sums of G (the bias gradient) into bias_ws[chunk][NO].
+template <int GW, int IC, int KH, int KW, int TG, int NO, bool X_HAS_LO, int KP, bool BIAS>
+static inline cudaError_t launch_winwgrad(SplitC X, SplitC G, long long R, int chunk, float* ws, float* bias_ws, cudaStream_t s) {
+    if (g_fast_math != 0) return launch_winwgrad_inst<GW, IC, KH, KW, TG, NO, false, false, false, KP, BIAS>(X, G, R, chunk, ws, bias_ws, s);
     if constexpr (!X_HAS_LO && NO == 32) {
-        return launch_winwgrad_inst<GW, IC, KH, KW, TG, NO, false, true, true, KP>(X, G, R, chunk, ws, s);
+        return launch_winwgrad_inst<GW, IC, KH, KW, TG, NO, false, true, true, KP, BIAS>(X, G, R, chunk, ws, bias_ws, s);
     } else {
-        return launch_winwgrad_inst<GW, IC, KH, KW, TG, NO, X_HAS_LO, true, false, KP>(X, G, R, chunk, ws, s);
+        return launch_winwgrad_inst<GW, IC, KH, KW, TG, NO, X_HAS_LO, true, false, KP, BIAS>(X, G, R, chunk, ws, bias_ws, s);
     }
 }
 
