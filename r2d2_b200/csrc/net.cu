@@ -720,35 +720,33 @@ static const bool g_window_conv = [] { const char* e = getenv("R2D2_WINDOW_CONV"
 template <int GW, int GH, int OW, int OH>
 struct EpiWinBiasSplit {        // out(split)[row*64 + n] = relu(v + bias[n])
     SplitW out; const float* bias;
-    __device__ __forceinline__ void store16(long long p, int n, const float (&v)[16]) const {
+    struct Pre {};
+    __device__ __forceinline__ void prefetch(long long, Pre&) const {}
+    __device__ __forceinline__ void store16(long long p, int n, const float (&v)[16], const Pre&) const {
         const int r = (int)(p % (GW * GH)), gy = r / GW, gx = r - gy * GW;
         if (gy >= OH || gx >= OW) return;
         const size_t row = (size_t)(p / (GW * GH)) * (OH * OW) + gy * OW + gx;
+        float o[16];
 #pragma unroll
-        for (int j = 0; j < 16; j += 8) {
-            float o[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = fmaxf(v[j + i] + __ldg(bias + n + j + i), 0.f);
-            split_store8(out.hi, out.lo, row * 64 + n + j, o);
-        }
+        for (int i = 0; i < 16; ++i) o[i] = fmaxf(v[i] + __ldg(bias + n + i), 0.f);
+        split_store16(out.hi, out.lo, row * 64 + n, o);
     }
 };
 struct EpiWinConv1Pair {        // 21x21 s2d grid -> 20x20; columns 0-31 online act1, 32-63 target act1
     SplitW out0, out1; const float* bias0; const float* bias1; float scale;
-    __device__ __forceinline__ void store16(long long p, int n, const float (&v)[16]) const {
+    struct Pre {};
+    __device__ __forceinline__ void prefetch(long long, Pre&) const {}
+    __device__ __forceinline__ void store16(long long p, int n, const float (&v)[16], const Pre&) const {
         const int r = (int)(p % 441), gy = r / 21, gx = r - gy * 21;
         if (gy >= 20 || gx >= 20) return;
         const size_t o1 = ((size_t)(p / 441) * 100 + (gy >> 1) * 10 + (gx >> 1)) * 128 + ((gy & 1) * 2 + (gx & 1)) * 32;   // act1: s2d-by-2
         const SplitW& o = n < 32 ? out0 : out1;
         const float* b = n < 32 ? bias0 : bias1;
         const int c = n & 31;
+        float q[16];
 #pragma unroll
-        for (int j = 0; j < 16; j += 8) {
-            float q[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) q[i] = fmaxf(v[j + i] * scale + __ldg(b + c + j + i), 0.f);
-            split_store8(o.hi, o.lo, o1 + c + j, q);
-        }
+        for (int i = 0; i < 16; ++i) q[i] = fmaxf(v[i] * scale + __ldg(b + c + i), 0.f);
+        split_store16(o.hi, o.lo, o1 + c, q);
     }
 };
 
@@ -756,42 +754,52 @@ struct EpiWinConv1Pair {        // 21x21 s2d grid -> 20x20; columns 0-31 online 
 // conv2's 10x10 gradient grid (row f*100 + y*10 + x; gy == 9 / gx == 9 stay zero)
 struct EpiWinDgrad3 {
     SplitW out; SplitC act;
-    __device__ __forceinline__ void store16(long long p, int n, const float (&v)[16]) const {
+    struct Pre { uint4 m[8]; };
+    __device__ __forceinline__ void prefetch(long long p, Pre& pre) const {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pre.m[i] = __ldg(reinterpret_cast<const uint4*>(act.hi + (size_t)p * 64) + i);
+    }
+    __device__ __forceinline__ void store16(long long p, int n, const float (&v)[16], const Pre& pre) const {
         const int r = (int)(p % 81), y = r / 9, x = r - y * 9;
-        const size_t o = ((size_t)(p / 81) * 100 + y * 10 + x) * 64 + n, a = (size_t)p * 64 + n;
+        const size_t o = ((size_t)(p / 81) * 100 + y * 10 + x) * 64 + n;
+        float q[16];
 #pragma unroll
         for (int j = 0; j < 16; j += 8) {
-            const uint4 h = *reinterpret_cast<const uint4*>(act.hi + a + j);
+            const uint4 h = pre.m[(n + j) >> 3];
             const uint32_t hw4[4] = {h.x, h.y, h.z, h.w};
-            float q[8];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                q[2 * i] = (hw4[i] & 0x7FFFu) ? v[j + 2 * i] : 0.f;
-                q[2 * i + 1] = (hw4[i] & 0x7FFF0000u) ? v[j + 2 * i + 1] : 0.f;
+                q[j + 2 * i] = (hw4[i] & 0x7FFFu) ? v[j + 2 * i] : 0.f;
+                q[j + 2 * i + 1] = (hw4[i] & 0x7FFF0000u) ? v[j + 2 * i + 1] : 0.f;
             }
-            split_store8(out.hi, out.lo, o + j, q);
         }
+        split_store16(out.hi, out.lo, o, q);
     }
 };
 // conv2 data gradient: row p = (f, Y, X) of the 10x10 s2d-by-2 grid, column n = (ry*2+rx)*32 + c = act1 pixel
 // (2Y+ry, 2X+rx); ReLU mask from act1 (same layout); result on conv1's 21x21 gradient grid, 32 channels per pixel
 struct EpiWinDgrad2 {
     SplitW out; SplitC act;
-    __device__ __forceinline__ void store16(long long p, int n, const float (&v)[16]) const {
+    struct Pre { uint4 m[16]; };
+    __device__ __forceinline__ void prefetch(long long p, Pre& pre) const {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pre.m[i] = __ldg(reinterpret_cast<const uint4*>(act.hi + (size_t)p * 128) + i);
+    }
+    __device__ __forceinline__ void store16(long long p, int n, const float (&v)[16], const Pre& pre) const {
         const int r = (int)(p % 100), Y = r / 10, X = r - Y * 10, sub = n >> 5, c = n & 31;
-        const size_t o = ((size_t)(p / 100) * 441 + (2 * Y + (sub >> 1)) * 21 + 2 * X + (sub & 1)) * 32 + c, a = (size_t)p * 128 + n;
+        const size_t o = ((size_t)(p / 100) * 441 + (2 * Y + (sub >> 1)) * 21 + 2 * X + (sub & 1)) * 32 + c;
+        float q[16];
 #pragma unroll
         for (int j = 0; j < 16; j += 8) {
-            const uint4 h = *reinterpret_cast<const uint4*>(act.hi + a + j);
+            const uint4 h = pre.m[(n + j) >> 3];
             const uint32_t hw4[4] = {h.x, h.y, h.z, h.w};
-            float q[8];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                q[2 * i] = (hw4[i] & 0x7FFFu) ? v[j + 2 * i] : 0.f;
-                q[2 * i + 1] = (hw4[i] & 0x7FFF0000u) ? v[j + 2 * i + 1] : 0.f;
+                q[j + 2 * i] = (hw4[i] & 0x7FFFu) ? v[j + 2 * i] : 0.f;
+                q[j + 2 * i + 1] = (hw4[i] & 0x7FFF0000u) ? v[j + 2 * i + 1] : 0.f;
             }
-            split_store8(out.hi, out.lo, o + j, q);
         }
+        split_store16(out.hi, out.lo, o, q);
     }
 };
 // window weight gradient + split reduction into the reference layout

@@ -56,6 +56,19 @@ __device__ __forceinline__ void split_store8(bf16* hi, bf16* lo, size_t off, con
     *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
     *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
 }
+// 16 floats -> one 32-byte sector per plane (256-bit stores: a lane fills whole sectors even when neighbouring lanes
+// write rows far apart).  off must be a multiple of 16 elements.
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t (&w)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]),
+                 "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+}
+__device__ __forceinline__ void split_store16(bf16* hi, bf16* lo, size_t off, const float* v) {
+    uint32_t h[8], l[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) split2(v[2 * j], v[2 * j + 1], h[j], l[j]);
+    st_global_256(hi + off, h);
+    st_global_256(lo + off, l);
+}
 __device__ __forceinline__ float split_load(const bf16* hi, const bf16* lo, size_t off) {
     return __bfloat162float(hi[off]) + __bfloat162float(lo[off]);
 }

@@ -35,7 +35,7 @@ struct WinCfg {
     static_assert(kStages >= 2, "not enough shared memory for two window stages");
 };
 
-// Epilogue contract: store_row(p, acc-chunk) style functor with  void store16(long long p, int n, const float (&v)[16]) const
+// Epilogue contract: struct Pre; void prefetch(long long p, Pre&) const; void store16(long long p, int n, const float (&v)[16], const Pre&) const
 // where p is the GRID pixel index (frame * GW*GH + gy * GW + gx); the functor drops junk pixels itself.
 template <int GW, int IC, int KH, int KW, int N, bool A_LO, bool B_LO, bool BACK, class Epi>
 __global__ void __launch_bounds__(UM_THREADS, 1)
@@ -112,14 +112,16 @@ winconv_kernel(const bf16* __restrict__ Xhi, const bf16* __restrict__ Xlo, long 
         long long ti = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
             const int a = (int)(ti & 1);
+            const long long p = tile * 128 + (warp & 3) * 32 + lane;
+            typename Epi::Pre pre;                                              // operands the epilogue needs from global memory (ReLU masks):
+            if (p < R) ep.prefetch(p, pre);                                     // requested BEFORE waiting for the accumulator
             mbar_wait(smem_u32(&bars[2 * S + a]), (uint32_t)(ti >> 1) & 1u);
             tc_fence_after();
-            const long long p = tile * 128 + (warp & 3) * 32 + lane;
 #pragma unroll
             for (int c = 0; c < N; c += 16) {
                 float v[16];
                 tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(a * ACC_COLS + c), v);
-                if (p < R) ep.store16(p, c, v);
+                if (p < R) ep.store16(p, c, v, pre);
             }
             tc_fence_before();
             __syncwarp();
