@@ -366,13 +366,10 @@ struct Epi2Latent {
         if (m >= B * T || n >= LATENT) return;
         const int b = m / T, t = m - b * T;
         const size_t o = ((size_t)t * B + b) * KU + n;
+        float r[16];
 #pragma unroll
-        for (int j = 0; j < 16; j += 8) {
-            float r[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) r[i] = fmaxf(v[j + i] + __ldg(bias + n + j + i), 0.f);
-            split_store8(U.hi, U.lo, o + j, r);
-        }
+        for (int i = 0; i < 16; ++i) r[i] = fmaxf(v[i] + __ldg(bias + n + i), 0.f);
+        split_store16(U.hi, U.lo, o, r);                                        // KU % 16 == 0
     }
 };
 // d latent epilogue: rows are time-major (t,b); mask by latent>0; write frame-major for the encoder backward
@@ -381,18 +378,18 @@ struct Epi2DLatent {
     __device__ __forceinline__ void store16(int m, int n, const float (&v)[16], int) const {
         if (m >= B * T || n >= LATENT) return;
         const int t = m / B, b = m - t * B;
+        float r[16];
 #pragma unroll
         for (int j = 0; j < 16; j += 8) {
             const uint4 h = *reinterpret_cast<const uint4*>(U.hi + (size_t)m * KU + n + j);
             const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
-            float r[8];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                r[2 * i] = (hw[i] & 0x7FFFu) ? v[j + 2 * i] : 0.f;
-                r[2 * i + 1] = (hw[i] & 0x7FFF0000u) ? v[j + 2 * i + 1] : 0.f;
+                r[j + 2 * i] = (hw[i] & 0x7FFFu) ? v[j + 2 * i] : 0.f;
+                r[j + 2 * i + 1] = (hw[i] & 0x7FFF0000u) ? v[j + 2 * i + 1] : 0.f;
             }
-            split_store8(dlat.hi, dlat.lo, ((size_t)b * T + t) * LATENT + n + j, r);
         }
+        split_store16(dlat.hi, dlat.lo, ((size_t)b * T + t) * LATENT + n, r);
     }
 };
 // FC data gradient -> dpre3 on conv3's INPUT grid (9x9, the 7x7 valid outputs at gy,gx < 7; the rest stays zero), masked
@@ -403,18 +400,18 @@ struct Epi2MaskedToGrid3 {
         if (m >= M || n >= FLAT3) return;
         const int hw = n >> 6, c = n & 63, oy = hw / 7, ox = hw - oy * 7;
         const size_t o = ((size_t)m * 81 + oy * 9 + ox) * 64 + c, a = (size_t)m * FLAT3 + n;
+        float r[16];
 #pragma unroll
         for (int j = 0; j < 16; j += 8) {
             const uint4 h = *reinterpret_cast<const uint4*>(act.hi + a + j);
             const uint32_t hw4[4] = {h.x, h.y, h.z, h.w};
-            float r[8];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                r[2 * i] = (hw4[i] & 0x7FFFu) ? v[j + 2 * i] : 0.f;
-                r[2 * i + 1] = (hw4[i] & 0x7FFF0000u) ? v[j + 2 * i + 1] : 0.f;
+                r[j + 2 * i] = (hw4[i] & 0x7FFFu) ? v[j + 2 * i] : 0.f;
+                r[j + 2 * i + 1] = (hw4[i] & 0x7FFF0000u) ? v[j + 2 * i + 1] : 0.f;
             }
-            split_store8(out.hi, out.lo, o + j, r);
         }
+        split_store16(out.hi, out.lo, o, r);
     }
 };
 // scatter rows of d(hidden rows) to dH[t][b] (fp32) through the row map
@@ -432,23 +429,32 @@ struct Epi2ScatterRows {
 
 // split-K reduce + routing of a weight gradient into the reference's parameter layout
 enum RouteKind { R_C1, R_C2, R_C3, R_FC, R_WIH, R_WHH, R_H0, R_H2, R_C1W, R_C2W, R_C3W };   // R_C*W: window wgrad partials [tap*IC + c][out channel]
-__global__ void reduce_route_kernel(const float* __restrict__ ws, int splits, int M, int N, int kind, float* __restrict__ g,
-                                    const int64_t* __restrict__ off, int A, int C, float scale) {
-    // block = 32 consecutive outputs x 8 slices of the split index, summed in a fixed order
-    __shared__ float sm[8][33];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int64_t i = blockIdx.x * 32ll + tx;
-    const bool in = i < (int64_t)M * N;
-    float acc = 0.f;
-    if (in)
-        for (int z = ty; z < splits; z += 8) acc += ws[(size_t)z * M * N + i];
-    sm[ty][tx] = acc;
-    __syncthreads();
-    if (ty != 0 || !in) return;
-    int m = i / N, n = i % N;
+// SL = 8: block = 32 consecutive outputs x 8 slices of the split index (many splits, few outputs: the window wgrads);
+// SL = 1: one thread per output.  Fixed summation order either way.
+template <int SL>
+__global__ void __launch_bounds__(256) reduce_route_kernel(const float* __restrict__ ws, int splits, int M, int N, int kind, float* __restrict__ g,
+                                                           const int64_t* __restrict__ off, int A, int C, float scale) {
+    int64_t i;
     float s = 0.f;
+    if constexpr (SL == 1) {
+        i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+        if (i >= (int64_t)M * N) return;
+        for (int z = 0; z < splits; ++z) s += ws[(size_t)z * M * N + i];
+    } else {
+        __shared__ float sm[SL][33];
+        const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+        i = blockIdx.x * 32ll + tx;
+        const bool in = i < (int64_t)M * N;
+        float acc = 0.f;
+        if (in)
+            for (int z = ty; z < splits; z += SL) acc += ws[(size_t)z * M * N + i];
+        sm[ty][tx] = acc;
+        __syncthreads();
+        if (ty != 0 || !in) return;
 #pragma unroll
-    for (int y = 0; y < 8; ++y) s += sm[y][tx];
+        for (int y = 0; y < SL; ++y) s += sm[y][tx];
+    }
+    int m = i / N, n = i % N;
     s *= scale;
     if (kind >= R_C1W) { const int t = m; m = n; n = t; kind = kind == R_C1W ? R_C1 : kind == R_C2W ? R_C2 : R_C3; }   // (k, out) -> (out, k)
     const int KIH = LATENT + A + 1;
@@ -588,7 +594,8 @@ static cudaError_t wgrad2(const AS& a, const BS& b, int M, int N, int K, int spl
     cudaError_t e = launch_umma2<UBN, POL>(a, b, ep, M, N, K, splits, s);
     if (e != cudaSuccess) return e;
     const int64_t tot = (int64_t)M * N;
-    reduce_route_kernel<<<cdiv(tot, 32), 256, 0, s>>>(net->ws, splits, M, N, kind, grads, d_off, net->A, net->C, scale);
+    if (splits >= 16) reduce_route_kernel<8><<<cdiv(tot, 32), 256, 0, s>>>(net->ws, splits, M, N, kind, grads, d_off, net->A, net->C, scale);
+    else reduce_route_kernel<1><<<cdiv(tot, 256), 256, 0, s>>>(net->ws, splits, M, N, kind, grads, d_off, net->A, net->C, scale);
     return cudaGetLastError();
 }
 
@@ -812,7 +819,7 @@ static cudaError_t winwgrad(SplitC X, SplitC G, long long R, int chunk, int kind
     if ((size_t)splits * M * NO > net->ws_floats || (size_t)splits * NO > (size_t)kColP * 4096 || chunk % KP) return cudaErrorInvalidValue;
     cudaError_t e = launch_winwgrad<GW, IC, KH, KW, TG, NO, X_HAS_LO, KP, true>(X, G, R, chunk, net->ws, net->colws, s);
     if (e != cudaSuccess) return e;
-    reduce_route_kernel<<<cdiv((int64_t)M * NO, 32), 256, 0, s>>>(net->ws, splits, M, NO, kind, grads, d_off, net->A, net->C, scale);
+    reduce_route_kernel<8><<<cdiv((int64_t)M * NO, 32), 256, 0, s>>>(net->ws, splits, M, NO, kind, grads, d_off, net->A, net->C, scale);
     colsum_final_kernel<<<(NO + 31) / 32, 256, 0, s>>>(net->colws, splits, NO, B_PLAIN, grads, bias_off, 0, net->A);
     return cudaGetLastError();
 }
@@ -1062,9 +1069,9 @@ int r2d2_net_backward(r2d2_net* n, const float* params, const float* dq, float* 
                                             n->dhid);
     R2D2_LAUNCH_CHECK();
     {   // layer-2 weights: [A+1 (pad 16)] x [1024] = dout16^T . hid   (tiny: CUDA cores)
-        const int P = 16, chunk = (Rmax + P - 1) / P;
+        const int P = 128, chunk = (Rmax + P - 1) / P;
         head_w2_grad_kernel<<<dim3(2 * H / 128, P), 128, 0, s>>>(n->dout16, ro(ac.hid), Rmax, chunk, n->ws);
-        reduce_route_kernel<<<cdiv(16 * 2 * H, 32), 256, 0, s>>>(n->ws, P, 16, 2 * H, R_H2, grads, d_off, A, n->C, 1.f);
+        reduce_route_kernel<8><<<cdiv(16 * 2 * H, 32), 256, 0, s>>>(n->ws, P, 16, 2 * H, R_H2, grads, d_off, A, n->C, 1.f);
         R2D2_CUDA_CHECK(colsum_f32(n->dout16, Rmax, 16, B_H2, grads, off[P_A2B], off[P_V2B], A, n->colws, s));
     }
     {   // layer-0 weights: [1024] x [512] = dhid^T . Hsel
