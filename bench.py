@@ -189,6 +189,32 @@ def count_kernels(fn):
     return ours, other
 
 
+def kernel_times(fn, steps=3):
+    """Per-kernel durations of `steps` warm learner steps (CUPTI via torch.profiler; no replay, no serialisation)."""
+    import collections
+    import re
+    from torch.profiler import ProfilerActivity, profile
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for i in range(steps):
+            fn(i)
+        torch.cuda.synchronize()
+    agg = collections.OrderedDict()
+    for ev in prof.events():
+        if ev.device_type != torch.autograd.DeviceType.CUDA:
+            continue
+        name = re.sub(r"^void ", "", ev.name)
+        name = re.sub(r"\(.*", "", name)[:140]
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += ev.device_time if hasattr(ev, "device_time") else ev.cuda_time
+    tot = sum(a[1] for a in agg.values())
+    lines = [f"{steps} steps: sum of kernel durations {tot / steps:.1f} us/step (CUPTI, warm)"]
+    for k, a in sorted(agg.items(), key=lambda x: -x[1][1]):
+        lines.append(f"{a[1] / steps:9.1f} us {a[0] / steps:6.1f} {100 * a[1] / tot:5.1f}%  {k}")
+    return "\n".join(lines)
+
+
 def run_ours(args):
     import torch.distributed as dist
     from r2d2_b200 import _lib, config
@@ -276,6 +302,12 @@ def run_ours(args):
             core.backward(core.dq)
         ms_unroll = timed(unroll_only, max(5, args.steps // 2), 3)
 
+    if args.kernel_times and world == 1:
+        text = kernel_times(step_resident)
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "kernel_times.txt"), "w") as f:
+            f.write(text + "\n")
+        print(text, file=sys.stderr)
     ours, other = count_kernels(lambda: step_resident(0))      # every rank runs it: the step contains the all-reduce
     if rank == 0:
         peaks = measured_peaks()
@@ -329,6 +361,7 @@ def main():
     ap.add_argument("--fast", action="store_true", help="same as --precision fast")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-times", action="store_true", help="also write gpurun_out/kernel_times.txt (per-kernel CUPTI durations)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

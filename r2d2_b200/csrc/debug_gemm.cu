@@ -144,7 +144,12 @@ __global__ void __launch_bounds__(128) shift_probe_kernel(const bf16* __restrict
     if (tid == 0) {
         const uint32_t start = sA + 128u * (uint32_t)shift;
         const uint64_t bdesc = umma_desc_sw128(sB);
-        if (mode == 2) {
+        if (mode >= 3) {
+            // MN-major, M = 128 as two OVERLAPPING 64-column atoms: atom 1 starts (mode - 2) lines after atom 0 (LBO = 128 B x lines)
+            const uint64_t adesc = umma_desc_sw128_mn(start, 128u * (uint32_t)(mode - 2));
+            const uint32_t idesc = ((1u << 4) | (1u << 7) | (1u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24)) | (1u << 15);
+            for (int k = 0; k < 4; ++k) umma_bf16(tmem, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 2), idesc, k ? 1u : 0u);
+        } else if (mode == 2) {
             // A read MN-major: smem rows are the REDUCTION index (64 + shift lines of 64 M-elements), M = 64
             const uint64_t adesc = umma_desc_sw128_mn(start, 8192);
             const uint32_t idesc = ((1u << 4) | (1u << 7) | (1u << 10) | ((32u >> 3) << 17) | ((64u >> 4) << 24)) | (1u << 15);
@@ -171,7 +176,7 @@ __global__ void __launch_bounds__(128) shift_probe_kernel(const bf16* __restrict
 }  // namespace r2d2
 
 extern "C" int r2d2_debug_shift_probe(const void* A, const void* B, float* D, int shift, int mode, void* stream) {
-    R2D2_REQUIRE(A && B && D && shift >= 0 && shift <= 16, "bad arguments");
+    R2D2_REQUIRE(A && B && D && shift >= 0 && shift <= 16 && mode >= 0 && mode <= 24, "bad arguments");
     const int smem = 144 * 128 + 32 * 128 + 1024 + 64;
     r2d2::shift_probe_kernel<<<1, 128, smem, r2d2::as_stream(stream)>>>((const r2d2::bf16*)A, (const r2d2::bf16*)B, D, shift, mode);
     R2D2_LAUNCH_CHECK();

@@ -1139,7 +1139,7 @@ int r2d2_net_backward(r2d2_net* n, const float* params, const float* dq, float* 
     // The conv layers run as window convolutions (winconv.cuh): gradients live on each layer's input grid.
     {   // conv3: weights from act2 (9x9 grid) x dpre3 (same grid); data gradient = 3x3 window conv of dpre3 with flipped taps
         const long long R3 = (long long)NF * 81;
-        R2D2_CUDA_CHECK((winwgrad<9, 64, 3, 3, 3, 64, true, 64>(ro(ac.act2), ro(n->dpre3), R3, 3072, R_C3W, off[P_C3B], n, grads, d_off, 1.f, s)));
+        R2D2_CUDA_CHECK((winwgrad<9, 64, 3, 3, 9, 64, true, 64>(ro(ac.act2), ro(n->dpre3), R3, 3072, R_C3W, off[P_C3B], n, grads, d_off, 1.f, s)));
         EpiWinDgrad3 e{n->dpre2, ro(ac.act2)};
         R2D2_CUDA_CHECK((launch_winconv<9, 64, 3, 3, 64, true, true>(ro(n->dpre3), R3, SplitC{pk.W3d.hi, pk.W3d.lo}, e, s)));
     }

@@ -101,11 +101,19 @@ winconv_kernel(const bf16* __restrict__ Xhi, const bf16* __restrict__ Xlo, long 
                     if (A_LO) cp_async16(st + Cfg::kWinBytes + dst, Xlo + src, ok);
                 }
                 cp_async_commit();
-                cp_async_wait<0>();
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&bars[s]));
+                if (it > 0) {                                                   // hand over the PREVIOUS stage: two groups stay in flight per thread
+                    cp_async_wait<1>();
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&bars[(int)((it - 1) % S)]));
+                }
             }
+        }
+        if (it > 0) {
+            cp_async_wait<0>();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars[(int)((it - 1) % S)]));
         }
     } else if (warp < 8) {
         // ------------------------------------------------------------------ epilogue
@@ -228,7 +236,12 @@ struct WinWgradCfg {
     static constexpr int kGBytes = (PACK_G ? 1 : (G_LO ? 2 : 1)) * kGPlane;
     static constexpr int kStage = kXBytes + kGBytes;
     static constexpr int kNMMA = PACK_G ? 64 : NO;
-    static constexpr int kUsedCols = (TG + (BIAS ? 1 : 0)) * kNMMA;             // BIAS: one more accumulator, ones^T . G
+    // IC = 64 would leave half of the M = 128 datapath idle (an M = 64 MMA costs the same cycles): two taps share one
+    // MMA instead -- atom 0 = the window at tap 2a, atom 1 = the SAME buffer off(2a+1) - off(2a) lines further (the
+    // descriptor's atom stride is plain address arithmetic; tools/shift_probe.py).  Rows 64..127 of accumulator a = tap 2a+1.
+    static constexpr bool kPair = IC == 64;
+    static constexpr int kNAcc = kPair ? (TG + 1) / 2 : TG;
+    static constexpr int kUsedCols = (kNAcc + (BIAS ? 1 : 0)) * kNMMA;          // BIAS: one more accumulator, ones^T . G
     static constexpr int kCols = kUsedCols <= 32 ? 32 : kUsedCols <= 64 ? 64 : kUsedCols <= 128 ? 128 : kUsedCols <= 256 ? 256 : 512;
     static constexpr int kOnesBytes = 4096;                                     // two 16-line atoms of bf16 1.0
     static constexpr int kStagesRaw = (227 * 1024 - 2048 - kOnesBytes) / kStage;
@@ -321,31 +334,43 @@ winwgrad_kernel(const bf16* __restrict__ Xhi, const bf16* __restrict__ Xlo, cons
                 }
             }
             cp_async_commit();
-            cp_async_wait<0>();
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&bars[s]));
+            if (it > 0) {                                                       // hand over the PREVIOUS stage: two groups stay in flight per thread
+                cp_async_wait<1>();
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bars[(it - 1) % S]));
+            }
         }
+        cp_async_wait<0>();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars[(nst - 1) % S]));
         // ------------------------------------------------------------------ epilogue: TMEM -> partial [chunk][taps*IC][NO]
         mbar_wait(smem_u32(&bars[2 * S]), 0);
         tc_fence_after();
         const int q = warp & 3, half = warp >> 2;
-        const bool lane_ok = (IC == 128) || lane < 16;                          // M = 64: rows live in lanes 32q + (0..15)
-        const int m = (IC == 128) ? q * 32 + lane : q * 16 + lane;
         float* out = ws + (size_t)blockIdx.x * (Cfg::kTaps * IC * NO);
-        constexpr int NCH = NO / 16;                                            // 16-column chunks per tap
-        for (int u = half; u < TG * NCH; u += 2) {
-            const int t = u / NCH, c = (u % NCH) * 16;
+        constexpr int NCH = NO / 16;                                            // 16-column chunks per accumulator
+        for (int u = half; u < Cfg::kNAcc * NCH; u += 2) {
+            const int a = u / NCH, c = (u % NCH) * 16;
             float v[16];
-            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * NMMA + c), v);
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * NMMA + c), v);
             if (PACK_G) {
                 float w[16];
-                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * NMMA + 32 + c), w);
+                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * NMMA + 32 + c), w);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] += w[i];
             }
-            if (lane_ok) {
-                float* o = out + ((size_t)(tap0 + t) * IC + m) * NO + c;
+            // accumulator row -> (tap, channel).  M = 128: row = 32q + lane; paired taps put tap 2a+1 in rows 64..127.
+            // M = 64 (unpaired last tap): rows live in lanes 32q + (0..15)
+            int tap, ch; bool ok = true;
+            if (Cfg::kPair) {
+                const bool paired = 2 * a + 1 < TG;
+                if (paired) { tap = 2 * a + (q >> 1); ch = (q & 1) * 32 + lane; }
+                else { tap = 2 * a; ch = q * 16 + lane; ok = lane < 16; }
+            } else { tap = a; ch = q * 32 + lane; }
+            if (ok) {
+                float* o = out + ((size_t)(tap0 + tap) * IC + ch) * NO + c;
 #pragma unroll
                 for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
             }
@@ -353,10 +378,10 @@ winwgrad_kernel(const bf16* __restrict__ Xhi, const bf16* __restrict__ Xlo, cons
         if (do_bias && warp == 0) {                                              // row 0 of the ones^T . G accumulator = column sums
             for (int c = 0; c < NO; c += 16) {
                 float v[16];
-                tmem_ld16(tmem_base + (uint32_t)(TG * NMMA + c), v);
+                tmem_ld16(tmem_base + (uint32_t)(Cfg::kNAcc * NMMA + c), v);
                 if (PACK_G) {
                     float w[16];
-                    tmem_ld16(tmem_base + (uint32_t)(TG * NMMA + 32 + c), w);
+                    tmem_ld16(tmem_base + (uint32_t)(Cfg::kNAcc * NMMA + 32 + c), w);
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] += w[i];
                 }
@@ -369,7 +394,9 @@ winwgrad_kernel(const bf16* __restrict__ Xhi, const bf16* __restrict__ Xlo, cons
         tc_fence_before();
     } else {
         // ------------------------------------------------------------------ MMA issue
-        constexpr uint32_t idesc = ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NMMA >> 3) << 17) | ((uint32_t)(IC >> 4) << 24)) | (1u << 15) | (1u << 16);
+        constexpr uint32_t idesc_base = ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NMMA >> 3) << 17)) | (1u << 15) | (1u << 16);
+        constexpr uint32_t idesc = idesc_base | ((uint32_t)(IC >> 4) << 24);      // M = IC (bias row, unpaired taps)
+        constexpr uint32_t idesc128 = idesc_base | (8u << 24);                    // M = 128
         const bool leader = elect_one();
         const uint32_t uS = __shfl_sync(0xffffffffu, sbase, 0), uT = __shfl_sync(0xffffffffu, tmem_base, 0);
         for (int it = 0; it < nst; ++it) {
@@ -380,26 +407,30 @@ winwgrad_kernel(const bf16* __restrict__ Xhi, const bf16* __restrict__ Xlo, cons
             const uint32_t st = uS + s * Cfg::kStage;
             if (leader) {
 #pragma unroll
-                for (int t = 0; t < TG; ++t) {
-                    const int tap = tap0 + t;                                    // (ky, kx); tap0 is a multiple of KW or 0
-                    const uint32_t shift = (uint32_t)(((tap / KW) * GW + (tap % KW)) - wbase) * 128u;
-                    const uint64_t x_hi = umma_desc_sw128_mn(st + shift, Cfg::kWinBytes);
-                    const uint64_t x_lo = umma_desc_sw128_mn(st + ATOMS * Cfg::kWinBytes + shift, Cfg::kWinBytes);
+                for (int a = 0; a < Cfg::kNAcc; ++a) {
+                    const int t1 = tap0 + (Cfg::kPair ? 2 * a : a);             // (ky, kx); tap0 is a multiple of KW or 0
+                    const bool paired = Cfg::kPair && (2 * a + 1 < TG);
+                    const int off1 = (t1 / KW) * GW + (t1 % KW), off2 = ((t1 + 1) / KW) * GW + ((t1 + 1) % KW);
+                    const uint32_t shift = (uint32_t)(off1 - wbase) * 128u;
+                    const uint32_t lbo = paired ? (uint32_t)(off2 - off1) * 128u : (uint32_t)Cfg::kWinBytes;
+                    const uint32_t id = (paired || IC == 128) ? idesc128 : idesc;
+                    const uint64_t x_hi = umma_desc_sw128_mn(st + shift, lbo);
+                    const uint64_t x_lo = umma_desc_sw128_mn(st + ATOMS * Cfg::kWinBytes + shift, lbo);
                     const uint64_t g_hi = umma_desc_sw128_mn(st + Cfg::kXBytes, 8192), g_lo = umma_desc_sw128_mn(st + Cfg::kXBytes + Cfg::kGPlane, 8192);
-                    const uint32_t acc = uT + t * NMMA;
+                    const uint32_t acc = uT + a * NMMA;
 #pragma unroll
                     for (int k = 0; k < KP / 16; ++k) {
                         const uint64_t adv = (uint64_t)(k * 128);                // 16 lines x 128 B, >> 4
                         uint32_t accum = (it | k) ? 1u : 0u;
-                        if (X_LO) { umma_bf16(acc, x_lo + adv, g_hi + adv, idesc, accum); accum = 1u; }
-                        if (G_LO && !PACK_G) { umma_bf16(acc, x_hi + adv, g_lo + adv, idesc, accum); accum = 1u; }
-                        umma_bf16(acc, x_hi + adv, g_hi + adv, idesc, accum);
+                        if (X_LO) { umma_bf16(acc, x_lo + adv, g_hi + adv, id, accum); accum = 1u; }
+                        if (G_LO && !PACK_G) { umma_bf16(acc, x_hi + adv, g_lo + adv, id, accum); accum = 1u; }
+                        umma_bf16(acc, x_hi + adv, g_hi + adv, id, accum);
                     }
                 }
                 if (do_bias) {
                     const uint64_t ones = umma_desc_sw128_mn(sOnes, 2048);
                     const uint64_t g_hi = umma_desc_sw128_mn(st + Cfg::kXBytes, 8192), g_lo = umma_desc_sw128_mn(st + Cfg::kXBytes + Cfg::kGPlane, 8192);
-                    const uint32_t acc = uT + TG * NMMA;
+                    const uint32_t acc = uT + Cfg::kNAcc * NMMA;
 #pragma unroll
                     for (int k = 0; k < KP / 16; ++k) {
                         const uint64_t adv = (uint64_t)(k * 128);

@@ -30,3 +30,16 @@ for s in range(0, 12):
     err = (D[lanes] - ref).abs().max().item() / ref.abs().max().item()
     line.append(f"{s}:{'ok' if err < 1e-2 else f'{err:.1e}'}")
 print("MN-major shifted (mode 2): " + " ".join(line))
+
+# mode 2+d: M = 128 built from two overlapping MN-major atoms d lines apart (LBO = 128*d bytes): rows 0-63 = window at
+# shift, rows 64-127 = window at shift + d  (pairs two kernel taps in one MMA)
+for d in (1, 2, 9, 21):
+    line = []
+    for s in range(0, 12, 3):
+        D = torch.zeros(128, 32, device="cuda")
+        _lib.check(_lib.lib().r2d2_debug_shift_probe(_lib.ptr(A), _lib.ptr(B), _lib.ptr(D), s, 2 + d, _lib.stream_ptr()))
+        torch.cuda.synchronize()
+        ref = torch.cat([A[s:s + 64].float().t() @ B.float().t(), A[s + d:s + d + 64].float().t() @ B.float().t()])
+        err = (D - ref).abs().max().item() / ref.abs().max().item()
+        line.append(f"{s}:{'ok' if err < 1e-2 else f'{err:.1e}'}")
+    print(f"paired taps, atom distance {d} lines: " + " ".join(line))
