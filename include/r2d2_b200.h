@@ -193,6 +193,9 @@ int r2d2_debug_gemm2(int ubn, int a_major, int b_major, int M, int N, int K, con
  * SWIZZLE_128B descriptor whose start address is shifted by `shift` rows inside one staged buffer (A bf16 [144][64]);
  * mode 1 also sets the descriptor's base_offset field to shift & 7. */
 int r2d2_debug_shift_probe(const void* A, const void* B, float* D, int shift, int mode, void* stream);
+/* hardware probe: cycles for reps*4 back-to-back tcgen05.mma (M x N x 16, bf16, operands in shared memory) on each of
+ * `ctas` CTAs; mode bit 0 alternates two accumulators, bit 1 reads A MN-major.  cycles[0] <- clock64 delta of CTA 0. */
+int r2d2_debug_mma_rate(int M, int N, int reps, int mode, int ctas, long long* cycles, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K5  clip_grad_norm_(max_norm) + Adam(lr, eps).step()  (worker.py:289,364-365) on the flat

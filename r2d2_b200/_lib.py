@@ -81,6 +81,7 @@ SIGNATURES = {
     "r2d2_set_fast_math": (C.c_int, [C.c_int]),
     "r2d2_debug_gemm2": (C.c_int, [C.c_int] * 6 + [p] * 5 + [C.c_int, p]),
     "r2d2_debug_shift_probe": (C.c_int, [p, p, p, C.c_int, C.c_int, p]),
+    "r2d2_debug_mma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, p, p]),
     "r2d2_clip_adam": (C.c_int, [p, p, p, p, i64, p, p, f32, f32, f32, f32, f32, i64, p, p]),
 }
 

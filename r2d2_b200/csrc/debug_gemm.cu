@@ -182,3 +182,62 @@ extern "C" int r2d2_debug_shift_probe(const void* A, const void* B, float* D, in
     R2D2_LAUNCH_CHECK();
     return R2D2_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// tcgen05.mma issue-rate probe (SS mode, operands in shared memory): one CTA issues `reps` x 4 MMAs of M x N x 16
+// back to back and reports clock64 cycles.  mode bit 0: alternate two accumulators; bit 1: A consumed MN-major.
+namespace r2d2 {
+__global__ void __launch_bounds__(128) mma_rate_kernel(int M, int N, int reps, int mode, long long* __restrict__ cycles) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;
+    uint8_t* smem = smem_raw + pad;
+    const uint32_t sA = raw + pad, sB = sA + 16384;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 16384 + 32768);
+    uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int u = tid; u < (16384 + 32768) / 4; u += 128) reinterpret_cast<uint32_t*>(smem)[u] = 0x3C003C00u;   // small finite bf16
+    if (tid == 0) { mbar_init(smem_u32(bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *slot;
+    if (warp == 0) {
+        const bool leader = elect_one();
+        const bool amn = mode & 2;
+        const uint32_t idesc = ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24)) | (amn ? (1u << 15) : 0u);
+        const uint64_t a0 = amn ? umma_desc_sw128_mn(sA, 8192) : umma_desc_sw128(sA), b0 = umma_desc_sw128(sB);
+        const uint64_t astep = amn ? 128 : 2;
+        const uint32_t acc1 = (mode & 1) ? (uint32_t)N : 0u;
+        long long t0 = clock64();
+        for (int r = 0; r < reps; ++r) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (leader) umma_bf16(tmem + ((k & 1) ? acc1 : 0u), a0 + astep * k, b0 + 2 * k, idesc, 1u);
+        }
+        if (leader) umma_commit(smem_u32(bar));
+        __syncwarp();
+        mbar_wait(smem_u32(bar), 0);
+        long long t1 = clock64();
+        if (leader && blockIdx.x == 0) cycles[0] = t1 - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { tc_fence_after(); asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory"); }
+}
+}  // namespace r2d2
+
+extern "C" int r2d2_debug_mma_rate(int M, int N, int reps, int mode, int ctas, long long* cycles, void* stream) {
+    R2D2_REQUIRE((M == 64 || M == 128) && N >= 16 && N <= 256 && N % 16 == 0 && reps > 0 && ctas > 0 && cycles, "bad arguments");
+    const int smem = 16384 + 32768 + 1024 + 64;
+    static bool configured = false;
+    if (!configured) { R2D2_CUDA_CHECK(cudaFuncSetAttribute(r2d2::mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); configured = true; }
+    r2d2::mma_rate_kernel<<<ctas, 128, smem, r2d2::as_stream(stream)>>>(M, N, reps, mode, cycles);
+    R2D2_LAUNCH_CHECK();
+    return R2D2_OK;
+}

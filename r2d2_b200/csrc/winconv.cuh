@@ -31,7 +31,7 @@ struct WinCfg {
     static constexpr int kBBytes = (B_LO ? 2 : 1) * kTaps * kKB * kBTile;
     static constexpr int kStages = ((227 * 1024 - 2048 - kBBytes) / kAStage) >= 4 ? 4 : ((227 * 1024 - 2048 - kBBytes) / kAStage);
     static constexpr int kSmem = kBBytes + kStages * kAStage + 1024 + 256;
-    static_assert(IC % 64 == 0 && N % 16 == 0 && N <= 128, "window conv shape");
+    static_assert(IC % 64 == 0 && (N == 32 || N == 64 || N == 128), "window conv shape");
     static_assert(kStages >= 2, "not enough shared memory for two window stages");
 };
 
@@ -60,8 +60,12 @@ winconv_kernel(const bf16* __restrict__ Xhi, const bf16* __restrict__ Xlo, long 
         for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&bars[2 * S + a]), 1); mbar_init(smem_u32(&bars[2 * S + 2 + a]), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // Accumulators per tile the MMAs rotate over (summed by the epilogue).  1: rotating buys nothing -- the SS-mode issue
+    // rate is set by the operand reads from shared memory, (M + N) * 32 B / 128 B/clk per instruction (tools/mma_rate.py:
+    // 48 clk for 128 x 64 x 16, with one or two accumulators).  x2 for the tile double buffer.
+    constexpr int NACC = 1;
     if (warp == 8) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * (N < 32 ? 32 : N)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * NACC * (N < 32 ? 32 : N)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     // resident weights (all threads help)
@@ -128,7 +132,14 @@ winconv_kernel(const bf16* __restrict__ Xhi, const bf16* __restrict__ Xlo, long 
 #pragma unroll
             for (int c = 0; c < N; c += 16) {
                 float v[16];
-                tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(a * ACC_COLS + c), v);
+                tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((a * NACC) * ACC_COLS + c), v);
+#pragma unroll
+                for (int j = 1; j < NACC; ++j) {
+                    float w[16];
+                    tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((a * NACC + j) * ACC_COLS + c), w);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] += w[i];
+                }
                 if (p < R) ep.store16(p, c, v, pre);
             }
             tc_fence_before();
@@ -146,7 +157,7 @@ winconv_kernel(const bf16* __restrict__ Xhi, const bf16* __restrict__ Xlo, long 
             const int a = (int)(ti & 1);
             mbar_wait(smem_u32(&bars[2 * S + 2 + a]), ((uint32_t)(ti >> 1) & 1u) ^ 1u);       // accumulator drained
             tc_fence_after();
-            const uint32_t acc = uT + a * ACC_COLS;
+            const uint32_t acc0 = uT + (a * NACC) * ACC_COLS;
             for (int kb = 0; kb < KB; ++kb, ++it) {
                 const int s = (int)(it % S);
                 const uint32_t ph = (uint32_t)(it / S) & 1u;
@@ -161,13 +172,16 @@ winconv_kernel(const bf16* __restrict__ Xhi, const bf16* __restrict__ Xlo, long 
                         const uint64_t a_hi = umma_desc_sw128(st + shift), a_lo = umma_desc_sw128(st + Cfg::kWinBytes + shift);
                         const uint32_t bt = uB + (t * KB + kb) * Cfg::kBTile;
                         const uint64_t b_hi = umma_desc_sw128(bt), b_lo = umma_desc_sw128(bt + TAPS * KB * Cfg::kBTile);
+                        constexpr int TERMS = 1 + (A_LO ? 1 : 0) + (B_LO ? 1 : 0);
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const uint64_t adv = (uint64_t)(k * 2);
-                            uint32_t accum = (kb | t | k) ? 1u : 0u;
-                            if (A_LO) { umma_bf16(acc, a_lo + adv, b_hi + adv, idesc, accum); accum = 1u; }
-                            if (B_LO) { umma_bf16(acc, a_hi + adv, b_lo + adv, idesc, accum); accum = 1u; }
-                            umma_bf16(acc, a_hi + adv, b_hi + adv, idesc, accum);
+                            // running MMA index of the tile: accumulator = index % NACC, the first NACC MMAs overwrite
+                            const int i0 = ((kb * TAPS + t) * 4 + k) * TERMS;
+                            int j = 0;
+                            if (A_LO) { umma_bf16(acc0 + ((i0 + j) % NACC) * ACC_COLS, a_lo + adv, b_hi + adv, idesc, (i0 + j) >= NACC ? 1u : 0u); ++j; }
+                            if (B_LO) { umma_bf16(acc0 + ((i0 + j) % NACC) * ACC_COLS, a_hi + adv, b_lo + adv, idesc, (i0 + j) >= NACC ? 1u : 0u); ++j; }
+                            umma_bf16(acc0 + ((i0 + j) % NACC) * ACC_COLS, a_hi + adv, b_hi + adv, idesc, (i0 + j) >= NACC ? 1u : 0u);
                         }
                     }
                     umma_commit(smem_u32(&bars[S + s]));
@@ -180,7 +194,7 @@ winconv_kernel(const bf16* __restrict__ Xhi, const bf16* __restrict__ Xlo, long 
     __syncthreads();
     if (warp == 8) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * ACC_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * NACC * ACC_COLS) : "memory");
     }
 }
 
@@ -406,37 +420,33 @@ winwgrad_kernel(const bf16* __restrict__ Xhi, const bf16* __restrict__ Xlo, cons
             tc_fence_after();
             const uint32_t st = uS + s * Cfg::kStage;
             if (leader) {
+                // loop order k -> term -> accumulator
+                const uint64_t g_hi = umma_desc_sw128_mn(st + Cfg::kXBytes, 8192), g_lo = umma_desc_sw128_mn(st + Cfg::kXBytes + Cfg::kGPlane, 8192);
+                const uint64_t ones = umma_desc_sw128_mn(sOnes, 2048);
 #pragma unroll
-                for (int a = 0; a < Cfg::kNAcc; ++a) {
-                    const int t1 = tap0 + (Cfg::kPair ? 2 * a : a);             // (ky, kx); tap0 is a multiple of KW or 0
-                    const bool paired = Cfg::kPair && (2 * a + 1 < TG);
-                    const int off1 = (t1 / KW) * GW + (t1 % KW), off2 = ((t1 + 1) / KW) * GW + ((t1 + 1) % KW);
-                    const uint32_t shift = (uint32_t)(off1 - wbase) * 128u;
-                    const uint32_t lbo = paired ? (uint32_t)(off2 - off1) * 128u : (uint32_t)Cfg::kWinBytes;
-                    const uint32_t id = (paired || IC == 128) ? idesc128 : idesc;
-                    const uint64_t x_hi = umma_desc_sw128_mn(st + shift, lbo);
-                    const uint64_t x_lo = umma_desc_sw128_mn(st + ATOMS * Cfg::kWinBytes + shift, lbo);
-                    const uint64_t g_hi = umma_desc_sw128_mn(st + Cfg::kXBytes, 8192), g_lo = umma_desc_sw128_mn(st + Cfg::kXBytes + Cfg::kGPlane, 8192);
-                    const uint32_t acc = uT + a * NMMA;
+                for (int k = 0; k < KP / 16; ++k) {
+                    const uint64_t adv = (uint64_t)(k * 128);                    // 16 lines x 128 B, >> 4
+                    const uint32_t first = (it | k) ? 1u : 0u;
 #pragma unroll
-                    for (int k = 0; k < KP / 16; ++k) {
-                        const uint64_t adv = (uint64_t)(k * 128);                // 16 lines x 128 B, >> 4
-                        uint32_t accum = (it | k) ? 1u : 0u;
-                        if (X_LO) { umma_bf16(acc, x_lo + adv, g_hi + adv, id, accum); accum = 1u; }
-                        if (G_LO && !PACK_G) { umma_bf16(acc, x_hi + adv, g_lo + adv, id, accum); accum = 1u; }
-                        umma_bf16(acc, x_hi + adv, g_hi + adv, id, accum);
-                    }
-                }
-                if (do_bias) {
-                    const uint64_t ones = umma_desc_sw128_mn(sOnes, 2048);
-                    const uint64_t g_hi = umma_desc_sw128_mn(st + Cfg::kXBytes, 8192), g_lo = umma_desc_sw128_mn(st + Cfg::kXBytes + Cfg::kGPlane, 8192);
-                    const uint32_t acc = uT + Cfg::kNAcc * NMMA;
+                    for (int term = 0; term < 3; ++term) {
+                        if (term == 0 && !X_LO) continue;
+                        if (term == 1 && !(G_LO && !PACK_G)) continue;
+                        // accumulate flag: only the first issued term of the first k-step overwrites
+                        const bool first_term = (term == 0) || (term == 1 && !X_LO) || (term == 2 && !X_LO && !(G_LO && !PACK_G));
+                        const uint32_t accum = first_term ? first : 1u;
 #pragma unroll
-                    for (int k = 0; k < KP / 16; ++k) {
-                        const uint64_t adv = (uint64_t)(k * 128);
-                        uint32_t accum = (it | k) ? 1u : 0u;
-                        if (G_LO && !PACK_G) { umma_bf16(acc, ones, g_lo + adv, idesc, accum); accum = 1u; }
-                        umma_bf16(acc, ones, g_hi + adv, idesc, accum);
+                        for (int a = 0; a < Cfg::kNAcc; ++a) {
+                            const int t1 = tap0 + (Cfg::kPair ? 2 * a : a);     // (ky, kx); tap0 is a multiple of KW or 0
+                            const bool paired = Cfg::kPair && (2 * a + 1 < TG);
+                            const int off1 = (t1 / KW) * GW + (t1 % KW), off2 = ((t1 + 1) / KW) * GW + ((t1 + 1) % KW);
+                            const uint32_t shift = (uint32_t)(off1 - wbase) * 128u;
+                            const uint32_t lbo = paired ? (uint32_t)(off2 - off1) * 128u : (uint32_t)Cfg::kWinBytes;
+                            const uint32_t id = (paired || IC == 128) ? idesc128 : idesc;
+                            const uint64_t x = umma_desc_sw128_mn(st + (term == 0 ? ATOMS * Cfg::kWinBytes : 0) + shift, lbo);
+                            umma_bf16(uT + a * NMMA, x + adv, (term == 1 ? g_lo : g_hi) + adv, id, accum);
+                        }
+                        if (do_bias && term != 0)                                // ones^T . G (hi, and lo when it is a separate plane)
+                            umma_bf16(uT + Cfg::kNAcc * NMMA, ones, (term == 1 ? g_lo : g_hi) + adv, idesc, (term == 2 && G_LO && !PACK_G) ? 1u : first);
                     }
                 }
                 umma_commit(smem_u32(&bars[S + s]));
