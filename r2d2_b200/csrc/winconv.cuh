@@ -60,21 +60,24 @@ winconv_kernel(const bf16* __restrict__ Xhi, const bf16* __restrict__ Xlo, long 
         for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&bars[2 * S + a]), 1); mbar_init(smem_u32(&bars[2 * S + 2 + a]), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // Accumulators per tile the MMAs rotate over (summed by the epilogue).  1: rotating buys nothing -- the SS-mode issue
-    // rate is set by the operand reads from shared memory, (M + N) * 32 B / 128 B/clk per instruction (tools/mma_rate.py:
-    // 48 clk for 128 x 64 x 16, with one or two accumulators).  x2 for the tile double buffer.
-    constexpr int NACC = 1;
+    // FOLD (N <= 64, weights split): the lo plane of a weight tile sits right behind its hi plane, so ONE instruction with
+    // N' = 2N computes  a_hi.b_hi | a_hi.b_lo  side by side; the epilogue adds the halves.  An SS-mode instruction costs
+    // max(128 N/256, (128 + N) / 4) clk (tools/mma_rate.py): 64 clk for the folded 128 x 128 x 16 against 2 x 48 for two
+    // 128 x 64 x 16.  Rotating accumulators instead buys nothing (same probe).  x2: tile double buffer.
+    constexpr bool FOLD = B_LO && N <= 64;
+    constexpr int ACC_COLS = (FOLD ? 2 * N : N) < 32 ? 32 : (FOLD ? 2 * N : N);
+    constexpr int BT = (B_LO ? 2 : 1) * Cfg::kBTile;                    // bytes of one (tap, kb) weight tile: [hi][lo]
     if (warp == 8) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * NACC * (N < 32 ? 32 : N)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * ACC_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     // resident weights (all threads help)
     for (int u = tid; u < TAPS * KB * N * 8; u += UM_THREADS) {
         const int j = u & 7, row = (u >> 3) % N, tile = (u >> 3) / N;          // tile = tap*KB + kb
-        const uint32_t dst = (uint32_t)(tile * Cfg::kBTile + (row >> 3) * 1024 + (row & 7) * 128 + ((j ^ (row & 7)) << 4));
+        const uint32_t dst = (uint32_t)(tile * BT + (row >> 3) * 1024 + (row & 7) * 128 + ((j ^ (row & 7)) << 4));
         const size_t src = (size_t)row * KTOT + (size_t)tile * 64 + j * 8;      // k = tap*IC + kb*64 + ...
         cp_async16(sB + dst, Whi + src, true);
-        if (B_LO) cp_async16(sB + TAPS * KB * Cfg::kBTile + dst, Wlo + src, true);
+        if (B_LO) cp_async16(sB + Cfg::kBTile + dst, Wlo + src, true);
     }
     cp_async_commit();
     cp_async_wait<0>();
@@ -83,7 +86,6 @@ winconv_kernel(const bf16* __restrict__ Xhi, const bf16* __restrict__ Xlo, long 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    constexpr int ACC_COLS = N < 32 ? 32 : N;
 
     if (warp < 4) {
         // ------------------------------------------------------------------ producers: window rows -> smem
@@ -132,11 +134,10 @@ winconv_kernel(const bf16* __restrict__ Xhi, const bf16* __restrict__ Xlo, long 
 #pragma unroll
             for (int c = 0; c < N; c += 16) {
                 float v[16];
-                tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((a * NACC) * ACC_COLS + c), v);
-#pragma unroll
-                for (int j = 1; j < NACC; ++j) {
+                tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(a * ACC_COLS + c), v);
+                if (FOLD) {
                     float w[16];
-                    tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((a * NACC + j) * ACC_COLS + c), w);
+                    tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(a * ACC_COLS + N + c), w);
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] += w[i];
                 }
@@ -148,7 +149,7 @@ winconv_kernel(const bf16* __restrict__ Xhi, const bf16* __restrict__ Xlo, long 
         }
     } else {
         // ------------------------------------------------------------------ MMA issue (whole warp, elected lane)
-        constexpr uint32_t idesc = umma_idesc_bf16(N);
+        constexpr uint32_t idesc = umma_idesc_bf16(N), idesc2 = umma_idesc_bf16(2 * N);
         const bool leader = elect_one();
         const uint32_t uA = __shfl_sync(0xffffffffu, sA, 0), uB = __shfl_sync(0xffffffffu, sB, 0);
         const uint32_t uT = __shfl_sync(0xffffffffu, tmem_base, 0);
@@ -157,7 +158,7 @@ winconv_kernel(const bf16* __restrict__ Xhi, const bf16* __restrict__ Xlo, long 
             const int a = (int)(ti & 1);
             mbar_wait(smem_u32(&bars[2 * S + 2 + a]), ((uint32_t)(ti >> 1) & 1u) ^ 1u);       // accumulator drained
             tc_fence_after();
-            const uint32_t acc0 = uT + (a * NACC) * ACC_COLS;
+            const uint32_t acc = uT + a * ACC_COLS;
             for (int kb = 0; kb < KB; ++kb, ++it) {
                 const int s = (int)(it % S);
                 const uint32_t ph = (uint32_t)(it / S) & 1u;
@@ -170,18 +171,20 @@ winconv_kernel(const bf16* __restrict__ Xhi, const bf16* __restrict__ Xlo, long 
                         const int off_t = (t / KW) * GW + (t % KW);
                         const uint32_t shift = (uint32_t)(BACK ? Cfg::kHalo - off_t : off_t) * 128u;  // row-shifted view of the window
                         const uint64_t a_hi = umma_desc_sw128(st + shift), a_lo = umma_desc_sw128(st + Cfg::kWinBytes + shift);
-                        const uint32_t bt = uB + (t * KB + kb) * Cfg::kBTile;
-                        const uint64_t b_hi = umma_desc_sw128(bt), b_lo = umma_desc_sw128(bt + TAPS * KB * Cfg::kBTile);
-                        constexpr int TERMS = 1 + (A_LO ? 1 : 0) + (B_LO ? 1 : 0);
+                        const uint32_t bt = uB + (t * KB + kb) * BT;
+                        const uint64_t b_hi = umma_desc_sw128(bt), b_lo = umma_desc_sw128(bt + Cfg::kBTile);
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const uint64_t adv = (uint64_t)(k * 2);
-                            // running MMA index of the tile: accumulator = index % NACC, the first NACC MMAs overwrite
-                            const int i0 = ((kb * TAPS + t) * 4 + k) * TERMS;
-                            int j = 0;
-                            if (A_LO) { umma_bf16(acc0 + ((i0 + j) % NACC) * ACC_COLS, a_lo + adv, b_hi + adv, idesc, (i0 + j) >= NACC ? 1u : 0u); ++j; }
-                            if (B_LO) { umma_bf16(acc0 + ((i0 + j) % NACC) * ACC_COLS, a_hi + adv, b_lo + adv, idesc, (i0 + j) >= NACC ? 1u : 0u); ++j; }
-                            umma_bf16(acc0 + ((i0 + j) % NACC) * ACC_COLS, a_hi + adv, b_hi + adv, idesc, (i0 + j) >= NACC ? 1u : 0u);
+                            uint32_t accum = (kb | t | k) ? 1u : 0u;
+                            if (FOLD) {
+                                umma_bf16(acc, a_hi + adv, b_hi + adv, idesc2, accum);            // [hi rows | lo rows] of the weight tile: N' = 2N
+                                if (A_LO) umma_bf16(acc, a_lo + adv, b_hi + adv, idesc, 1u);
+                            } else {
+                                if (A_LO) { umma_bf16(acc, a_lo + adv, b_hi + adv, idesc, accum); accum = 1u; }
+                                if (B_LO) { umma_bf16(acc, a_hi + adv, b_lo + adv, idesc, accum); accum = 1u; }
+                                umma_bf16(acc, a_hi + adv, b_hi + adv, idesc, accum);
+                            }
                         }
                     }
                     umma_commit(smem_u32(&bars[S + s]));
@@ -194,7 +197,7 @@ winconv_kernel(const bf16* __restrict__ Xhi, const bf16* __restrict__ Xlo, long 
     __syncthreads();
     if (warp == 8) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * NACC * ACC_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * ACC_COLS) : "memory");
     }
 }
 
