@@ -131,17 +131,29 @@ winconv_kernel(const bf16* __restrict__ Xhi, const bf16* __restrict__ Xlo, long 
             if (p < R) ep.prefetch(p, pre);                                     // requested BEFORE waiting for the accumulator
             mbar_wait(smem_u32(&bars[2 * S + a]), (uint32_t)(ti >> 1) & 1u);
             tc_fence_after();
+            // all TMEM loads of (up to) 64 columns are issued before one wait: their latencies overlap
+            constexpr int GRP = N < 64 ? N : 64;
 #pragma unroll
-            for (int c = 0; c < N; c += 16) {
-                float v[16];
-                tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(a * ACC_COLS + c), v);
-                if (FOLD) {
-                    float w[16];
-                    tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(a * ACC_COLS + N + c), w);
+            for (int c0 = 0; c0 < N; c0 += GRP) {
+                uint32_t rv[GRP / 16][16], rw[FOLD ? GRP / 16 : 1][16];
+                const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(a * ACC_COLS + c0);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] += w[i];
+                for (int g = 0; g < GRP / 16; ++g) {
+                    tmem_ld16_issue(lane_base + g * 16, rv[g]);
+                    if (FOLD) tmem_ld16_issue(lane_base + N + g * 16, rw[g]);
                 }
-                if (p < R) ep.store16(p, c, v, pre);
+#pragma unroll
+                for (int g = 0; g < GRP / 16; ++g) {
+                    tmem_ld_wait(rv[g]);
+                    if (FOLD) tmem_ld_wait(rw[g]);
+                }
+#pragma unroll
+                for (int g = 0; g < GRP / 16; ++g) {
+                    float v[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rv[g][i]) + (FOLD ? __uint_as_float(rw[g][i]) : 0.f);
+                    if (p < R) ep.store16(p, c0 + g * 16, v, pre);
+                }
             }
             tc_fence_before();
             __syncwarp();
