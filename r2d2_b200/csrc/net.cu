@@ -728,8 +728,8 @@ template <int GW, int GH, int OW, int OH>
 struct EpiWinBiasSplit {        // out(split)[row*64 + n] = relu(v + bias[n])
     SplitW out; const float* bias;
     struct Pre {};
-    __device__ __forceinline__ void prefetch(long long, Pre&) const {}
-    __device__ __forceinline__ void store16(long long p, int n, const float (&v)[16], const Pre&) const {
+    __device__ __forceinline__ void prefetch(long long, int, Pre&) const {}
+    __device__ __forceinline__ void store16(long long p, int n, const float (&v)[16], int, const Pre&) const {
         const int r = (int)(p % (GW * GH)), gy = r / GW, gx = r - gy * GW;
         if (gy >= OH || gx >= OW) return;
         const size_t row = (size_t)(p / (GW * GH)) * (OH * OW) + gy * OW + gx;
@@ -742,8 +742,8 @@ struct EpiWinBiasSplit {        // out(split)[row*64 + n] = relu(v + bias[n])
 struct EpiWinConv1Pair {        // 21x21 s2d grid -> 20x20; columns 0-31 online act1, 32-63 target act1
     SplitW out0, out1; const float* bias0; const float* bias1; float scale;
     struct Pre {};
-    __device__ __forceinline__ void prefetch(long long, Pre&) const {}
-    __device__ __forceinline__ void store16(long long p, int n, const float (&v)[16], const Pre&) const {
+    __device__ __forceinline__ void prefetch(long long, int, Pre&) const {}
+    __device__ __forceinline__ void store16(long long p, int n, const float (&v)[16], int, const Pre&) const {
         const int r = (int)(p % 441), gy = r / 21, gx = r - gy * 21;
         if (gy >= 20 || gx >= 20) return;
         const size_t o1 = ((size_t)(p / 441) * 100 + (gy >> 1) * 10 + (gx >> 1)) * 128 + ((gy & 1) * 2 + (gx & 1)) * 32;   // act1: s2d-by-2
@@ -761,18 +761,18 @@ struct EpiWinConv1Pair {        // 21x21 s2d grid -> 20x20; columns 0-31 online 
 // conv2's 10x10 gradient grid (row f*100 + y*10 + x; gy == 9 / gx == 9 stay zero)
 struct EpiWinDgrad3 {
     SplitW out; SplitC act;
-    struct Pre { uint4 m[8]; };
-    __device__ __forceinline__ void prefetch(long long p, Pre& pre) const {
+    struct Pre { uint4 m[8]; };                                             // masks of the row's 64 columns (EW = 4: col0 = 0)
+    __device__ __forceinline__ void prefetch(long long p, int col0, Pre& pre) const {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) pre.m[i] = __ldg(reinterpret_cast<const uint4*>(act.hi + (size_t)p * 64) + i);
+        for (int i = 0; i < 8; ++i) pre.m[i] = __ldg(reinterpret_cast<const uint4*>(act.hi + (size_t)p * 64 + col0) + i);
     }
-    __device__ __forceinline__ void store16(long long p, int n, const float (&v)[16], const Pre& pre) const {
+    __device__ __forceinline__ void store16(long long p, int n, const float (&v)[16], int col0, const Pre& pre) const {
         const int r = (int)(p % 81), y = r / 9, x = r - y * 9;
         const size_t o = ((size_t)(p / 81) * 100 + y * 10 + x) * 64 + n;
         float q[16];
 #pragma unroll
         for (int j = 0; j < 16; j += 8) {
-            const uint4 h = pre.m[(n + j) >> 3];
+            const uint4 h = pre.m[(n - col0 + j) >> 3];
             const uint32_t hw4[4] = {h.x, h.y, h.z, h.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -787,18 +787,18 @@ struct EpiWinDgrad3 {
 // (2Y+ry, 2X+rx); ReLU mask from act1 (same layout); result on conv1's 21x21 gradient grid, 32 channels per pixel
 struct EpiWinDgrad2 {
     SplitW out; SplitC act;
-    struct Pre { uint4 m[16]; };
-    __device__ __forceinline__ void prefetch(long long p, Pre& pre) const {
+    struct Pre { uint4 m[16]; };                                            // masks of the row's 128 columns (EW = 4: col0 = 0)
+    __device__ __forceinline__ void prefetch(long long p, int col0, Pre& pre) const {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) pre.m[i] = __ldg(reinterpret_cast<const uint4*>(act.hi + (size_t)p * 128) + i);
+        for (int i = 0; i < 16; ++i) pre.m[i] = __ldg(reinterpret_cast<const uint4*>(act.hi + (size_t)p * 128 + col0) + i);
     }
-    __device__ __forceinline__ void store16(long long p, int n, const float (&v)[16], const Pre& pre) const {
+    __device__ __forceinline__ void store16(long long p, int n, const float (&v)[16], int col0, const Pre& pre) const {
         const int r = (int)(p % 100), Y = r / 10, X = r - Y * 10, sub = n >> 5, c = n & 31;
         const size_t o = ((size_t)(p / 100) * 441 + (2 * Y + (sub >> 1)) * 21 + 2 * X + (sub & 1)) * 32 + c;
         float q[16];
 #pragma unroll
         for (int j = 0; j < 16; j += 8) {
-            const uint4 h = pre.m[(n + j) >> 3];
+            const uint4 h = pre.m[(n - col0 + j) >> 3];
             const uint32_t hw4[4] = {h.x, h.y, h.z, h.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -860,7 +860,7 @@ static cudaError_t conv1_forward_pair(r2d2_net* n, const float* p0, const float*
     if constexpr (CH == 4) {
         if (g_window_conv) {
             EpiWinConv1Pair we{n->ac[0].act1, n->ac[1].act1, p0 + n->off[P_C1B], p1 + n->off[P_C1B], 1.f / 255.f};
-            return launch_winconv<21, 64, 2, 2, 64, false>(SplitC{n->s2d, nullptr}, (long long)n->NF * 441, SplitC{n->W1both.hi, n->W1both.lo}, we, s);
+            return launch_winconv<21, 64, 2, 2, 64, false, false, 8>(SplitC{n->s2d, nullptr}, (long long)n->NF * 441, SplitC{n->W1both.hi, n->W1both.lo}, we, s);
         }
     }
     SrcConvK<21, 21, 16 * CH, 20, 20, 2, 2, 1, false> a{n->s2d, nullptr, n->NF};

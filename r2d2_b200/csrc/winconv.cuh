@@ -11,8 +11,8 @@
 // (persistent CTAs loop over pixel tiles), so L2 traffic per 128-pixel tile is one window instead of KH*KW tiles
 // plus the weight matrix.
 //
-// Warp roles (288 threads): warps 0-3 producers (cp.async of the window rows), warps 4-7 epilogue (TMEM -> bias/ReLU
-// -> split store), warp 8 MMA issue.  Two TMEM accumulators alternate between consecutive tiles so that the epilogue
+// Warp roles: warps 0-3 producers (cp.async of the window rows), 4 or 8 epilogue warps (TMEM -> bias/ReLU -> split
+// store), one MMA-issue warp.  Two TMEM accumulators alternate between consecutive tiles so that the epilogue
 // of tile i overlaps the MMAs of tile i+1.
 #pragma once
 #include "umma2.cuh"
@@ -35,14 +35,21 @@ struct WinCfg {
     static_assert(kStages >= 2, "not enough shared memory for two window stages");
 };
 
-// Epilogue contract: struct Pre; void prefetch(long long p, Pre&) const; void store16(long long p, int n, const float (&v)[16], const Pre&) const
+// Warp roles: warps 0-3 producers (two were too few: the staging loop became the bottleneck), then EW = 4 or 8 epilogue
+// warps (warp & 3 = TMEM lane quadrant; with 8, the first four take columns [0, N/2) and the others [N/2, N)), then the
+// MMA warp.  EW = 8 is for epilogue-bound layers: conv1 ran 1,170 instructions per tile on ONE epilogue warp per
+// scheduler at IPC 0.44 (ncu) -- 194 -> 156 us with two; the MMA-bound layers are faster with four (measured).
+constexpr int WC_PRODUCERS = 128;
+// Epilogue contract: struct Pre; void prefetch(long long p, int col0, Pre&) const  (operands of columns [col0, col0 + N/2));
+// void store16(long long p, int n, const float (&v)[16], int col0, const Pre&) const
 // where p is the GRID pixel index (frame * GW*GH + gy * GW + gx); the functor drops junk pixels itself.
-template <int GW, int IC, int KH, int KW, int N, bool A_LO, bool B_LO, bool BACK, class Epi>
-__global__ void __launch_bounds__(UM_THREADS, 1)
+template <int GW, int IC, int KH, int KW, int N, bool A_LO, bool B_LO, bool BACK, int EW, class Epi>
+__global__ void __launch_bounds__(WC_PRODUCERS + 32 * EW + 32, 1)
 winconv_kernel(const bf16* __restrict__ Xhi, const bf16* __restrict__ Xlo, long long R /* total grid pixels */,
                const bf16* __restrict__ Whi, const bf16* __restrict__ Wlo /* [N][taps*IC], k = tap*IC + c */, const Epi ep) {
     using Cfg = WinCfg<GW, IC, KH, KW, N, A_LO, B_LO>;
     constexpr int S = Cfg::kStages, KB = Cfg::kKB, TAPS = Cfg::kTaps, KTOT = TAPS * IC;
+    constexpr int WC_THREADS = WC_PRODUCERS + 32 * EW + 32, WC_MMA_WARP = WC_PRODUCERS / 32 + EW;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;
@@ -56,8 +63,8 @@ winconv_kernel(const bf16* __restrict__ Xhi, const bf16* __restrict__ Xlo, long 
     const long long ntiles = (R + 127) / 128;
 
     if (tid == 0) {
-        for (int s = 0; s < S; ++s) { mbar_init(smem_u32(&bars[s]), 4); mbar_init(smem_u32(&bars[S + s]), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&bars[2 * S + a]), 1); mbar_init(smem_u32(&bars[2 * S + 2 + a]), 4); }
+        for (int s = 0; s < S; ++s) { mbar_init(smem_u32(&bars[s]), WC_PRODUCERS / 32); mbar_init(smem_u32(&bars[S + s]), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&bars[2 * S + a]), 1); mbar_init(smem_u32(&bars[2 * S + 2 + a]), EW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // FOLD (N <= 64, weights split): the lo plane of a weight tile sits right behind its hi plane, so ONE instruction with
@@ -67,12 +74,12 @@ winconv_kernel(const bf16* __restrict__ Xhi, const bf16* __restrict__ Xlo, long 
     constexpr bool FOLD = B_LO && N <= 64;
     constexpr int ACC_COLS = (FOLD ? 2 * N : N) < 32 ? 32 : (FOLD ? 2 * N : N);
     constexpr int BT = (B_LO ? 2 : 1) * Cfg::kBTile;                    // bytes of one (tap, kb) weight tile: [hi][lo]
-    if (warp == 8) {
+    if (warp == WC_MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * ACC_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     // resident weights (all threads help)
-    for (int u = tid; u < TAPS * KB * N * 8; u += UM_THREADS) {
+    for (int u = tid; u < TAPS * KB * N * 8; u += WC_THREADS) {
         const int j = u & 7, row = (u >> 3) % N, tile = (u >> 3) / N;          // tile = tap*KB + kb
         const uint32_t dst = (uint32_t)(tile * BT + (row >> 3) * 1024 + (row & 7) * 128 + ((j ^ (row & 7)) << 4));
         const size_t src = (size_t)row * KTOT + (size_t)tile * 64 + j * 8;      // k = tap*IC + kb*64 + ...
@@ -87,7 +94,7 @@ winconv_kernel(const bf16* __restrict__ Xhi, const bf16* __restrict__ Xlo, long 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 4) {
+    if (warp < WC_PRODUCERS / 32) {
         // ------------------------------------------------------------------ producers: window rows -> smem
         long long it = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -97,7 +104,7 @@ winconv_kernel(const bf16* __restrict__ Xhi, const bf16* __restrict__ Xlo, long 
                 const uint32_t ph = (uint32_t)(it / S) & 1u;
                 mbar_wait(smem_u32(&bars[S + s]), ph ^ 1u);
                 const uint32_t st = sA + s * Cfg::kAStage;
-                for (int u = tid; u < Cfg::kWinRows * 8; u += 128) {
+                for (int u = tid; u < Cfg::kWinRows * 8; u += WC_PRODUCERS) {
                     const int row = u >> 3, j = u & 7;
                     const long long p = p0 + row - (BACK ? Cfg::kHalo : 0);
                     const bool ok = p >= 0 && p < R;
@@ -121,38 +128,40 @@ winconv_kernel(const bf16* __restrict__ Xhi, const bf16* __restrict__ Xlo, long 
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bars[(int)((it - 1) % S)]));
         }
-    } else if (warp < 8) {
-        // ------------------------------------------------------------------ epilogue
+    } else if (warp < WC_MMA_WARP) {
+        // ------------------------------------------------------------------ epilogue (8 warps: lane quadrant x column half)
+        constexpr int GRP = N * 4 / EW;                                         // columns per epilogue warp
+        const int q = warp & 3, col0 = ((warp - WC_PRODUCERS / 32) >> 2) * GRP;
         long long ti = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
             const int a = (int)(ti & 1);
-            const long long p = tile * 128 + (warp & 3) * 32 + lane;
+            const long long p = tile * 128 + q * 32 + lane;
             typename Epi::Pre pre;                                              // operands the epilogue needs from global memory (ReLU masks):
-            if (p < R) ep.prefetch(p, pre);                                     // requested BEFORE waiting for the accumulator
+            if (p < R) ep.prefetch(p, col0, pre);                               // requested BEFORE waiting for the accumulator
             mbar_wait(smem_u32(&bars[2 * S + a]), (uint32_t)(ti >> 1) & 1u);
             tc_fence_after();
-            // all TMEM loads of (up to) 64 columns are issued before one wait: their latencies overlap
-            constexpr int GRP = N < 64 ? N : 64;
+            // all TMEM loads of this warp's columns are issued before one wait: their latencies overlap
+            constexpr int SUB = GRP < 64 ? GRP : 64;                            // register budget: 64 columns at a time
 #pragma unroll
-            for (int c0 = 0; c0 < N; c0 += GRP) {
-                uint32_t rv[GRP / 16][16], rw[FOLD ? GRP / 16 : 1][16];
-                const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(a * ACC_COLS + c0);
+            for (int c0 = 0; c0 < GRP; c0 += SUB) {
+                uint32_t rv[SUB / 16][16], rw[FOLD ? SUB / 16 : 1][16];
+                const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * ACC_COLS + col0 + c0);
 #pragma unroll
-                for (int g = 0; g < GRP / 16; ++g) {
+                for (int g = 0; g < SUB / 16; ++g) {
                     tmem_ld16_issue(lane_base + g * 16, rv[g]);
                     if (FOLD) tmem_ld16_issue(lane_base + N + g * 16, rw[g]);
                 }
 #pragma unroll
-                for (int g = 0; g < GRP / 16; ++g) {
+                for (int g = 0; g < SUB / 16; ++g) {
                     tmem_ld_wait(rv[g]);
                     if (FOLD) tmem_ld_wait(rw[g]);
                 }
 #pragma unroll
-                for (int g = 0; g < GRP / 16; ++g) {
+                for (int g = 0; g < SUB / 16; ++g) {
                     float v[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rv[g][i]) + (FOLD ? __uint_as_float(rw[g][i]) : 0.f);
-                    if (p < R) ep.store16(p, c0 + g * 16, v, pre);
+                    if (p < R) ep.store16(p, col0 + c0 + g * 16, v, col0, pre);
                 }
             }
             tc_fence_before();
@@ -207,16 +216,16 @@ winconv_kernel(const bf16* __restrict__ Xhi, const bf16* __restrict__ Xlo, long 
         }
     }
     __syncthreads();
-    if (warp == 8) {
+    if (warp == WC_MMA_WARP) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * ACC_COLS) : "memory");
     }
 }
 
-template <int GW, int IC, int KH, int KW, int N, bool A_LO, bool B_LO, bool BACK, class Epi>
+template <int GW, int IC, int KH, int KW, int N, bool A_LO, bool B_LO, bool BACK, int EW, class Epi>
 static inline cudaError_t launch_winconv_inst(SplitC X, long long R, SplitC W, const Epi& ep, cudaStream_t s) {
     using Cfg = WinCfg<GW, IC, KH, KW, N, A_LO, B_LO>;
-    auto kern = winconv_kernel<GW, IC, KH, KW, N, A_LO, B_LO, BACK, Epi>;
+    auto kern = winconv_kernel<GW, IC, KH, KW, N, A_LO, B_LO, BACK, EW, Epi>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
@@ -225,20 +234,20 @@ static inline cudaError_t launch_winconv_inst(SplitC X, long long R, SplitC W, c
     }
     const long long ntiles = (R + 127) / 128;
     const int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
-    kern<<<grid, UM_THREADS, Cfg::kSmem, s>>>(X.hi, X.lo, R, W.hi, W.lo, ep);
+    kern<<<grid, WC_PRODUCERS + 32 * EW + 32, Cfg::kSmem, s>>>(X.hi, X.lo, R, W.hi, W.lo, ep);
     return cudaGetLastError();
 }
 
 // A_HAS_LO: whether X has a lo plane at all (u8 frames do not).  Precision policy as in launch_umma2 (weights are B).
 // BACK = true is the data gradient: out[q] = sum_taps X[q - off(tap)] . W[tap] with X the (zero-junk) gradient grid.
-template <int GW, int IC, int KH, int KW, int N, bool A_HAS_LO, bool BACK = false, class Epi>
+template <int GW, int IC, int KH, int KW, int N, bool A_HAS_LO, bool BACK = false, int EW = 4, class Epi>
 static inline cudaError_t launch_winconv(SplitC X, long long R, SplitC W, const Epi& ep, cudaStream_t s) {
-    if (g_fast_math == 1) return launch_winconv_inst<GW, IC, KH, KW, N, false, false, BACK>(X, R, W, ep, s);
+    if (g_fast_math == 1) return launch_winconv_inst<GW, IC, KH, KW, N, false, false, BACK, EW>(X, R, W, ep, s);
     if constexpr (!A_HAS_LO) {
-        return launch_winconv_inst<GW, IC, KH, KW, N, false, true, BACK>(X, R, W, ep, s);
+        return launch_winconv_inst<GW, IC, KH, KW, N, false, true, BACK, EW>(X, R, W, ep, s);
     } else {
-        if (g_fast_math == 2) return launch_winconv_inst<GW, IC, KH, KW, N, false, true, BACK>(X, R, W, ep, s);
-        return launch_winconv_inst<GW, IC, KH, KW, N, true, true, BACK>(X, R, W, ep, s);
+        if (g_fast_math == 2) return launch_winconv_inst<GW, IC, KH, KW, N, false, true, BACK, EW>(X, R, W, ep, s);
+        return launch_winconv_inst<GW, IC, KH, KW, N, true, true, BACK, EW>(X, R, W, ep, s);
     }
 }
 
