@@ -56,15 +56,27 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ p, c
     const float coef = fminf(max_norm / (total_norm + 1e-6f), 1.f) * scale;
     if (norm_out && blockIdx.x == 0 && threadIdx.x == 0) *norm_out = total_norm;
     const float step_size = lr / bc1;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const float gi = g[i] * coef;
-        float mi = m[i], vi = v[i];
+    auto adam = [&](float gr, float& pi, float& mi, float& vi) {
+        const float gi = gr * coef;
         mi = mi + (gi - mi) * (1.f - beta1);                 // exp_avg.lerp_(grad, 1-beta1)
         vi = vi * beta2 + (1.f - beta2) * gi * gi;           // exp_avg_sq.mul_(b2).addcmul_(g, g, 1-b2)
         const float denom = sqrtf(vi) / bc2_sqrt + eps;
-        p[i] = p[i] - step_size * (mi / denom);
-        m[i] = mi;
-        v[i] = vi;
+        pi = pi - step_size * (mi / denom);
+    };
+    // 16-byte accesses over the aligned bulk (cudaMalloc'd flat buffers), scalar tail
+    const bool aligned = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                           reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+    const int64_t n4 = aligned ? n / 4 : 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 g4 = reinterpret_cast<const float4*>(g)[i];
+        float4 p4 = reinterpret_cast<float4*>(p)[i], m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i];
+        adam(g4.x, p4.x, m4.x, v4.x); adam(g4.y, p4.y, m4.y, v4.y); adam(g4.z, p4.z, m4.z, v4.z); adam(g4.w, p4.w, m4.w, v4.w);
+        reinterpret_cast<float4*>(p)[i] = p4; reinterpret_cast<float4*>(m)[i] = m4; reinterpret_cast<float4*>(v)[i] = v4;
+    }
+    for (int64_t i = 4 * n4 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float pi = p[i], mi = m[i], vi = v[i];
+        adam(g[i], pi, mi, vi);
+        p[i] = pi; m[i] = mi; v[i] = vi;
     }
 }
 

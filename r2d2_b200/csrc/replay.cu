@@ -93,20 +93,32 @@ __global__ void __launch_bounds__(256) replay_copy_kernel(const uint8_t* __restr
         // item = (c, Y, X): four coalesced 32-bit reads (rows 4Y..4Y+3, pixels 4X..4X+3) -> one 32-byte sector of bf16
         const int items = C * 441;
         const uint32_t* wsrc = reinterpret_cast<const uint32_t*>(blob + lay.obs + (int64_t)(d.start + (t < len ? t : 0)) * frame_bytes);
-        for (int i = threadIdx.x; i < items; i += blockDim.x) {
-            const int X = i % 21, Y = (i / 21) % 21, c = i / 441;
-            uint32_t o[8];
+        // two items per thread and iteration: eight independent loads in flight, one 256-bit store per item
+        for (int i0 = threadIdx.x; i0 < items; i0 += 2 * blockDim.x) {
+            uint32_t w[2][4];
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const uint32_t w = (t < len) ? __ldg(wsrc + (c * 84 + 4 * Y + r) * 21 + X) : 0u;
-                const __nv_bfloat162 p0 = __floats2bfloat162_rn((float)(w & 255u), (float)((w >> 8) & 255u));
-                const __nv_bfloat162 p1 = __floats2bfloat162_rn((float)((w >> 16) & 255u), (float)(w >> 24));
-                o[2 * r] = *reinterpret_cast<const uint32_t*>(&p0);
-                o[2 * r + 1] = *reinterpret_cast<const uint32_t*>(&p1);
+            for (int u = 0; u < 2; ++u) {
+                const int i = i0 + u * blockDim.x;
+                const int X = i % 21, Y = (i / 21) % 21, c = i / 441;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) w[u][r] = (t < len && i < items) ? __ldg(wsrc + (c * 84 + 4 * Y + r) * 21 + X) : 0u;
             }
-            uint4* q = reinterpret_cast<uint4*>(sdst + ((Y * 21 + X) * 16 * C + c * 16));
-            q[0] = make_uint4(o[0], o[1], o[2], o[3]);
-            q[1] = make_uint4(o[4], o[5], o[6], o[7]);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int i = i0 + u * blockDim.x;
+                if (i >= items) break;
+                const int X = i % 21, Y = (i / 21) % 21, c = i / 441;
+                uint32_t o[8];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const __nv_bfloat162 p0 = __floats2bfloat162_rn((float)(w[u][r] & 255u), (float)((w[u][r] >> 8) & 255u));
+                    const __nv_bfloat162 p1 = __floats2bfloat162_rn((float)((w[u][r] >> 16) & 255u), (float)(w[u][r] >> 24));
+                    o[2 * r] = *reinterpret_cast<const uint32_t*>(&p0);
+                    o[2 * r + 1] = *reinterpret_cast<const uint32_t*>(&p1);
+                }
+                asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(sdst + ((Y * 21 + X) * 16 * C + c * 16)), "r"(o[0]),
+                             "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+            }
         }
     }
     if (t < len) {
