@@ -142,23 +142,35 @@ __global__ void pack_kernel(const float* __restrict__ p, const int64_t* __restri
 // u8 frames (C,84,84) -> space-to-depth bf16 [f][Y][X][c*16 + r*4 + q],  pixel (c, 4Y+r, 4X+q).
 // item = (f, c, Y, X): four coalesced 32-bit reads -> one 32-byte sector of bf16
 __global__ void s2d_kernel(const uint8_t* __restrict__ obs, bf16* __restrict__ s2d, int C, int64_t total /* NF*C*441 */) {
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int X = i % 21, Y = (i / 21) % 21, c = (i / 441) % C;
-    const int64_t f = i / (441 * (int64_t)C);
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(obs) + ((f * C + c) * 84 + 4 * Y) * 21 + X;
-    uint32_t o[8];
+    // two items per thread: eight independent loads in flight, one 256-bit store per item
+    const int64_t i0 = (blockIdx.x * (int64_t)blockDim.x) * 2 + threadIdx.x;
+    uint32_t w[2][4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const uint32_t w = __ldg(src + r * 21);
-        const __nv_bfloat162 p0 = __floats2bfloat162_rn((float)(w & 255u), (float)((w >> 8) & 255u));
-        const __nv_bfloat162 p1 = __floats2bfloat162_rn((float)((w >> 16) & 255u), (float)(w >> 24));
-        o[2 * r] = *reinterpret_cast<const uint32_t*>(&p0);
-        o[2 * r + 1] = *reinterpret_cast<const uint32_t*>(&p1);
+    for (int u = 0; u < 2; ++u) {
+        const int64_t i = i0 + u * blockDim.x;
+        if (i >= total) { w[u][0] = w[u][1] = w[u][2] = w[u][3] = 0u; continue; }
+        const int X = i % 21, Y = (i / 21) % 21, c = (i / 441) % C;
+        const int64_t f = i / (441 * (int64_t)C);
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(obs) + ((f * C + c) * 84 + 4 * Y) * 21 + X;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) w[u][r] = __ldg(src + r * 21);
     }
-    uint4* q = reinterpret_cast<uint4*>(s2d + ((f * 21 + Y) * 21 + X) * (16 * C) + c * 16);
-    q[0] = make_uint4(o[0], o[1], o[2], o[3]);
-    q[1] = make_uint4(o[4], o[5], o[6], o[7]);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int64_t i = i0 + u * blockDim.x;
+        if (i >= total) return;
+        const int X = i % 21, Y = (i / 21) % 21, c = (i / 441) % C;
+        const int64_t f = i / (441 * (int64_t)C);
+        uint32_t o[8];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const __nv_bfloat162 p0 = __floats2bfloat162_rn((float)(w[u][r] & 255u), (float)((w[u][r] >> 8) & 255u));
+            const __nv_bfloat162 p1 = __floats2bfloat162_rn((float)((w[u][r] >> 16) & 255u), (float)(w[u][r] >> 24));
+            o[2 * r] = *reinterpret_cast<const uint32_t*>(&p0);
+            o[2 * r + 1] = *reinterpret_cast<const uint32_t*>(&p1);
+        }
+        st_global_256(s2d + ((f * 21 + Y) * 21 + X) * (16 * C) + c * 16, o);
+    }
 }
 
 // row maps + sequence lengths (block 0) + split copy of h0 (other blocks).  model.py:102-111 (shifted rows) and model.py:143.
@@ -890,7 +902,7 @@ static int net_prep(r2d2_net* n, const uint8_t* obs, const float* hidden, const 
                                                              n->len_full, n->len_learn, n->d_rows);
     if (obs) {                                             // obs == NULL: the frames were staged by r2d2_replay_gather_s2d
         const int64_t total = (int64_t)n->NF * n->C * 441;
-        s2d_kernel<<<cdiv(total, 256), 256, 0, s>>>(obs, n->s2d, n->C, total);
+        s2d_kernel<<<cdiv(total, 512), 256, 0, s>>>(obs, n->s2d, n->C, total);
     }
     R2D2_LAUNCH_CHECK();
     return R2D2_OK;
