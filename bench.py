@@ -338,7 +338,7 @@ def run_ours(args):
                     traffic = json.load(f)["bytes"]        # dram bytes of the same launches from the committed ncu pass
             line["roofline"] = {"bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s",
                                 "frac": ach / peaks["tflops"], "traffic": traffic, "peak_source": peaks["source"],
-                                "kernel": "K1+K1b unroll group (forward online+target, BPTT backward): umma2_kernel launches",
+                                "kernel": "K1+K1b unroll group (forward online+target, BPTT backward): winconv/winwgrad/umma2/rec_fwd/rec_bwd launches",
                                 "ms": ms_unroll, "algorithmic_gflop_per_launch": fl / 1e9}
         if world == 1 and not args.no_cpu_baseline:
             val, dt, threads, cores = cpu_learner_rate(C, 2, 8)
