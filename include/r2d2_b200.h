@@ -121,6 +121,10 @@ int r2d2_net_pack(r2d2_net* n, int which, const float* params, void* stream);
 int r2d2_net_forward(r2d2_net* n, int which, const float* params, const uint8_t* obs, const uint8_t* last_action,
                      const float* last_reward, const float* hidden, const uint8_t* burn, const uint8_t* learn,
                      const uint8_t* fwd, float* q_learn_out, float* q_shift_out, void* stream);
+/* (h, c) of slot `which` after time step t of the last r2d2_net_forward*, as f32 [B][2][512] (the layout of `hidden`).
+ * Replaces the state Network.forward returns to an actor (model.py:65-79, worker.py:533-541): on a T = 1 net,
+ * r2d2_net_forward + r2d2_net_state_after is one batched environment step of B actors. */
+int r2d2_net_state_after(r2d2_net* n, int which, int t, float* hidden_out, void* stream);
 /* The three Q tensors of one learner update (worker.py:346,347,352) in one call: both slots are unrolled on the
  * same batch and the two recurrences advance together in shared launches. */
 /* obs may be NULL when the frames were already staged by r2d2_replay_gather_s2d. */

@@ -206,6 +206,16 @@ __global__ void prep_rows_kernel(const uint8_t* __restrict__ burn, const uint8_t
     }
 }
 
+// recurrent state after step t in the [B][2][H] layout of Block.hidden / the `hidden` input (worker.py:198,340)
+__global__ void state_after_kernel(SplitC Hs, const float* __restrict__ Cs, int B, int t, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * H) return;
+    const int b = i / H, j = i - b * H;
+    const size_t o = ((size_t)t * B + b) * H + j;
+    out[(size_t)b * 2 * H + j] = split_load(Hs.hi, Hs.lo, o);
+    out[(size_t)b * 2 * H + H + j] = Cs[o];
+}
+
 // U side columns: one-hot last action, last reward, zero pad  (model.py:92)
 __global__ void side_columns_kernel(SplitW U, const uint8_t* __restrict__ last_action, const float* __restrict__ last_reward,
                                     int B, int T, int A, int KU) {
@@ -1035,6 +1045,17 @@ int r2d2_net_forward(r2d2_net* n, int which, const float* params, const uint8_t*
     if (!rc) rc = net_recurrence(n, which, hidden, s);
     if (!rc) rc = net_heads(n, which, params, q_learn_out, q_shift_out, s);
     return rc;
+}
+
+/* (h, c) of slot `which` after time step t of the last forward, as [B][2][512] -- what an actor carries to its next
+ * step (model.py:65-79 returns it; worker.py:533-541).  With T = 1 nets this turns r2d2_net_forward into a batched
+ * single-step actor inference: hidden_out of one call is the `hidden` argument of the next. */
+int r2d2_net_state_after(r2d2_net* n, int which, int t, float* hidden_out, void* stream) {
+    R2D2_REQUIRE(n && (which == 0 || which == 1) && t >= 0 && t < n->T && hidden_out, "bad arguments");
+    const Acts& ac = n->ac[which];
+    state_after_kernel<<<cdiv((int64_t)n->B * H, 256), 256, 0, as_stream(stream)>>>(ro(ac.Hs), ac.Cs, n->B, t, hidden_out);
+    R2D2_LAUNCH_CHECK();
+    return R2D2_OK;
 }
 
 /* The learner's three Q tensors in one call (worker.py:346,347,352): online and target unrolls on the same

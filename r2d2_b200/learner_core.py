@@ -66,6 +66,66 @@ class FlatParams:
         return {k: (v.detach().clone() if device is None else v.detach().to(device)) for k, v in self.views.items()}
 
 
+class WeightPublisher:
+    """Asynchronous publication of the online parameters to a host-side (shared-memory) model -- the reference's
+    `shared_model.load_state_dict(...)` every 4 updates (worker.py:306-307,372-373), off the learner's critical path:
+    a device snapshot of the flat buffer, one 17 MB device->pinned-host copy of it on a side stream, then a daemon thread waits for it and copies
+    the host views into the shared model.  A publication that is still in flight is skipped, never queued (actors only
+    ever want the newest weights)."""
+
+    def __init__(self, params: FlatParams, shared_model):
+        import queue
+        import threading
+        self.params = params
+        self.shared = shared_model
+        self.stream = torch.cuda.Stream(device=params.flat.device)
+        self.host = torch.empty(params.flat.numel(), dtype=torch.float32).pin_memory()
+        self.snap = torch.empty_like(params.flat)                   # device snapshot: later optimizer steps may run during the D2H
+        self.host_views = {}
+        for i, name in enumerate(PARAM_NAMES):
+            shape = params.shapes[name]
+            n = 1
+            for d in shape:
+                n *= d
+            self.host_views[name] = self.host[params.offsets[i]:params.offsets[i] + n].view(shape)
+        self._done = torch.cuda.Event()
+        self._busy = threading.Event()
+        self._q = queue.Queue()
+        self.published = 0
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+
+    def publish(self) -> bool:
+        """Enqueue one publication of the CURRENT parameters; False if the previous one is still in flight."""
+        if self._busy.is_set():
+            return False
+        self._busy.set()
+        self.snap.copy_(self.params.flat)                                       # 17 MB device copy on the launching stream
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.params.flat.device))
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            self.host.copy_(self.snap, non_blocking=True)
+            self._done.record(self.stream)
+        self._q.put(1)
+        return True
+
+    def _run(self):
+        while True:
+            self._q.get()
+            self._done.synchronize()
+            with torch.no_grad():
+                self.shared.load_state_dict(self.host_views)
+            self.published += 1
+            self._busy.clear()
+
+    def wait(self, timeout: float = 10.0) -> None:
+        import time
+        t0 = time.time()
+        while self._busy.is_set() and time.time() - t0 < timeout:
+            time.sleep(0.001)
+
+
 class BatchStager:
     """Double-buffered host -> device staging of reference-format batches on a copy stream.
 

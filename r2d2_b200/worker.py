@@ -239,13 +239,21 @@ class Learner:
         self._sum_loss = 0.0
         self.env_steps = 0
         self._stager = None
+        self._publisher = None
 
     # -- parameters ---------------------------------------------------------------------------------------------
     def state_dict(self):
         return self.core.online.state_dict()
 
-    def store_weights(self):                                                       # worker.py:306-307
-        self.shared_model.load_state_dict(self.core.online.state_dict(device='cpu'))
+    def store_weights(self, wait: bool = False):                                   # worker.py:306-307
+        """Publish the online weights to the shared (CPU) model the actors read; asynchronous (side-stream D2H into pinned
+        memory + a daemon thread doing the host copy), so the learner loop does not stall on it."""
+        if self._publisher is None:
+            from .learner_core import WeightPublisher
+            self._publisher = WeightPublisher(self.core.online, self.shared_model)
+        self._publisher.publish()
+        if wait:
+            self._publisher.wait()
 
     # -- one update from a reference-format host/device 14-tuple (worker.py:330-369) -----------------------------
     def prefetch(self, data):

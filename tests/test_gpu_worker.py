@@ -118,3 +118,72 @@ def test_learner_run_consumes_reference_tuples(golden_dir, monkeypatch):
         np.testing.assert_array_equal(idxes, g[f"k{k}_out_idxes"])
         np.testing.assert_allclose(prio, g[f"k{k}_out_priorities"], atol=1e-4, rtol=0)
         assert abs(loss - float(g[f"k{k}_out_loss"])) < 2e-5
+
+
+def test_async_weight_publication_reaches_the_shared_model():
+    """store_weights (worker.py:306-307): the shared CPU model the actors read receives the online parameters, via the
+    side-stream D2H + daemon thread, without the learner waiting on it."""
+    import torch
+    from r2d2_b200 import config
+    from r2d2_b200.model import Network
+    from r2d2_b200.worker import Learner
+    from oracle.learner import init_params
+    A, C = 6, 1
+    config.obs_shape = (C, 84, 84)
+    shared = Network(A, obs_shape=(C, 84, 84))
+    shared.load_state_dict(init_params(A, in_channels=C, seed=3))
+    learner = Learner(None, None, shared, save_interval=10 ** 9, device=torch.device("cuda", 0))
+    with torch.no_grad():
+        learner.core.online.flat.mul_(1.5).add_(0.25)                  # pretend an update happened
+    want = {k: v.clone().cpu() for k, v in learner.core.online.views.items()}
+    learner.store_weights(wait=True)
+    assert learner._publisher.published == 1
+    got = shared.state_dict()
+    for k, v in want.items():
+        assert torch.equal(got[k].cpu(), v), k
+    assert learner._publisher.publish() is True                         # idle again
+    learner._publisher.wait()
+
+
+def test_batched_policy_matches_cpu_network_forward():
+    """N actors stepped by ONE GPU forward (actor_inference.BatchedPolicy) == N batch-1 CPU Network.forward calls
+    (model.py:65-79), over several steps with the recurrent state carried on the device."""
+    import numpy as np
+    import torch
+    from r2d2_b200 import config
+    from r2d2_b200.actor_inference import BatchedPolicy
+    from r2d2_b200.model import AgentState, Network
+    from oracle.learner import init_params
+    for C, N, A in [(1, 5, 6), (4, 16, 9)]:
+        config.obs_shape = (C, 84, 84)
+        net = Network(A, obs_shape=(C, 84, 84))
+        net.load_state_dict(init_params(A, in_channels=C, seed=11))
+        net.eval()
+        pol = BatchedPolicy(A, N, obs_shape=(C, 84, 84), device=torch.device("cuda", 0))
+        pol.load_state_dict(net.state_dict())
+        rng = np.random.default_rng(5)
+        states = [AgentState(torch.zeros(1, C, 84, 84), A) for _ in range(N)]
+        hidden = torch.zeros(N, 2, 512)
+        last_action = np.zeros(N, dtype=np.int64)
+        last_reward = np.zeros(N, dtype=np.float32)
+        first = True
+        for step in range(4):
+            obs = rng.integers(0, 256, size=(N, C, 84, 84), dtype=np.uint8)
+            la = np.zeros((N, A), dtype=np.uint8)
+            if not first:
+                la[np.arange(N), last_action] = 1
+            q_gpu, h_gpu = pol.step(obs, la, last_reward, hidden if first else None)
+            q_gpu, h_gpu = q_gpu.cpu(), h_gpu.cpu()
+            for i in range(N):
+                st = states[i]
+                st.obs = torch.from_numpy(obs[i]).unsqueeze(0).float()
+                st.last_action = torch.from_numpy(la[i]).float().unsqueeze(0)
+                st.last_reward = torch.tensor([[last_reward[i]]])
+                with torch.no_grad():
+                    q_cpu, (h, c) = net(st)
+                st.hidden_state = (h, c)
+                assert torch.allclose(q_gpu[i], q_cpu[0], atol=2e-5, rtol=1e-5), (C, step, i, (q_gpu[i] - q_cpu[0]).abs().max())
+                assert torch.allclose(h_gpu[i, 0], h.reshape(-1), atol=2e-5) and torch.allclose(h_gpu[i, 1], c.reshape(-1), atol=2e-5)
+            last_action = q_gpu.argmax(1).numpy()
+            last_reward = rng.normal(size=N).astype(np.float32)
+            first = False
