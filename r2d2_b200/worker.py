@@ -530,3 +530,92 @@ class Actor:
         obs = self.env.reset()
         self.local_buffer.reset(obs)
         return AgentState(torch.from_numpy(obs).unsqueeze(0), self.action_dim)
+
+
+class VectorActor:
+    """N epsilon-greedy environment workers stepped together with ONE batched GPU inference per environment step
+    (actor_inference.BatchedPolicy) instead of N batch-1 CPU forwards (worker.py:526-544) -- SURVEY 8(f) item 3.
+    Ships the same [Block, priorities, episode_reward|None] triples as `Actor`; per-env epsilons as in train.py:28-31.
+
+    The bootstrap value of a block that is cut mid-episode (worker.py:548-552: one extra inference on the new state) is
+    the Q of the NEXT batched step, so it costs nothing: a cut block is finished at the start of the following step."""
+
+    WEIGHT_REFRESH_STEPS = Actor.WEIGHT_REFRESH_STEPS
+
+    def __init__(self, epsilons, model, sample_queue, obs_shape=None, max_episode_steps: int = config.max_episode_steps,
+                 block_length: int = config.block_length, device=None, envs=None):
+        from .actor_inference import BatchedPolicy
+        self.envs = list(envs) if envs is not None else [create_env(noop_start=True) for _ in epsilons]
+        self.N = len(self.envs)
+        assert self.N == len(epsilons)
+        self.action_dim = self.envs[0].action_space.n
+        obs_shape = tuple(obs_shape if obs_shape is not None else config.obs_shape)
+        self.policy = BatchedPolicy(self.action_dim, self.N, obs_shape=obs_shape, device=device)
+        self.shared_model, self.sample_queue = model, sample_queue
+        self.policy.load_state_dict(model.state_dict())
+        self.epsilons = list(epsilons)
+        self.max_episode_steps, self.block_length = max_episode_steps, block_length
+        self.buffers = [LocalBuffer(self.action_dim, block_length=block_length) for _ in range(self.N)]
+        self.obs = np.zeros((self.N,) + obs_shape, dtype=np.uint8)
+        self.last_action = np.zeros((self.N, self.action_dim), dtype=np.uint8)
+        self.last_reward = np.zeros(self.N, dtype=np.float32)
+        self.hidden = torch.zeros(self.N, 2, config.hidden_dim)
+        self.episode_steps = [0] * self.N
+        self.pending_cut = [False] * self.N
+        self.actor_steps = 0
+        for i in range(self.N):
+            self._reset(i)
+
+    def _reset(self, i):
+        obs = self.envs[i].reset()
+        self.buffers[i].reset(obs)
+        self.obs[i] = obs
+        self.last_action[i] = 0
+        self.last_reward[i] = 0.0
+        self.hidden[i] = 0.0
+        self.episode_steps[i] = 0
+        self.pending_cut[i] = False
+
+    def _ship(self, i, triple, episode_over):
+        if not episode_over and self.epsilons[i] > 0.01:
+            triple[2] = None
+        self.sample_queue.put(triple)
+
+    def step(self):
+        """one environment step of every actor"""
+        q, hidden = self.policy.step(self.obs, self.last_action, self.last_reward, self.hidden)
+        q = q.cpu().numpy()
+        self.hidden = hidden.cpu()
+        hid_np = self.hidden.numpy()
+        for i, env in enumerate(self.envs):
+            qi = q[i:i + 1]
+            if self.pending_cut[i]:                                 # bootstrap of the block cut at the previous step
+                self._ship(i, self.buffers[i].finish(qi), False)
+                self.pending_cut[i] = False
+                if self.episode_steps[i] >= self.max_episode_steps:
+                    self._reset(i)
+                    continue                                        # this actor acts again from the fresh episode next step
+            explore = random.random() < self.epsilons[i]
+            action = env.action_space.sample() if explore else int(np.argmax(qi, 1)[0])
+            next_obs, reward, done, _ = env.step(action)
+            self.buffers[i].add(action, reward, next_obs, qi, hid_np[i].copy())
+            self.episode_steps[i] += 1
+            self.obs[i] = next_obs
+            self.last_action[i] = 0
+            self.last_action[i, action] = 1
+            self.last_reward[i] = reward
+            if done:
+                self._ship(i, self.buffers[i].finish(), True)
+                self._reset(i)
+            elif len(self.buffers[i]) == self.block_length or self.episode_steps[i] == self.max_episode_steps:
+                self.pending_cut[i] = True
+        self.actor_steps += 1
+        if self.actor_steps % self.WEIGHT_REFRESH_STEPS == 0:
+            self.update_weights()
+
+    def run(self):
+        while True:
+            self.step()
+
+    def update_weights(self):
+        self.policy.load_state_dict(self.shared_model.state_dict())

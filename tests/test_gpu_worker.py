@@ -187,3 +187,57 @@ def test_batched_policy_matches_cpu_network_forward():
             last_action = q_gpu.argmax(1).numpy()
             last_reward = rng.normal(size=N).astype(np.float32)
             first = False
+
+
+def test_vector_actor_ships_the_same_blocks_as_cpu_actors():
+    """worker.VectorActor (one batched GPU inference per step for N envs) vs N reference-style `Actor`s (batch-1 CPU
+    inference) on action-independent synthetic environments with epsilon 0: identical frames/rewards/segmentation,
+    hidden states and initial priorities within the inference tolerance, including blocks cut mid-episode
+    (worker.py:548-552) whose bootstrap Q comes from the next batched step."""
+    import queue
+    import numpy as np
+    import torch
+    from r2d2_b200 import config
+    from r2d2_b200.environment import SyntheticAtariEnv
+    from r2d2_b200.model import Network
+    from r2d2_b200.worker import Actor, LocalBuffer, VectorActor
+    from oracle.learner import init_params
+    A, C, N, STEPS, BL = 9, 1, 3, 230, 80
+    config.obs_shape = (C, 84, 84)
+    shared = Network(A, obs_shape=(C, 84, 84))
+    shared.load_state_dict(init_params(A, in_channels=C, seed=21))
+    shared.eval()
+    mk = lambda i: SyntheticAtariEnv(A, (C, 84, 84), mean_episode_len=150, seed=300 + i)
+
+    shipped = [[] for _ in range(N)]
+    va = VectorActor([0.0] * N, shared, queue.Queue(), obs_shape=(C, 84, 84), max_episode_steps=10 ** 6, block_length=BL,
+                     device=torch.device("cuda", 0), envs=[mk(i) for i in range(N)])
+    va._ship = lambda i, triple, over: shipped[i].append(triple)
+    for _ in range(STEPS):
+        va.step()
+
+    total_blocks = 0
+    for i in range(N):
+        q = queue.Queue()
+        ac = Actor(0.0, shared, q, obs_shape=(C, 84, 84), max_episode_steps=10 ** 6, block_length=BL)
+        ac.env = mk(i)
+        ac.model.load_state_dict(shared.state_dict())
+        ac.local_buffer = LocalBuffer(A, block_length=BL)
+        ref = []
+        ac._ship = lambda triple, over, ref=ref: ref.append(triple)
+        while ac.actor_steps < STEPS + 200:
+            ac.play_episode()
+        assert len(shipped[i]) >= 2
+        for (blk, prio, ret), (rblk, rprio, rret) in zip(shipped[i], ref):
+            total_blocks += 1
+            assert np.array_equal(blk.obs, rblk.obs) and np.array_equal(blk.last_reward, rblk.last_reward)
+            assert blk.num_sequences == rblk.num_sequences
+            for f in ("burn_in_steps", "learning_steps", "forward_steps", "n_step_reward", "gamma"):
+                assert np.array_equal(getattr(blk, f), getattr(rblk, f)), f
+            assert (blk.action == rblk.action).mean() >= 0.98            # argmax of Q: ties aside identical
+            if np.array_equal(blk.action, rblk.action):
+                assert np.array_equal(blk.last_action, rblk.last_action)
+                assert np.allclose(blk.hidden, rblk.hidden, atol=1e-4)
+                assert np.allclose(prio, rprio, atol=1e-4)
+            assert (ret is None) == (rret is None)
+    assert total_blocks >= 2 * N
