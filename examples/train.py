@@ -23,16 +23,29 @@ def epsilon_for(actor_id: int, num_actors: int, base_eps: float = config.base_ep
     return base_eps ** (1 + (actor_id / (num_actors - 1) if num_actors > 1 else 0) * alpha)
 
 
+def _gpu_actor_main(epsilons, model, sample_queue, obs_shape, block_length, device_index, overrides):
+    """child process (spawned: it needs its own CUDA context): all environments behind one batched GPU inference"""
+    for k, v in overrides.items():
+        setattr(config, k, v)
+    torch.set_num_threads(1)
+    from r2d2_b200.worker import VectorActor
+    VectorActor(epsilons, model, sample_queue, obs_shape=obs_shape, block_length=block_length,
+                device=torch.device("cuda", device_index)).run()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--actors", type=int, default=config.num_actors)
+    ap.add_argument("--gpu-actors", action="store_true",
+                    help="step all actors' environments in ONE process with a batched GPU inference per step "
+                         "(worker.VectorActor) instead of one CPU-inference process per actor")
     for name in ("training_steps", "learning_starts", "buffer_capacity", "batch_size", "log_interval", "block_length",
                  "burn_in_steps", "learning_steps", "forward_steps", "save_interval"):
         ap.add_argument("--" + name.replace("_", "-"), type=int, default=None)
     args = ap.parse_args()
-    for name, val in vars(args).items():
-        if name != "actors" and val is not None:
-            setattr(config, name, val)
+    overrides = {name: val for name, val in vars(args).items() if name not in ("actors", "gpu_actors") and val is not None}
+    for name, val in overrides.items():
+        setattr(config, name, val)
 
     torch.manual_seed(0)
     np.random.seed(0)
@@ -45,16 +58,22 @@ def main():
 
     model = Network(create_env().action_space.n)
     model.share_memory()
-    sample_queues = [mp.Queue() for _ in range(args.actors)]
+    spawn = mp.get_context("spawn")
+    sample_queues = [spawn.Queue()] if args.gpu_actors else [mp.Queue() for _ in range(args.actors)]
     batch_queue, priority_queue = mp.Queue(8), mp.Queue(8)
 
     buffer = ReplayBuffer(sample_queues, batch_queue, priority_queue, buffer_capacity=config.buffer_capacity,
                           batch_size=config.batch_size)
     learner = Learner(batch_queue, priority_queue, model, save_interval=config.save_interval)     # CUDA is initialised here
-    actors = [Actor(epsilon_for(i, args.actors), model, sample_queues[i], block_length=config.block_length)
-              for i in range(args.actors)]
-
-    procs = [mp.Process(target=a.run, daemon=True) for a in actors]
+    if args.gpu_actors:
+        eps = [epsilon_for(i, args.actors) for i in range(args.actors)]
+        procs = [spawn.Process(target=_gpu_actor_main, daemon=True,
+                               args=(eps, model, sample_queues[0], tuple(config.obs_shape), config.block_length,
+                                     torch.cuda.current_device(), overrides))]
+    else:
+        actors = [Actor(epsilon_for(i, args.actors), model, sample_queues[i], block_length=config.block_length)
+                  for i in range(args.actors)]
+        procs = [mp.Process(target=a.run, daemon=True) for a in actors]
     for p in procs:
         p.start()
     buffer_proc = mp.Process(target=buffer.run)
