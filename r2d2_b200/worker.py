@@ -239,7 +239,8 @@ class Learner:
         self._sum_loss = 0.0
         self.env_steps = 0
         self._stager = None
-        self._publisher = None
+        from .learner_core import WeightPublisher                        # eager: pinning 17 MB and starting the thread take
+        self._publisher = WeightPublisher(self.core.online, self.shared_model) if model is not None else None   # milliseconds
 
     # -- parameters ---------------------------------------------------------------------------------------------
     def state_dict(self):
