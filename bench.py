@@ -239,7 +239,7 @@ def run_ours(args):
     learner._start_time = time.time()
     if world > 1:
         r2dist.broadcast_parameters(learner.core)
-        learner.core.grad_hook = r2dist.make_grad_hook()
+        learner.core.grad_hook = r2dist.make_overlapped_grad_hook(learner.core)   # dense-layer all-reduce overlaps the conv backward
 
     # HBM replay shard of this rank: NUM_BLOCKS blocks, tree over 2^20 slots
     replay = DeviceReplay(NUM_BLOCKS * BLOCK_LEN, BLOCK_LEN, BURN, LEARN, FWD, A, (C, 84, 84), 512, 0.9, 0.6, B, device=dev,

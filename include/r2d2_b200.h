@@ -121,6 +121,11 @@ int r2d2_net_pack(r2d2_net* n, int which, const float* params, void* stream);
 int r2d2_net_forward(r2d2_net* n, int which, const float* params, const uint8_t* obs, const uint8_t* last_action,
                      const float* last_reward, const float* hidden, const uint8_t* burn, const uint8_t* learn,
                      const uint8_t* fwd, float* q_learn_out, float* q_shift_out, void* stream);
+/* cuda_event: a cudaEvent_t (or NULL to clear).  r2d2_net_backward records it on its stream once the gradients of
+ * feature.7.weight and every later tensor of the flat layout (FC, LSTM, heads: 98 % of the bytes) are final, before the
+ * conv layers' backward; a data-parallel learner waits on it from a side stream to overlap the gradient all-reduce
+ * (the one exchange step this path adds to worker.py:362-365) with the remaining backward kernels. */
+int r2d2_net_set_dense_grads_event(r2d2_net* n, void* cuda_event);
 /* (h, c) of slot `which` after time step t of the last r2d2_net_forward*, as f32 [B][2][512] (the layout of `hidden`).
  * Replaces the state Network.forward returns to an actor (model.py:65-79, worker.py:533-541): on a T = 1 net,
  * r2d2_net_forward + r2d2_net_state_after is one batched environment step of B actors. */

@@ -79,6 +79,7 @@ SIGNATURES = {
     "r2d2_replay_gather_s2d": (C.c_int, [p, p, p, C.c_int, C.c_int] + [p] * 13),
     "r2d2_net_s2d_buffer": (p, [p]),
     "r2d2_net_state_after": (C.c_int, [p, C.c_int, C.c_int, p, p]),
+    "r2d2_net_set_dense_grads_event": (C.c_int, [p, p]),
     "r2d2_set_fast_math": (C.c_int, [C.c_int]),
     "r2d2_debug_gemm2": (C.c_int, [C.c_int] * 6 + [p] * 5 + [C.c_int, p]),
     "r2d2_debug_shift_probe": (C.c_int, [p, p, p, C.c_int, C.c_int, p]),

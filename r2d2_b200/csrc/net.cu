@@ -75,6 +75,7 @@ struct r2d2_net {
     r2d2::SplitW dhid, DG, dlat, dpre3, dpre2, dpre1g;   // dpre*: pre-activation grads on the layer's INPUT grid (9x9x64, 10x10x64, 21x21x32), junk pixels stay 0
     float *dH, *dhrec, *dcrec, *dout16, *ws, *colws, *rec_partial;
     size_t ws_floats;
+    void* dense_grads_event;         // optional cudaEvent_t recorded in r2d2_net_backward once every non-conv gradient is final
     const float* hidden;             // last forward's stored state (caller-owned, alive until backward)
 };
 
@@ -1047,6 +1048,15 @@ int r2d2_net_forward(r2d2_net* n, int which, const float* params, const uint8_t*
     return rc;
 }
 
+/* cudaEvent_t (or NULL) that r2d2_net_backward records on its stream as soon as the gradients of feature.7.weight and of
+ * every later tensor of the flat layout are final (before the conv layers' backward).  Multi-GPU learners wait on it from
+ * a side stream to overlap the all-reduce of that range with the rest of the backward pass. */
+int r2d2_net_set_dense_grads_event(r2d2_net* n, void* cuda_event) {
+    R2D2_REQUIRE(n, "null handle");
+    n->dense_grads_event = cuda_event;
+    return R2D2_OK;
+}
+
 /* (h, c) of slot `which` after time step t of the last forward, as [B][2][512] -- what an actor carries to its next
  * step (model.py:65-79 returns it; worker.py:533-541).  With T = 1 nets this turns r2d2_net_forward into a batched
  * single-step actor inference: hidden_out of one call is the `hidden` argument of the next. */
@@ -1164,6 +1174,9 @@ int r2d2_net_backward(r2d2_net* n, const float* params, const float* dq, float* 
         SrcMatMN b{ac.act3.hi, ac.act3.lo, FLAT3, NF, FLAT3};
         R2D2_CUDA_CHECK((wgrad2<128, LO_NO_WEIGHT>(a, b, LATENT, FLAT3, NF, 2, R_FC, n, grads, d_off, 1.f, s)));
         R2D2_CUDA_CHECK(colsum_split(ro(n->dlat), NF, LATENT, B_PLAIN, grads, off[P_FCB], 0, A, n->colws, s));
+        // every gradient from feature.7.weight to the end of the flat layout (FC, LSTM, heads: 98 % of the bytes) is final:
+        // a data-parallel caller can start reducing that range while the conv layers' backward still runs
+        if (n->dense_grads_event) R2D2_CUDA_CHECK(cudaEventRecord((cudaEvent_t)n->dense_grads_event, s));
         SrcMatK a2{n->dlat.hi, n->dlat.lo, NF, LATENT, LATENT};
         SrcMatMN b2{pk.Wfcp.hi, pk.Wfcp.lo, FLAT3, LATENT, FLAT3};
         Epi2MaskedToGrid3 e{n->dpre3, ro(ac.act3), NF};

@@ -57,6 +57,37 @@ def make_grad_hook(group=None):
     return hook
 
 
+def make_overlapped_grad_hook(learner, group=None):
+    """Same reduction as make_grad_hook, but the FC/LSTM/head range of the flat gradient (98 % of the bytes) is all-reduced
+    from a side stream as soon as r2d2_net_backward has finished it (r2d2_net_set_dense_grads_event), i.e. WHILE the conv
+    layers' data/weight gradients are still being computed; only the 0.3 MB conv range and the row count are reduced after
+    the backward pass.  NCCL backend only (the collectives are ordered by CUDA streams)."""
+    from . import _lib
+    from .learner_core import PARAM_NAMES
+    dev = learner.grads.flat.device
+    side = torch.cuda.Stream(device=dev)
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(dev))                 # materialise the cudaEvent_t
+    _lib.check(_lib.lib().r2d2_net_set_dense_grads_event(learner._h, ev.cuda_event))
+    dense_off = learner.grads.offsets[PARAM_NAMES.index("feature.7.weight")]
+    rows_g = torch.zeros(1, dtype=torch.float32, device=dev)
+    keep = {"event": ev, "stream": side}                      # owned by the hook: the library only borrows the event
+
+    def hook(lrn):
+        assert lrn is learner and keep
+        flat = lrn.grads.flat
+        with torch.cuda.stream(side):
+            side.wait_event(ev)                               # recorded inside the backward call that just returned
+            w_dense = dist.all_reduce(flat[dense_off:], op=dist.ReduceOp.SUM, group=group, async_op=True)
+        w_conv = dist.all_reduce(flat[:dense_off], op=dist.ReduceOp.SUM, group=group, async_op=True)
+        rows_g.copy_(lrn.rows)
+        dist.all_reduce(rows_g, op=dist.ReduceOp.SUM, group=group)
+        w_dense.wait()
+        w_conv.wait()
+        torch.reciprocal(rows_g, out=lrn.grad_scale)
+    return hook
+
+
 def broadcast_parameters(learner, src: int = 0, group=None) -> None:
     """Make every rank start from rank `src`'s online/target parameters and optimizer state."""
     for t in (learner.online.flat, learner.target.flat, learner.exp_avg, learner.exp_avg_sq):
