@@ -238,26 +238,37 @@ __global__ void head_out_kernel(SplitC hid, size_t row_offset, const float* __re
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= rows_cap) return;
     const size_t base = (row_offset + warp) * 2 * H;
-    float ha[H / 32], hv[H / 32];
-#pragma unroll
-    for (int i = 0; i < H / 32; ++i) {
-        ha[i] = split_load(hid.hi, hid.lo, base + lane + 32 * i);
-        hv[i] = split_load(hid.hi, hid.lo, base + H + lane + 32 * i);
-    }
+    // lane owns 16 consecutive hidden units of each branch: 16-byte loads of the split planes and of the weight rows
+    constexpr int PER = H / 32;                                      // 16
+    float ha[PER], hv[PER];
+    split_load8(hid.hi, hid.lo, base + lane * PER, ha);
+    split_load8(hid.hi, hid.lo, base + lane * PER + 8, ha + 8);
+    split_load8(hid.hi, hid.lo, base + H + lane * PER, hv);
+    split_load8(hid.hi, hid.lo, base + H + lane * PER + 8, hv + 8);
     float adv[16];
     float sum = 0.f;
     for (int a = 0; a < A; ++a) {
         float s = 0.f;
+        const float4* w = reinterpret_cast<const float4*>(Wa2 + a * H + lane * PER);
 #pragma unroll
-        for (int i = 0; i < H / 32; ++i) s = fmaf(ha[i], __ldg(Wa2 + a * H + lane + 32 * i), s);
+        for (int i = 0; i < PER / 4; ++i) {
+            const float4 x = __ldg(w + i);
+            s = fmaf(ha[4 * i], x.x, s); s = fmaf(ha[4 * i + 1], x.y, s); s = fmaf(ha[4 * i + 2], x.z, s); s = fmaf(ha[4 * i + 3], x.w, s);
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         adv[a] = s + ba2[a];
         sum += adv[a];
     }
     float v = 0.f;
+    {
+        const float4* w = reinterpret_cast<const float4*>(Wv2 + lane * PER);
 #pragma unroll
-    for (int i = 0; i < H / 32; ++i) v = fmaf(hv[i], __ldg(Wv2 + lane + 32 * i), v);
+        for (int i = 0; i < PER / 4; ++i) {
+            const float4 x = __ldg(w + i);
+            v = fmaf(hv[4 * i], x.x, v); v = fmaf(hv[4 * i + 1], x.y, v); v = fmaf(hv[4 * i + 2], x.z, v); v = fmaf(hv[4 * i + 3], x.w, v);
+        }
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     v += bv2[0];
