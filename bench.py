@@ -260,11 +260,17 @@ def run_ours(args):
     from collections import deque
     staged = deque([learner.prefetch(tuples[0])])
 
+    tickets = deque()
+
     def step_e2e(i):
         # every step moves one full batch host -> device inside the timed region; like the reference's prefetch thread
-        # (worker.py:309-316) the copy of batch i+1 is issued before batch i is trained on, on a copy stream
+        # (worker.py:309-316) the copy of batch i+1 is issued before batch i is trained on, on a copy stream.  As in
+        # Learner.run, update i is launched before the host reads update i-1's priorities/loss (one D2H read per step):
+        # enqueueing the 60 launches of an update overlaps the previous update instead of idling the GPU.
         staged.append(learner.prefetch(tuples[(i + 1) % len(tuples)]))
-        learner.update_from_batch(staged.popleft())            # update + priorities/loss D2H, host synchronises on the result
+        tickets.append(learner.enqueue_update(staged.popleft()))
+        if len(tickets) > 1:
+            learner.collect(tickets.popleft())                  # priorities + loss of the previous update, host-synchronised
 
     def timed(fn, steps, warmup):
         for w in range(warmup):

@@ -234,8 +234,7 @@ class Learner:
         self.shared_model = model
         self.game_name = game_name
         self.replay = None                     # DeviceReplay, created on the first forwarded block
-        self._prio_host = torch.empty(self.batch_size, dtype=torch.float32).pin_memory()
-        self._loss_host = torch.empty(2, dtype=torch.float32).pin_memory()
+        self._results = None                   # two pinned result slots (priorities, loss) for enqueue_update/collect
         self._sum_loss = 0.0
         self.env_steps = 0
         self._stager = None
@@ -271,21 +270,41 @@ class Learner:
                                          forward=forward_steps, is_weights=is_weights))
         return ("staged", handle, idxes, old_ptr, env_steps)
 
-    def update_from_batch(self, data):
+    def enqueue_update(self, data):
+        """Launch one update on a (staged or raw) 14-tuple WITHOUT waiting for it: the priorities / loss are copied into a
+        pinned result slot behind the kernels and an event marks them ready.  Returns a ticket for collect().  Two tickets
+        may be outstanding, so a caller can launch update i+1 before it reads update i's results -- the ~0.4 ms the host
+        needs to enqueue an update's 60 launches then overlaps the previous update instead of idling the GPU."""
         if not (isinstance(data, tuple) and len(data) == 5 and isinstance(data[0], str) and data[0] == "staged"):
             data = self.prefetch(data)
         _, handle, idxes, old_ptr, env_steps = data
         b = self._stager.acquire(handle)
         self.core.update(b)
         self._stager.release(handle)
-        self._prio_host.copy_(self.core.prio, non_blocking=True)                   # worker.py:357: priorities back to the host
-        self._loss_host[0:1].copy_(self.core.loss_sum, non_blocking=True)
-        self._loss_host[1:2].copy_(self.core.rows.float(), non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        loss = float(self._loss_host[0] / self._loss_host[1])
+        if self._results is None:
+            self._results = [dict(prio=torch.empty(self.batch_size, dtype=torch.float32).pin_memory(),
+                                  loss=torch.empty(2, dtype=torch.float32).pin_memory(), ready=torch.cuda.Event())
+                             for _ in range(2)]
+            self._result_i = 0
+        slot = self._results[self._result_i]
+        self._result_i ^= 1
+        slot["prio"].copy_(self.core.prio, non_blocking=True)                      # worker.py:357: priorities back to the host
+        slot["loss"][0:1].copy_(self.core.loss_sum, non_blocking=True)
+        slot["loss"][1:2].copy_(self.core.rows.float(), non_blocking=True)
+        slot["ready"].record(torch.cuda.current_stream(self.device))
         self.env_steps = env_steps
         self._after_update()
-        return idxes, self._prio_host.numpy().copy(), old_ptr, loss
+        return (slot, idxes, old_ptr)
+
+    def collect(self, ticket):
+        """(idxes, priorities f32[B], old_ptr, loss) of an enqueued update -- the message worker.py:369 puts on the queue."""
+        slot, idxes, old_ptr = ticket
+        slot["ready"].synchronize()
+        loss = float(slot["loss"][0] / slot["loss"][1])
+        return idxes, slot["prio"].numpy().copy(), old_ptr, loss
+
+    def update_from_batch(self, data):
+        return self.collect(self.enqueue_update(data))
 
     # -- one update from the HBM-resident replay (sample -> update -> priority update, no host round trip) --------
     def update_from_replay(self):
@@ -329,6 +348,7 @@ class Learner:
         self._start_time = time.time()
         last_stats = time.time()
         loss_acc = torch.zeros(1, device=self.device)
+        pending = None
         while self.num_updates < config.training_steps:
             worked = False
             while self.batched_data:
@@ -340,7 +360,10 @@ class Learner:
                     staged = data if (isinstance(data[0], str) and data[0] == "staged") else self.prefetch(data)
                     if self.batched_data and not isinstance(self.batched_data[0][0], str):
                         self.batched_data[0] = self.prefetch(self.batched_data[0])   # H2D of the next batch overlaps this update
-                    self.priority_queue.put(self.update_from_batch(staged))
+                    ticket = self.enqueue_update(staged)                           # launched; the PREVIOUS update's results go out
+                    if pending is not None:                                        # while this one runs (the reference's queue of
+                        self.priority_queue.put(self.collect(pending))             # prefetched batches lags priorities further)
+                    pending = ticket
                     break
             if self.replay is not None and len(self.replay) >= config.learning_starts:
                 self.update_from_replay()
@@ -352,7 +375,12 @@ class Learner:
                     loss_acc.zero_()
                     last_stats = time.time()
             if not worked:
+                if pending is not None:
+                    self.priority_queue.put(self.collect(pending))
+                    pending = None
                 time.sleep(0.01)
+        if pending is not None:
+            self.priority_queue.put(self.collect(pending))
 
     @staticmethod
     def value_rescale(value, eps=1e-3):                                            # worker.py:383-385
