@@ -6,10 +6,15 @@
 //
 // Data layout in HBM.  "split" = two bf16 tensors (hi, lo) of identical layout with x = hi + lo
 // (|err| <= 2^-17 |x|): every tensor that feeds a contraction is stored that way by its producer so
-// the GEMM kernels (umma2.cuh) stage operands with pure 16-byte cp.async copies.
+// the GEMM (umma2.cuh) and window-convolution (winconv.cuh) kernels stage operands with pure 16-byte cp.async copies.
 //   s2d   [NF][21][21][16C] bf16   frames after space-to-depth by 4 (u8 pixels are exact in bf16):
 //                                   conv1 (8x8 stride 4) becomes a 2x2 stride-1 conv over 16C channels
-//   act1  [NF*400][32]  act2 [NF*81][64]  act3 [NF][3136]     split, NHWC, post-ReLU  (f = b*T + t)
+//   act1  [NF*100][128] split      conv1 output (20x20x32) stored space-to-depth by 2: row (f, y/2, x/2), column
+//                                   (y&1, x&1, c) -- conv2 (4x4 stride 2) becomes a 2x2 stride-1 conv over 128 channels
+//   act2  [NF*81][64]  act3 [NF][3136]     split, NHWC, post-ReLU  (f = b*T + t)
+//   dpre3 [NF*81][64]  dpre2 [NF*100][64]  dpre1g [NF*441][32]   split pre-activation gradients, each on its layer's
+//                                   INPUT grid (9x9, 10x10, 21x21); grid pixels that are no conv output stay zero, so the
+//                                   conv layers' data / weight / bias gradients run as window convolutions (winconv.cuh)
 //   U     [T*B][KU] split   LSTM input rows, time-major: latent(512) | one-hot last action(A) |
 //                            last reward | zero pad, KU = roundup(512+A+1, 16)
 //   XP    [T*B][4H] fp32    input projection incl. both biases, gate-interleaved (col = 4*j + gate)
@@ -556,23 +561,6 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __rest
             for (int y = 0; y < 8; ++y) t += s[y][tx];
             part[(size_t)p * N + col] = t;
         }
-    }
-}
-// row sums of a split [R][N] tensor (bias gradient of the channel-major dpre1T): partial[p][r]
-__global__ void rowsum_partial_kernel(SplitC S, int R, long long N, long long chunk, float* __restrict__ part) {
-    __shared__ float s[8];
-    const int r = blockIdx.x, p = blockIdx.y;
-    const long long c0 = p * chunk, c1 = min(N, c0 + chunk);
-    float acc = 0.f;
-    for (long long c = c0 + threadIdx.x; c < c1; c += blockDim.x) acc += split_load(S.hi, S.lo, (size_t)(r * N + c));
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float t = 0.f;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s[w];
-        part[(size_t)p * R + r] = t;
     }
 }
 enum BiasKind { B_PLAIN, B_LSTM, B_H0, B_H2 };

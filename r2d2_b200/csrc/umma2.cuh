@@ -139,12 +139,6 @@ template <int ROWS, class Src> struct OperandStager {
     }
 };
 
-// N operand sets selected by blockIdx.x (gridDim.x == N, one N tile): e.g. the 4 output-parity classes of a
-// stride-2 dgrad in ONE launch, so that CTAs writing interleaved elements of the same sectors run together.
-template <class F, int N> struct Multi { F f[N]; };
-template <class F, int N> __device__ __forceinline__ const F& sel_z(const Multi<F, N>& f, int) { return f.f[blockIdx.x]; }
-template <class F> struct IsMulti { static constexpr bool value = false; };
-template <class F, int N> struct IsMulti<Multi<F, N>> { static constexpr bool value = true; };
 
 template <int BN, bool WANT_A_LO, bool WANT_B_LO, class ASrcT, class BSrcT, class EpiT>
 __global__ void __launch_bounds__(UM_THREADS, R2D2_STAGE_BUDGET_KB <= 104 ? 2 : 1)
@@ -169,7 +163,7 @@ umma2_kernel(const ASrcT a_, const BSrcT b_, const EpiT ep_, int K, int k_per_sp
     const ASrc& as = sel_z(a_, z);
     const BSrc& bs = sel_z(b_, z);
     const auto& ep = sel_z(ep_, z);
-    const int m0 = blockIdx.y * UM_BM, n0 = IsMulti<EpiT>::value ? 0 : blockIdx.x * BN;
+    const int m0 = blockIdx.y * UM_BM, n0 = blockIdx.x * BN;
     const int k_begin = IsPair<ASrcT>::value ? 0 : z * k_per_split;
     const int k_end = IsPair<ASrcT>::value ? K : min(K, k_begin + k_per_split);
     const int nk = (k_end - k_begin + UM_BK - 1) / UM_BK;
@@ -329,16 +323,6 @@ static inline cudaError_t launch_umma2(const ASrc& a, const BSrc& b, const Epi& 
     return launch_umma2_grid<BN, POL>(a, b, ep, grid, K, k_per_split, s);
 }
 
-// one launch over CNT operand sets selected by blockIdx.x (N <= BN: a single N tile per set)
-template <int BN, int CNT, int POL = LO_STRICT, class ASrc, class BSrc, class Epi>
-static inline cudaError_t launch_umma2_multi(const ASrc& a, const Multi<BSrc, CNT>& b, const Multi<Epi, CNT>& ep, int M, int K,
-                                             cudaStream_t s) {
-    if (M <= 0) return cudaSuccess;
-    const int k_per_split = (K + UM_BK - 1) / UM_BK * UM_BK;
-    dim3 grid(CNT, (M + UM_BM - 1) / UM_BM, 1);
-    return launch_umma2_grid<BN, POL>(a, b, ep, grid, K, k_per_split, s);
-}
-
 // ---------------------------------------------------------------------------------------------
 // chunk sources.  chunk(row, k) returns the element offset (into both planes) of the 8-element
 // chunk starting at (row, k) -- along k for K-major sources, along rows for MN-major sources --
@@ -418,27 +402,6 @@ struct SrcConvMN {   // MN-major (wgrad): row = kernel index (8 consecutive chan
         return (c >= 0 && p >= 0) ? c + p : -1;
     }
 };
-// dgrad gather (stride-1, or one parity class of a stride-2 conv): m = (frame, y', x') on GH x GW,
-// k = (jy, jx, c_out), value = dout[f][y'-jy][x'-jx][c_out]
-template <int GH, int GW, int OH, int OW, int OC, int JH, int JW>
-struct SrcDgradK {
-    static constexpr bool kMN = false, kHasLo = true;
-    struct RCtx { long long base; int y, x; };
-    const bf16* hi; const bf16* lo; int nframes;
-    __device__ __forceinline__ RCtx rctx(int m) const {
-        if (m >= nframes * GH * GW) return RCtx{-1, 0, 0};
-        const int f = m / (GH * GW), p = m - f * (GH * GW), y = p / GW, x = p - y * GW;
-        return RCtx{(((long long)f * OH + y) * OW + x) * OC, y, x};
-    }
-    __device__ __forceinline__ long long chunk(const RCtx& c, int k) const {
-        if (c.base < 0 || k >= JH * JW * OC) return -1;
-        const int tap = k / OC, ch = k - tap * OC, jy = tap / JW, jx = tap - jy * JW;
-        const int oy = c.y - jy, ox = c.x - jx;
-        if (oy < 0 || oy >= OH || ox < 0 || ox >= OW) return -1;
-        return c.base - (long long)(jy * OW + jx) * OC + ch;
-    }
-};
-
 // ---------------------------------------------------------------------------------------------
 // epilogues (16 consecutive columns of one row)
 // ---------------------------------------------------------------------------------------------
@@ -482,26 +445,6 @@ struct Epi2BiasSplit {        // out(split)[m*ld+n] = act(v*scale + bias[n]);  N
                 r[i] = kRelu ? fmaxf(x, 0.f) : x;
             }
             split_store8(out.hi, out.lo, (size_t)(m * ld + n + j), r);
-        }
-    }
-};
-struct Epi2MaskedSplit {      // dgrad: out = (act > 0) ? v : 0, act laid out like out
-    SplitW out; SplitC act; int M, N; long long ld;
-    __device__ __forceinline__ void store16(int m, int n, const float (&v)[16], int) const {
-        if (m >= M) return;
-#pragma unroll
-        for (int j = 0; j < 16; j += 8) {
-            if (n + j >= N) break;
-            const size_t o = (size_t)(m * ld + n + j);
-            const uint4 h = *reinterpret_cast<const uint4*>(act.hi + o);     // sign of hi decides (hi == 0 <=> x == 0 after ReLU)
-            const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
-            float r[8];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                r[2 * i] = (hw[i] & 0x7FFFu) ? v[j + 2 * i] : 0.f;
-                r[2 * i + 1] = (hw[i] & 0x7FFF0000u) ? v[j + 2 * i + 1] : 0.f;
-            }
-            split_store8(out.hi, out.lo, o, r);
         }
     }
 };
