@@ -36,4 +36,18 @@ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b)
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: remember per device (bit = ordinal) that a kernel
+// has been opted in, so a process that drives several GPUs configures each of them once.
+template <class Kernel>
+static inline cudaError_t ensure_dynamic_smem(Kernel kern, int bytes, unsigned long long* configured_devices) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (*configured_devices & bit) return cudaSuccess;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) *configured_devices |= bit;
+    return e;
+}
+
 }  // namespace r2d2

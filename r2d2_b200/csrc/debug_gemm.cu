@@ -235,8 +235,8 @@ __global__ void __launch_bounds__(128) mma_rate_kernel(int M, int N, int reps, i
 extern "C" int r2d2_debug_mma_rate(int M, int N, int reps, int mode, int ctas, long long* cycles, void* stream) {
     R2D2_REQUIRE((M == 64 || M == 128) && N >= 16 && N <= 256 && N % 16 == 0 && reps > 0 && ctas > 0 && cycles, "bad arguments");
     const int smem = 16384 + 32768 + 1024 + 64;
-    static bool configured = false;
-    if (!configured) { R2D2_CUDA_CHECK(cudaFuncSetAttribute(r2d2::mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); configured = true; }
+    static unsigned long long configured = 0;
+    R2D2_CUDA_CHECK(r2d2::ensure_dynamic_smem(r2d2::mma_rate_kernel, smem, &configured));
     r2d2::mma_rate_kernel<<<ctas, 128, smem, r2d2::as_stream(stream)>>>(M, N, reps, mode, cycles);
     R2D2_LAUNCH_CHECK();
     return R2D2_OK;

@@ -263,11 +263,10 @@ __global__ void __launch_bounds__(UM_THREADS, 1) rec_fwd_kernel(const RecFwdPara
 }
 
 static inline cudaError_t launch_rec_fwd(const RecFwdParams& P, int nets, cudaStream_t s) {
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(rec_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, REC_SMEM);
+    static unsigned long long configured = 0;                       // bit per device ordinal
+    {
+        cudaError_t e = ensure_dynamic_smem(rec_fwd_kernel, REC_SMEM, &configured);
         if (e != cudaSuccess) return e;
-        configured = true;
     }
     cudaError_t e = cudaMemsetAsync(P.bar, 0, 2 * REC_KB * sizeof(unsigned int), s);
     if (e != cudaSuccess) return e;
@@ -496,11 +495,10 @@ __global__ void __launch_bounds__(UM_THREADS, 1) rec_bwd_kernel(const RecBwdPara
 }
 
 static inline cudaError_t launch_rec_bwd(const RecBwdParams& P, cudaStream_t s) {
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(rec_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RB_SMEM);
+    static unsigned long long configured = 0;                       // bit per device ordinal
+    {
+        cudaError_t e = ensure_dynamic_smem(rec_bwd_kernel, RB_SMEM, &configured);
         if (e != cudaSuccess) return e;
-        configured = true;
     }
     cudaError_t e = cudaMemsetAsync(P.flags, 0, 24 * sizeof(unsigned int), s);
     if (e != cudaSuccess) return e;

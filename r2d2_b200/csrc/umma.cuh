@@ -330,11 +330,10 @@ static inline cudaError_t launch_umma(const ALoad& al, const BLoad& bl, const Ep
     if (M <= 0 || N <= 0) return cudaSuccess;
     using Cfg = UmmaCfg<BN, TERMS>;
     auto kern = umma_gemm_kernel<BN, TERMS, ALoad, BLoad, Epi>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+    static unsigned long long configured = 0;                       // bit per device ordinal
+    {
+        cudaError_t e = ensure_dynamic_smem(kern, Cfg::kSmem, &configured);
         if (e != cudaSuccess) return e;
-        configured = true;
     }
     int k_per_split = (K + splits - 1) / splits;
     k_per_split = (k_per_split + UM_BK - 1) / UM_BK * UM_BK;

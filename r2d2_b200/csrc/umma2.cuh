@@ -296,11 +296,10 @@ static inline cudaError_t launch_umma2_inst(const ASrc& a, const BSrc& b, const 
     using B0 = typename std::remove_cv<typename std::remove_reference<decltype(sel_z(b, 0))>::type>::type;
     using Cfg = Umma2Cfg<BN, A0::kHasLo && AL, B0::kHasLo && BL>;
     auto kern = umma2_kernel<BN, AL, BL, ASrc, BSrc, Epi>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+    static unsigned long long configured = 0;                       // bit per device ordinal
+    {
+        cudaError_t e = ensure_dynamic_smem(kern, Cfg::kSmem, &configured);
         if (e != cudaSuccess) return e;
-        configured = true;
     }
     kern<<<grid, UM_THREADS, Cfg::kSmem, s>>>(a, b, ep, K, k_per_split);
     return cudaGetLastError();

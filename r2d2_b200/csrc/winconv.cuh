@@ -226,11 +226,10 @@ template <int GW, int IC, int KH, int KW, int N, bool A_LO, bool B_LO, bool BACK
 static inline cudaError_t launch_winconv_inst(SplitC X, long long R, SplitC W, const Epi& ep, cudaStream_t s) {
     using Cfg = WinCfg<GW, IC, KH, KW, N, A_LO, B_LO>;
     auto kern = winconv_kernel<GW, IC, KH, KW, N, A_LO, B_LO, BACK, EW, Epi>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+    static unsigned long long configured = 0;                       // bit per device ordinal
+    {
+        cudaError_t e = ensure_dynamic_smem(kern, Cfg::kSmem, &configured);
         if (e != cudaSuccess) return e;
-        configured = true;
     }
     const long long ntiles = (R + 127) / 128;
     const int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
@@ -490,11 +489,10 @@ template <int GW, int IC, int KH, int KW, int TG, int NO, bool X_LO, bool G_LO, 
 static inline cudaError_t launch_winwgrad_inst(SplitC X, SplitC G, long long R, int chunk, float* ws, float* bias_ws, cudaStream_t s) {
     using Cfg = WinWgradCfg<GW, IC, KH, KW, TG, NO, X_LO, G_LO, PACK_G, KP, BIAS>;
     auto kern = winwgrad_kernel<GW, IC, KH, KW, TG, NO, X_LO, G_LO, PACK_G, KP, BIAS>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+    static unsigned long long configured = 0;                       // bit per device ordinal
+    {
+        cudaError_t e = ensure_dynamic_smem(kern, Cfg::kSmem, &configured);
         if (e != cudaSuccess) return e;
-        configured = true;
     }
     const int nchunks = (int)((R + chunk - 1) / chunk);
     kern<<<dim3(nchunks, Cfg::kGroups), UM_THREADS, Cfg::kSmem, s>>>(X.hi, X.lo, G.hi, G.lo, R, chunk, ws, bias_ws);
