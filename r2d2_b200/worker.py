@@ -572,14 +572,18 @@ class VectorActor:
     WEIGHT_REFRESH_STEPS = Actor.WEIGHT_REFRESH_STEPS
 
     def __init__(self, epsilons, model, sample_queue, obs_shape=None, max_episode_steps: int = config.max_episode_steps,
-                 block_length: int = config.block_length, device=None, envs=None):
-        from .actor_inference import BatchedPolicy
+                 block_length: int = config.block_length, device=None, envs=None, policy=None):
+        """policy: object with load_state_dict(sd) and step(obs, last_action, last_reward, hidden) -> (q, next_hidden);
+        defaults to the CUDA BatchedPolicy (tests inject a stub to exercise the block logic without a GPU)."""
         self.envs = list(envs) if envs is not None else [create_env(noop_start=True) for _ in epsilons]
         self.N = len(self.envs)
         assert self.N == len(epsilons)
         self.action_dim = self.envs[0].action_space.n
         obs_shape = tuple(obs_shape if obs_shape is not None else config.obs_shape)
-        self.policy = BatchedPolicy(self.action_dim, self.N, obs_shape=obs_shape, device=device)
+        if policy is None:
+            from .actor_inference import BatchedPolicy
+            policy = BatchedPolicy(self.action_dim, self.N, obs_shape=obs_shape, device=device)
+        self.policy = policy
         self.shared_model, self.sample_queue = model, sample_queue
         self.policy.load_state_dict(model.state_dict())
         self.epsilons = list(epsilons)

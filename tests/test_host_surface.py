@@ -96,3 +96,65 @@ def test_local_buffer_blocks_match_reference_golden(golden_dir):
         np.testing.assert_array_equal(np.stack([blk.burn_in_steps, blk.learning_steps, blk.forward_steps]), g[f"blk{i}_steps"])
         np.testing.assert_array_equal(prio, g[f"blk{i}_prio"])
         assert (-1.0 if ep is None else ep) == float(g[f"blk{i}_ep"])
+
+
+def test_vector_actor_block_logic_with_stub_policy():
+    """Host logic of worker.VectorActor (block cuts, bootstrap from the next step, resets, shipping) against N
+    reference-style CPU `Actor`s, with the batched policy replaced by a stub that loops the CPU Network -- the GPU parity of
+    the real policy is tests/test_gpu_worker.py."""
+    import queue
+    import numpy as np
+    import torch
+    from r2d2_b200 import config
+    from r2d2_b200.environment import SyntheticAtariEnv
+    from r2d2_b200.model import AgentState, Network
+    from r2d2_b200.worker import Actor, LocalBuffer, VectorActor
+    from oracle.learner import init_params
+    A, C, N, STEPS, BL = 9, 1, 2, 130, 80            # A = 9: `Actor` builds its own env (MsPacman action count)
+    config.obs_shape = (C, 84, 84)
+    torch.set_num_threads(4)
+    shared = Network(A, obs_shape=(C, 84, 84))
+    shared.load_state_dict(init_params(A, in_channels=C, seed=9))
+    shared.eval()
+    mk = lambda i: SyntheticAtariEnv(A, (C, 84, 84), mean_episode_len=100, seed=700 + i)
+
+    class StubPolicy:
+        def load_state_dict(self, sd):
+            pass
+
+        def step(self, obs, last_action, last_reward, hidden):
+            qs, hs = [], []
+            for i in range(N):
+                st = AgentState(torch.from_numpy(obs[i]).unsqueeze(0).float(), A)
+                st.last_action = torch.from_numpy(last_action[i]).float().unsqueeze(0)
+                st.last_reward = torch.tensor([[float(last_reward[i])]])
+                h = hidden[i]
+                st.hidden_state = (h[0].reshape(1, -1).contiguous(), h[1].reshape(1, -1).contiguous())
+                with torch.no_grad():
+                    q, (hn, cn) = shared(st)
+                qs.append(q[0])
+                hs.append(torch.stack([hn.reshape(-1), cn.reshape(-1)]))
+            return torch.stack(qs), torch.stack(hs)
+
+    shipped = [[] for _ in range(N)]
+    va = VectorActor([0.0] * N, shared, queue.Queue(), obs_shape=(C, 84, 84), max_episode_steps=10 ** 6, block_length=BL,
+                     envs=[mk(i) for i in range(N)], policy=StubPolicy())
+    va._ship = lambda i, triple, over: shipped[i].append(triple)
+    for _ in range(STEPS):
+        va.step()
+    for i in range(N):
+        ac = Actor(0.0, shared, queue.Queue(), obs_shape=(C, 84, 84), max_episode_steps=10 ** 6, block_length=BL)
+        ac.env = mk(i)
+        ac.model.load_state_dict(shared.state_dict())
+        ac.local_buffer = LocalBuffer(A, block_length=BL)
+        ref = []
+        ac._ship = lambda triple, over, ref=ref: ref.append(triple)
+        while ac.actor_steps < STEPS + 60:
+            ac.play_episode()
+        assert len(shipped[i]) >= 1
+        for (blk, prio, ret), (rblk, rprio, rret) in zip(shipped[i], ref):
+            for f in ("obs", "last_action", "last_reward", "action", "n_step_reward", "gamma", "burn_in_steps",
+                      "learning_steps", "forward_steps"):
+                assert np.array_equal(getattr(blk, f), getattr(rblk, f)), f
+            assert np.allclose(blk.hidden, rblk.hidden, atol=1e-6) and np.allclose(prio, rprio, atol=1e-5)
+            assert (ret is None) == (rret is None)
