@@ -27,6 +27,7 @@
 // The online pass is run ONCE for b+l+f steps: the reference's pass 1 (calculate_q_, no grad) and
 // pass 3 (calculate_q, grad) share every hidden state up to b+l-1, so Q at the learning positions
 // and at the n-step-shifted positions are two row gathers of the same unroll.
+#include <algorithm>
 #include <map>
 
 #include "recurrence.cuh"
@@ -79,7 +80,7 @@ struct r2d2_net {
     // backward scratch
     r2d2::SplitW dhid, DG, dlat, dpre3, dpre2, dpre1g;   // dpre*: pre-activation grads on the layer's INPUT grid (9x9x64, 10x10x64, 21x21x32), junk pixels stay 0
     float *dH, *dhrec, *dcrec, *dout16, *ws, *colws, *rec_partial;
-    size_t ws_floats;
+    size_t ws_floats, colws_floats;
     void* dense_grads_event;         // optional cudaEvent_t recorded in r2d2_net_backward once every non-conv gradient is final
     const float* hidden;             // last forward's stored state (caller-owned, alive until backward)
 };
@@ -696,8 +697,18 @@ int r2d2_net_create(int B, int T, int C, int A, int Lmax, int max_forward, r2d2_
     rc |= alloc_s(&n->dpre3, NF * 5184); rc |= alloc_s(&n->dpre2, NF * 6400); rc |= alloc_s(&n->dpre1g, NF * 14112);   // gradient grids (see struct)
     rc |= alloc_f(&n->dH, TB * H); rc |= alloc_f(&n->dhrec, (size_t)kRecSplits * B * H); rc |= alloc_f(&n->dcrec, (size_t)B * H);
     rc |= alloc_f(&n->dout16, (size_t)n->Rmax * 16); rc |= alloc_f(&n->rec_partial, 2ull * 8 * 64 * H);
-    n->ws_floats = 32ull << 20;                        // 128 MB split-K workspace
-    rc |= alloc_f(&n->ws, n->ws_floats); rc |= alloc_f(&n->colws, (size_t)kColP * 4096);
+    {   // split-K / chunk-partial workspace: 128 MB covers the batch-64 shapes; the conv weight-gradient kernels write one
+        // partial per <= 4096-pixel chunk, so very large batches need more (sized here, checked again at launch)
+        auto chunks = [](size_t rows, size_t chunk) { return (rows + chunk - 1) / chunk; };
+        size_t need = 32ull << 20;
+        need = std::max(need, chunks(NF * 441, 4096) * 256 * 32);        // conv1: [taps*64][32] per chunk
+        need = std::max(need, chunks(NF * 100, 3712) * 512 * 64);        // conv2
+        need = std::max(need, chunks(NF * 81, 3072) * 576 * 64);         // conv3
+        need = std::max(need, chunks(NF * 441, 4096) * 32 * 64 * (size_t)C);   // conv1 at C = 1 (im2col split-K)
+        n->ws_floats = need;
+        n->colws_floats = std::max((size_t)kColP * 4096, chunks(NF * 100, 3712) * 64 + chunks(NF * 441, 4096) * 64);
+    }
+    rc |= alloc_f(&n->ws, n->ws_floats); rc |= alloc_f(&n->colws, n->colws_floats);
     if (rc) return rc;
     R2D2_CUDA_CHECK(cudaDeviceSynchronize());
     *out = n;
@@ -838,7 +849,7 @@ static cudaError_t winwgrad(SplitC X, SplitC G, long long R, int chunk, int kind
                             const int64_t* d_off, float scale, cudaStream_t s) {
     constexpr int M = KH * KW * IC;
     const int splits = (int)((R + chunk - 1) / chunk);
-    if ((size_t)splits * M * NO > net->ws_floats || (size_t)splits * NO > (size_t)kColP * 4096 || chunk % KP) return cudaErrorInvalidValue;
+    if ((size_t)splits * M * NO > net->ws_floats || (size_t)splits * NO > net->colws_floats || chunk % KP) return cudaErrorInvalidValue;
     cudaError_t e = launch_winwgrad<GW, IC, KH, KW, TG, NO, X_HAS_LO, KP, true>(X, G, R, chunk, net->ws, net->colws, s);
     if (e != cudaSuccess) return e;
     reduce_route_kernel<8><<<cdiv((int64_t)M * NO, 32), 256, 0, s>>>(net->ws, splits, M, NO, kind, grads, d_off, net->A, net->C, scale);
