@@ -141,6 +141,10 @@ int r2d2_net_forward_pair(r2d2_net* n, const float* params_online, const float* 
  * included) and the encoder.  dq [rows_capacity][A]; grads: flat buffer in the parameter layout,
  * fully overwritten (alignment gaps are left untouched and must be zero). */
 int r2d2_net_backward(r2d2_net* n, const float* params, const float* dq, float* grads, void* stream);
+/* GEMM scheduling of the plain-matrix contractions of K1/K1b (FC layer, LSTM input projection, their data and weight
+ * gradients): 1 (default) = CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles, TMA-fed: csrc/umma3.cuh); 0 = single-CTA
+ * 128 x 128 tiles fed by cp.async (csrc/umma2.cuh).  Same results to fp32 rounding.  Returns the previous value. */
+int r2d2_set_pair_gemm(int on);
 /* Recurrence scheduling: 1 (default) = all T LSTM steps of both networks in ONE persistent cooperative kernel
  * (W_hh slices resident in shared memory, per-network step barriers) for B <= 64; 0 = one launch per step. */
 int r2d2_set_persistent_recurrence(int on);
@@ -197,6 +201,10 @@ int r2d2_set_fast_math(int mode);
 /* Test entry for the v2 kernel: operands as bf16 hi/lo planes; major 1 = [K][rows] storage (MN-major descriptors). */
 int r2d2_debug_gemm2(int ubn, int a_major, int b_major, int M, int N, int K, const void* a_hi, const void* a_lo,
                      const void* b_hi, const void* b_lo, float* C, int splits, void* stream);
+
+/* Test entry for the v3 kernel (CTA pairs with cta_group::2 MMAs, TMA-fed): same operand convention; C [splits][M][N] must be zeroed. */
+int r2d2_debug_gemm3(int a_major, int b_major, int M, int N, int K, const void* a_hi, const void* a_lo, const void* b_hi,
+                     const void* b_lo, float* C, int splits, void* stream);
 
 /* Hardware probe (tests/tools only): D[128][32] = A[shift .. shift+128)[64] . B[32][64]^T with a K-major
  * SWIZZLE_128B descriptor whose start address is shifted by `shift` rows inside one staged buffer (A bf16 [144][64]);

@@ -1,7 +1,7 @@
 // Test entry point: plain-matrix instances of the gather-GEMM on either backend, so the tcgen05
 // path (descriptors, swizzle, pipeline, TMEM epilogue) can be validated against the fp32 FFMA path
 // and a host reference independently of the network.
-#include "umma2.cuh"
+#include "umma3.cuh"
 
 namespace r2d2 {
 enum GemmBackend { GEMM_FFMA = 0, GEMM_UMMA_BF16X3 = 1, GEMM_UMMA_BF16 = 2 };
@@ -82,6 +82,24 @@ int r2d2_debug_gemm2(int ubn, int a_major, int b_major, int M, int N, int K, con
 #undef R2D2_DBG2
 #undef R2D2_DBG2_ALL
 #undef R2D2_DBG2_MNB
+    R2D2_CUDA_CHECK(e);
+    return R2D2_OK;
+}
+
+/* v3 test entry (CTA-pair, TMA-fed kernel of umma3.cuh): operands as bf16 hi/lo planes, majors as in r2d2_debug_gemm2.
+ * C fp32 [splits][M][N], zero-initialised by the caller (fewer partials may be written than requested). */
+int r2d2_debug_gemm3(int a_major, int b_major, int M, int N, int K, const void* a_hi, const void* a_lo, const void* b_hi,
+                     const void* b_lo, float* C, int splits, void* stream) {
+    R2D2_REQUIRE(a_hi && a_lo && b_hi && b_lo && C && M > 0 && N > 0 && K > 0 && splits >= 1, "bad arguments");
+    R2D2_REQUIRE(N % 8 == 0 && (a_major == 0 ? K % 8 == 0 : M % 8 == 0) && (b_major == 0 ? K % 8 == 0 : N % 8 == 0), "alignment");
+    cudaStream_t s = as_stream(stream);
+    const Mat3 A{(const bf16*)a_hi, (const bf16*)a_lo, M, K, a_major ? M : K}, B{(const bf16*)b_hi, (const bf16*)b_lo, N, K, b_major ? N : K};
+    Epi2Partial ep{C, M, N};
+    cudaError_t e;
+    if (!a_major && !b_major) e = launch_umma3<false, false>(A, B, ep, M, N, K, splits, s);
+    else if (a_major && !b_major) e = launch_umma3<true, false>(A, B, ep, M, N, K, splits, s);
+    else if (!a_major && b_major) e = launch_umma3<false, true>(A, B, ep, M, N, K, splits, s);
+    else e = launch_umma3<true, true>(A, B, ep, M, N, K, splits, s);
     R2D2_CUDA_CHECK(e);
     return R2D2_OK;
 }

@@ -31,6 +31,7 @@
 #include <map>
 
 #include "recurrence.cuh"
+#include "umma3.cuh"
 #include "winconv.cuh"
 
 namespace r2d2 {
@@ -622,6 +623,24 @@ static cudaError_t wgrad2(const AS& a, const BS& b, int M, int N, int K, int spl
     return cudaGetLastError();
 }
 
+// plain-matrix weight gradient on CTA pairs (umma3.cuh): both operands MN-major ([K][rows] storage)
+template <int POL = LO_STRICT>
+static cudaError_t wgrad3(const Mat3& a, const Mat3& b, int M, int N, int K, int splits, int kind, r2d2_net* net, float* grads,
+                          const int64_t* d_off, float scale, cudaStream_t s) {
+    splits = umma3_effective_splits(K, splits);
+    if ((size_t)splits * M * N > net->ws_floats) return cudaErrorInvalidValue;
+    Epi2Partial ep{net->ws, M, N};
+    cudaError_t e = launch_umma3<true, true, POL>(a, b, ep, M, N, K, splits, s);
+    if (e != cudaSuccess) return e;
+    const int64_t tot = (int64_t)M * N;
+    reduce_route_kernel<1><<<cdiv(tot, 256), 256, 0, s>>>(net->ws, splits, M, N, kind, grads, d_off, net->A, net->C, scale);
+    return cudaGetLastError();
+}
+
+// 1 (default): the plain-matrix GEMMs (FC, input projection, their data / weight gradients) run on CTA pairs with TMA
+// (umma3.cuh); 0: single-CTA cp.async kernels (umma2.cuh).  R2D2_PAIR_GEMM=0 in the environment or r2d2_set_pair_gemm.
+int g_pair_gemm = [] { const char* e = getenv("R2D2_PAIR_GEMM"); return (e && e[0] == '0') ? 0 : 1; }();
+
 int g_persistent_recurrence = 1;
 unsigned long long* g_rec_trace = nullptr;   // debug: device buffer [T][8] of step timestamps (r2d2_debug_rec_trace)     // 0: per-step launches (also the path for B > 64)
 
@@ -961,12 +980,19 @@ static int net_encode(r2d2_net* n, int which, const FwdArgs& fa, cudaStream_t s,
         SrcMatK a{ac.act3.hi, ac.act3.lo, NF, FLAT3, FLAT3};
         SrcMatK b{pk.Wfcp.hi, pk.Wfcp.lo, LATENT, FLAT3, FLAT3};
         Epi2Latent e{ac.U, params + off[P_FCB], B, T, KU};
+        if (g_pair_gemm)
+            R2D2_CUDA_CHECK((launch_umma3<false, false, LO_WEIGHT_B>(Mat3{ac.act3.hi, ac.act3.lo, NF, FLAT3, FLAT3}, Mat3{pk.Wfcp.hi, pk.Wfcp.lo, LATENT, FLAT3, FLAT3},
+                                                                    e, NF, LATENT, FLAT3, 1, s)));
+        else
         R2D2_CUDA_CHECK((launch_umma2<128, LO_WEIGHT_B>(a, b, e, NF, LATENT, FLAT3, 1, s)));
     }
     {   // LSTM input projection for all steps at once (hoisted out of the recurrence)
         SrcMatK a{ac.U.hi, ac.U.lo, T * B, KU, KU};
         SrcMatK b{pk.Wih_p.hi, pk.Wih_p.lo, G4, KU, KU};
         Epi2F32 e{ac.XP, pk.bias_p, T * B, G4, G4, 1.f};
+        if (g_pair_gemm)
+            R2D2_CUDA_CHECK((launch_umma3<false, false>(Mat3{ac.U.hi, ac.U.lo, T * B, KU, KU}, Mat3{pk.Wih_p.hi, pk.Wih_p.lo, G4, KU, KU}, e, T * B, G4, KU, 1, s)));
+        else
         R2D2_CUDA_CHECK((launch_umma2<128>(a, b, e, T * B, G4, KU, 1, s)));
     }
     return R2D2_OK;
@@ -1167,21 +1193,35 @@ int r2d2_net_backward(r2d2_net* n, const float* params, const float* dq, float* 
     {   // recurrent weight gradients over all (t,b) rows
         SrcMatMN a{n->DG.hi, n->DG.lo, G4, (int)TB, G4};
         SrcMatMN bh{ac.HsX.hi, ac.HsX.lo, H, (int)TB, H};        // row (t,b) of HsX is the state BEFORE step t
-        R2D2_CUDA_CHECK((wgrad2<128>(a, bh, G4, H, (int)TB, 2, R_WHH, n, grads, d_off, 1.f, s)));
         SrcMatMN bu{ac.U.hi, ac.U.lo, KU, (int)TB, KU};
+        if (g_pair_gemm) {       // 8 x 2 (x 3) pair tiles: split K so that one wave of 74 pairs is (nearly) full, K <= 4096 per partial
+            const Mat3 dg{n->DG.hi, n->DG.lo, G4, (int)TB, G4};
+            const int sp = std::max(4, cdiv((long long)TB, 4096));
+            R2D2_CUDA_CHECK((wgrad3<>(dg, Mat3{ac.HsX.hi, ac.HsX.lo, H, (int)TB, H}, G4, H, (int)TB, sp, R_WHH, n, grads, d_off, 1.f, s)));
+            R2D2_CUDA_CHECK((wgrad3<>(dg, Mat3{ac.U.hi, ac.U.lo, KU, (int)TB, KU}, G4, KU, (int)TB, std::max(3, cdiv((long long)TB, 4096)), R_WIH, n, grads, d_off, 1.f, s)));
+        } else {
+        R2D2_CUDA_CHECK((wgrad2<128>(a, bh, G4, H, (int)TB, 2, R_WHH, n, grads, d_off, 1.f, s)));
         R2D2_CUDA_CHECK((wgrad2<128>(a, bu, G4, KU, (int)TB, 2, R_WIH, n, grads, d_off, 1.f, s)));
+        }
         R2D2_CUDA_CHECK(colsum_split(ro(n->DG), (int)TB, G4, B_LSTM, grads, off[P_BIH], off[P_BHH], A, n->colws, s));
     }
     {   // d latent (ReLU-masked), frame-major
         SrcMatK a{n->DG.hi, n->DG.lo, (int)TB, G4, G4};
         SrcMatMN b{pk.Wih_p.hi, pk.Wih_p.lo, LATENT, G4, KU};
         Epi2DLatent e{n->dlat, ro(ac.U), B, T, KU};
+        if (g_pair_gemm)
+            R2D2_CUDA_CHECK((launch_umma3<false, true>(Mat3{n->DG.hi, n->DG.lo, (int)TB, G4, G4}, Mat3{pk.Wih_p.hi, pk.Wih_p.lo, LATENT, G4, KU}, e, (int)TB, LATENT, G4, 1, s)));
+        else
         R2D2_CUDA_CHECK((launch_umma2<128>(a, b, e, (int)TB, LATENT, G4, 1, s)));
     }
     // ---- encoder backward
     {
         SrcMatMN a{n->dlat.hi, n->dlat.lo, LATENT, NF, LATENT};
         SrcMatMN b{ac.act3.hi, ac.act3.lo, FLAT3, NF, FLAT3};
+        if (g_pair_gemm)     // 2 x 13 pair tiles x 2 splits: one wave
+            R2D2_CUDA_CHECK((wgrad3<LO_NO_WEIGHT>(Mat3{n->dlat.hi, n->dlat.lo, LATENT, NF, LATENT}, Mat3{ac.act3.hi, ac.act3.lo, FLAT3, NF, FLAT3}, LATENT, FLAT3, NF,
+                                                  std::max(2, cdiv(NF, 4096)), R_FC, n, grads, d_off, 1.f, s)));
+        else
         R2D2_CUDA_CHECK((wgrad2<128, LO_NO_WEIGHT>(a, b, LATENT, FLAT3, NF, 2, R_FC, n, grads, d_off, 1.f, s)));
         R2D2_CUDA_CHECK(colsum_split(ro(n->dlat), NF, LATENT, B_PLAIN, grads, off[P_FCB], 0, A, n->colws, s));
         // every gradient from feature.7.weight to the end of the flat layout (FC, LSTM, heads: 98 % of the bytes) is final:
@@ -1190,6 +1230,10 @@ int r2d2_net_backward(r2d2_net* n, const float* params, const float* dq, float* 
         SrcMatK a2{n->dlat.hi, n->dlat.lo, NF, LATENT, LATENT};
         SrcMatMN b2{pk.Wfcp.hi, pk.Wfcp.lo, FLAT3, LATENT, FLAT3};
         Epi2MaskedToGrid3 e{n->dpre3, ro(ac.act3), NF};
+        if (g_pair_gemm)
+            R2D2_CUDA_CHECK((launch_umma3<false, true, LO_WEIGHT_B>(Mat3{n->dlat.hi, n->dlat.lo, NF, LATENT, LATENT}, Mat3{pk.Wfcp.hi, pk.Wfcp.lo, FLAT3, LATENT, FLAT3}, e,
+                                                                   NF, FLAT3, LATENT, 1, s)));
+        else
         R2D2_CUDA_CHECK((launch_umma2<128, LO_WEIGHT_B>(a2, b2, e, NF, FLAT3, LATENT, 1, s)));
     }
     // The conv layers run as window convolutions (winconv.cuh): gradients live on each layer's input grid.
@@ -1209,6 +1253,13 @@ int r2d2_net_backward(r2d2_net* n, const float* params, const float* dq, float* 
         R2D2_CUDA_CHECK(n->C == 1 ? conv1_wgrad<1>(n, grads, s) : conv1_wgrad<4>(n, grads, s));
     }
     return R2D2_OK;
+}
+
+/* 1 (default): plain-matrix GEMMs of K1/K1b on CTA pairs (cta_group::2, TMA); 0: single-CTA cp.async kernels.  Returns the previous value. */
+int r2d2_set_pair_gemm(int on) {
+    int prev = g_pair_gemm;
+    g_pair_gemm = on ? 1 : 0;
+    return prev;
 }
 
 /* 1 (default): the T-step recurrence runs as one persistent cooperative kernel when B <= 64; 0: per-step launches. */
