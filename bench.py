@@ -90,84 +90,135 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def synthetic_blocks(n: int, C: int, seed: int):
-    """n full actor blocks (400 steps, 10 sequences) with SURVEY 8(d) distributions, built directly as arrays."""
-    from r2d2_b200.worker import Block
-    rng = np.random.default_rng(seed)
-    frames = BURN + BLOCK_LEN + 1
-    out = []
-    for _ in range(n):
-        la = np.zeros((frames, A), dtype=bool)
-        la[np.arange(frames), rng.integers(0, A, frames)] = True
-        spb = BLOCK_LEN // LEARN
-        fwd = np.full(spb, FWD, dtype=np.uint8)
-        fwd[-1] = 1
-        blk = Block(obs=rng.integers(0, 256, size=(frames, C, 84, 84), dtype=np.uint8), last_action=la,
-                    last_reward=rng.integers(0, 2, frames).astype(np.float32),
-                    action=rng.integers(0, A, BLOCK_LEN).astype(np.uint8),
-                    n_step_reward=rng.uniform(0, 3, BLOCK_LEN).astype(np.float32),
-                    gamma=np.full(BLOCK_LEN, 0.997 ** FWD, dtype=np.float32),
-                    hidden=(0.1 * rng.standard_normal((spb, 2, 512))).astype(np.float32), num_sequences=spb,
-                    burn_in_steps=np.full(spb, BURN, dtype=np.uint8), learning_steps=np.full(spb, LEARN, dtype=np.uint8),
-                    forward_steps=fwd)
-        out.append((blk, rng.uniform(0.1, 1.0, spb).astype(np.float32)))
-    return out
+# ----------------------------------------------------------------------------------------------- reference arm
+def reference_available() -> bool:
+    from oracle import ref_harness
+    return ref_harness.available()
 
 
-def host_tuple(C: int, seed: int, pinned: bool):
-    """A reference-format 14-tuple (worker.py:219-238) of host tensors."""
-    from oracle import synth            # input generator only (seeded NumPy), no compute
-    d = synth.synthetic_batch(B, A, BURN, LEARN, FWD, channels=C, seed=seed)
-    t = lambda a: (torch.from_numpy(a).pin_memory() if pinned else torch.from_numpy(a))
-    return (t(d["obs"]), t(d["last_action"]), t(d["last_reward"]), t(np.ascontiguousarray(d["hidden"])),
-            t(d["action"]).unsqueeze(1), t(d["n_step_reward"]), t(d["gamma"]), t(d["burn_in"]), t(d["learning"]), t(d["forward"]),
-            d["idxes"], t(d["is_weights"]), 0, np.int32(0)), d
+def reference_learner_times(C: int, steps: int, warmup: int, sample_B: int, device: str, thread_candidates=None, tail_1thread: int = 0):
+    """Drive the UNMODIFIED reference `worker.Learner.run` (worker.py:318-381) on synthetic 14-tuples of `sample_B`
+    sequences and return per-update wall times (interval between successive priority_queue.put calls, worker.py:369).
+
+    The reference is imported from baseline/_ref (a verbatim copy of the upstream files made by __graft_entry__.build();
+    /root/reference in the build container) with the two shims of SURVEY.md 8c (gym stub, int64 accumulator).  C = 4 needs
+    conv1 with 4 input channels, which model.py:40 hard-codes to 1: that one layer is re-instantiated (labelled).
+    device 'cpu' relies on CUDA being hidden from the process (worker.py:283 picks cuda whenever it is visible)."""
+    import queue
+
+    from oracle import ref_harness
+    from r2d2_b200.synthetic import reference_tuple, synthetic_batch
+    ref = ref_harness.load()
+    assert (device == "cuda") == torch.cuda.is_available(), "reference device is chosen by torch.cuda.is_available() (worker.py:283)"
+    torch.manual_seed(0)
+    net = ref.model.Network(A, obs_shape=(C, 84, 84))
+    if C != 1:
+        net.feature[0] = torch.nn.Conv2d(C, 32, 8, 4)
+    total = warmup + steps + tail_1thread
+    ref.config.training_steps = total
+    batches = [reference_tuple(synthetic_batch(sample_B, A, BURN, LEARN, FWD, channels=C, seed=s)) for s in (0, 1)]
+    stamps, threads_used = [], []
+    cands = list(thread_candidates or [])
+    state = {"best": None, "trial": []}
+
+    class PQ:
+        def put(self, item):
+            if device == "cuda":
+                torch.cuda.synchronize()
+            now = time.perf_counter()
+            stamps.append(now)
+            threads_used.append(torch.get_num_threads())
+            k = len(stamps)                      # updates finished so far
+            if device == "cpu" and cands:
+                # warm-up updates 2.. try the candidate thread counts, the timed updates use the fastest
+                if 1 <= k < warmup and k - 1 < len(cands):
+                    torch.set_num_threads(cands[k - 1])
+                elif k == warmup:
+                    durs = np.diff(stamps)
+                    tried = [(durs[i - 1], threads_used[i]) for i in range(1, k)]
+                    state["best"] = min(tried)[1] if tried else torch.get_num_threads()
+                    torch.set_num_threads(state["best"])
+                elif k == warmup + steps and tail_1thread:
+                    torch.set_num_threads(1)     # as shipped: train.py:13 pins torch to one thread
+
+    learner = ref.worker.Learner(queue.Queue(), PQ(), net)
+    learner.batched_data = [batches[i % 2] for i in range(total)]
+    t0 = time.perf_counter()
+    learner.run()                                # sleeps 2 s first (worker.py:321)
+    durs = np.diff([t0 + 2.0] + stamps)
+    return dict(timed=durs[warmup:warmup + steps], tail=durs[warmup + steps:], threads=state["best"] or torch.get_num_threads(),
+                device=str(learner.device))
 
 
-# ----------------------------------------------------------------------------------------------- CPU reference arm
-def cpu_learner_rate(C: int, steps: int, sample_B: int):
-    """Time the oracle port of the reference learner (oracle/learner.py: torch-CPU fp32, the reference's three-pass
-    structure and packed nn.LSTM op) on a bounded sample of `sample_B` sequences per update."""
+def port_learner_rate(C: int, steps: int, sample_B: int):
+    """Fallback when the reference files are not present: the oracle port (oracle/learner.py) on the host cores."""
     import oracle.learner as ol
     from oracle import synth
     from oracle.learner import LearnerState, init_params, learner_update
     ol.LSTM_MODE = "packed"
-    cores = os.cpu_count() or 1
     params = init_params(A, in_channels=C, seed=0)
     st = LearnerState(online={k: v.clone() for k, v in params.items()}, target={k: v.clone() for k, v in params.items()})
     batches = [synth.to_torch_batch(synth.synthetic_batch(sample_B, A, BURN, LEARN, FWD, channels=C, seed=s)) for s in (0, 1)]
-    best = None
-    for threads in sorted({min(cores, n) for n in (8, 16, 32, 64)}):       # pick the thread count the port runs best at
-        torch.set_num_threads(threads)
-        learner_update(st, batches[0])
-        t0 = time.perf_counter()
-        learner_update(st, batches[1])
-        dt = time.perf_counter() - t0
-        if best is None or dt < best[1]:
-            best = (threads, dt)
-    torch.set_num_threads(best[0])
+    torch.set_num_threads(min(os.cpu_count() or 1, 16))
+    learner_update(st, batches[0])
     t0 = time.perf_counter()
     for k in range(steps):
         learner_update(st, batches[k % 2])
     dt = (time.perf_counter() - t0) / steps
-    return sample_B / dt, dt, best[0], cores
+    return sample_B / dt, dt, torch.get_num_threads()
+
+
+def reference_subprocess(device: str, steps: int, warmup: int, C: int):
+    """Run `bench.py --impl reference` in a child process (CUDA hidden for the CPU arm) and return its JSON line."""
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--device", device, "--steps", str(steps),
+           "--warmup", str(warmup), "--channels", str(C)]
+    try:
+        out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+        for ln in reversed(out.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)
+        print(f"reference arm ({device}) printed no JSON: {out.stderr[-400:]}", file=sys.stderr)
+    except Exception as e:                                           # the comparator must never take the product number down
+        print(f"reference arm ({device}) failed: {e}", file=sys.stderr)
+    return None
 
 
 def run_reference(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
     C = args.channels
-    sample_B = 16
-    steps = max(1, min(args.steps, 5))
-    val, dt, threads, cores = cpu_learner_rate(C, steps, sample_B)
+    cores = os.cpu_count() or 1
+    workload = f"configs[1]: learner update, b/l/f {BURN}/{LEARN}/{FWD} (T={T}), {C}x84x84 u8 frames, A={A}"
+    if not reference_available():
+        val, dt, threads = port_learner_rate(C, max(1, min(args.steps, 5)), 16)
+        kind, sample, extra = "port", f"oracle port, 16-sequence sample per update, {threads} threads (reference files not found)", {}
+        steps, warmup = max(1, min(args.steps, 5)), 1
+    elif args.device == "cuda":
+        r = reference_learner_times(C, args.steps, args.warmup, B, "cuda")
+        dt = float(np.median(r["timed"]))
+        val, kind, steps, warmup = B / dt, "reference", args.steps, args.warmup
+        sample = f"full batch of {B} sequences per update on {r['device']} (stock PyTorch eager: cuDNN/cuBLAS), H2D of the batch inside the step as worker.py:331-334 does"
+        extra = {"device": "cuda"}
+    else:
+        sample_B = 16
+        cands = sorted({min(cores, n) for n in (8, 16, 32, 64)})
+        r = reference_learner_times(C, args.steps, max(args.warmup, 2), sample_B, "cpu", cands, tail_1thread=1)
+        dt = float(np.median(r["timed"]))
+        val, kind, steps, warmup = sample_B / dt, "reference", args.steps, max(args.warmup, 2)
+        one = sample_B / float(r["tail"][0]) if len(r["tail"]) else None
+        sample = (f"each update = a {sample_B}-sequence sample of the batch-{B} workload through the unmodified reference "
+                  f"worker.Learner.run (baseline/_ref) on the CPU, {r['threads']} of {cores} host threads (fastest of {cands} tried "
+                  f"during warm-up); median of {args.steps} updates" + ("; conv1 re-instantiated with 4 input channels" if C != 1 else ""))
+        extra = {"one_thread_value": one, "one_thread_note": "same sample, torch.set_num_threads(1) as train.py:13 ships, 1 update"}
     line = {"impl": "reference", "metric": "learner sequences/sec", "value": val, "unit": "sequences/s", "n_gpus": args.gpus,
-            "steps": steps, "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"configs[1]: learner update, b/l/f {BURN}/{LEARN}/{FWD} (T={T}), {C}x84x84 u8 frames, A={A}",
-                       "channels": C},
-            "cpu_baseline": {"value": val, "unit": "sequences/s", "cores": threads, "kind": "port",
-                             "sample": f"{steps} full updates of a {sample_B}-sequence sample of the batch-{B} workload after warm-up "
-                                       f"(oracle/learner.py, torch CPU fp32, {threads} of {cores} host threads: fastest of 8/16/32/64)"},
+            "config": {"workload": workload, "channels": C},
+            "cpu_baseline": {"value": val, "unit": "sequences/s", "cores": extra.get("threads", None) or (r["threads"] if kind == "reference" else 16),
+                             "kind": kind, "sample": sample, **{k: v for k, v in extra.items() if k != "threads"}},
             "e2e": {"value": val, "unit": "sequences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -222,7 +273,7 @@ def run_ours(args):
     from r2d2_b200.model import Network
     from r2d2_b200.replay import DeviceReplay
     from r2d2_b200.worker import Learner
-    from oracle.learner import init_params     # seeded NumPy initialiser only
+    from r2d2_b200.synthetic import init_state_dict, reference_tuple, synthetic_batch, synthetic_blocks
 
     rank, world, local = r2dist.init_from_env("nccl")
     torch.cuda.set_device(local)
@@ -234,7 +285,7 @@ def run_ours(args):
     _lib.lib().r2d2_set_fast_math({"strict": 0, "fast": 1, "balanced": 2}[args.precision])
 
     model = Network(A, obs_shape=(C, 84, 84))
-    model.load_state_dict(init_params(A, in_channels=C, seed=0))
+    model.load_state_dict(init_state_dict(A, in_channels=C, seed=0))
     learner = Learner(None, None, model, save_interval=10 ** 9, device=dev)
     learner._start_time = time.time()
     if world > 1:
@@ -244,14 +295,14 @@ def run_ours(args):
     # HBM replay shard of this rank: NUM_BLOCKS blocks, tree over 2^20 slots
     replay = DeviceReplay(NUM_BLOCKS * BLOCK_LEN, BLOCK_LEN, BURN, LEARN, FWD, A, (C, 84, 84), 512, 0.9, 0.6, B, device=dev,
                           seed=rank, tree_capacity=TREE_CAPACITY)
-    distinct = synthetic_blocks(16, C, seed=1000 + rank)
+    distinct = synthetic_blocks(16, A, C, seed=1000 + rank, burn_in=BURN, learning=LEARN, forward=FWD, block_len=BLOCK_LEN)
     for i in range(NUM_BLOCKS):
         blk, prio = distinct[i % len(distinct)]
         replay.add(blk, prio, None)
     learner.replay = replay
     torch.cuda.synchronize()
 
-    tuples = [host_tuple(C, 100 * rank + i, pinned=True)[0] for i in range(3)]
+    tuples = [reference_tuple(synthetic_batch(B, A, BURN, LEARN, FWD, channels=C, seed=100 * rank + i), pinned=True) for i in range(3)]
     in_bytes = sum(v.numel() * v.element_size() for v in tuples[0] if isinstance(v, torch.Tensor))
 
     def step_resident(i):
@@ -346,10 +397,15 @@ def run_ours(args):
                                 "kernel": "K1+K1b unroll group (forward online+target, BPTT backward): winconv/winwgrad/umma2/rec_fwd/rec_bwd launches",
                                 "ms": ms_unroll, "algorithmic_gflop_per_launch": fl / 1e9}
         if world == 1 and not args.no_cpu_baseline:
-            val, dt, threads, cores = cpu_learner_rate(C, 2, 8)
-            line["cpu_baseline"] = {"value": val, "unit": "sequences/s", "cores": threads, "kind": "port",
-                                    "sample": f"2 full updates of an 8-sequence sample of the batch-{B} workload after warm-up "
-                                              f"(oracle/learner.py, torch CPU fp32, {threads} of {cores} host threads)"}
+            torch.cuda.synchronize()
+            cpu = reference_subprocess("cpu", 3, 3, C)               # the reference's CPU learner on this box's host cores
+            if cpu is not None:
+                line["cpu_baseline"] = cpu["cpu_baseline"]
+            eager = reference_subprocess("cuda", 5, 2, C)            # the reference's own learner on this GPU (stock PyTorch eager)
+            if eager is not None:
+                line["vs_cuda_eager"] = {"reference_value": eager["value"], "unit": "sequences/s", "ratio": value / eager["value"],
+                                         "e2e_ratio": e2e / eager["value"], "sample": eager["cpu_baseline"]["sample"],
+                                         "ms_per_step": eager["ms_per_step"]}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -365,10 +421,15 @@ def main():
                     help="strict: bf16x3 split products everywhere; balanced: hi+lo only for encoder weight operands; fast: plain bf16")
     ap.add_argument("--fast", action="store_true", help="same as --precision fast")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference only: cpu = the reference's CPU learner (the driver's reference arm), cuda = the reference's own "
+                         "learner on this GPU through stock PyTorch eager (on-box comparator)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-times", action="store_true", help="also write gpurun_out/kernel_times.txt (per-kernel CUPTI durations)")
     args = ap.parse_args()
     if args.impl == "reference":
+        if args.device == "cpu":
+            os.environ["CUDA_VISIBLE_DEVICES"] = ""                   # worker.py:283 takes cuda whenever it is visible
         run_reference(args)
     else:
         args.warmup = max(args.warmup, 3)

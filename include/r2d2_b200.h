@@ -145,6 +145,12 @@ int r2d2_net_backward(r2d2_net* n, const float* params, const float* dq, float* 
  * gradients): 1 (default) = CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles, TMA-fed: csrc/umma3.cuh); 0 = single-CTA
  * 128 x 128 tiles fed by cp.async (csrc/umma2.cuh).  Same results to fp32 rounding.  Returns the previous value. */
 int r2d2_set_pair_gemm(int on);
+/* Forward recurrence: 1 (default) = one thread-block cluster of 16 CTAs per (network, 16 sequences): W_hh resident in tensor
+ * memory + shared memory, h_t exchanged over distributed shared memory (csrc/recurrence2.cuh); 0 = the persistent kernel
+ * that exchanges h_t through L2 flags (csrc/recurrence.cuh).  Returns the previous value. */
+int r2d2_set_cluster_recurrence(int on);
+/* Diagnostics: how many such clusters the current device can keep resident at once (< 0: the query failed). */
+int r2d2_debug_cluster_capacity(void);
 /* Recurrence scheduling: 1 (default) = all T LSTM steps of both networks in ONE persistent cooperative kernel
  * (W_hh slices resident in shared memory, per-network step barriers) for B <= 64; 0 = one launch per step. */
 int r2d2_set_persistent_recurrence(int on);
@@ -210,6 +216,9 @@ int r2d2_debug_gemm3(int a_major, int b_major, int M, int N, int K, const void* 
  * SWIZZLE_128B descriptor whose start address is shifted by `shift` rows inside one staged buffer (A bf16 [144][64]);
  * mode 1 also sets the descriptor's base_offset field to shift & 7. */
 int r2d2_debug_shift_probe(const void* A, const void* B, float* D, int shift, int mode, void* stream);
+/* hardware probe: D[128][16] = A[128][64] . B[16][64]^T (bf16) with A read from tensor memory (tcgen05.st) and B from
+ * K-major SWIZZLE_64B shared-memory tiles -- the operand forms of the cluster recurrence (csrc/recurrence2.cuh). */
+int r2d2_debug_ts_probe(const void* A, const void* B, float* D, void* stream);
 /* hardware probe: cycles for reps*4 back-to-back tcgen05.mma (M x N x 16, bf16, operands in shared memory) on each of
  * `ctas` CTAs; mode bit 0 alternates two accumulators, bit 1 reads A MN-major.  cycles[0] <- clock64 delta of CTA 0. */
 int r2d2_debug_mma_rate(int M, int N, int reps, int mode, int ctas, long long* cycles, void* stream);

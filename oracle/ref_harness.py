@@ -1,8 +1,9 @@
 """Import the UNMODIFIED reference (build container only; TEST INFRASTRUCTURE).
 
-The reference cannot travel to the GPU box, so this module is used only by
-``oracle/gen_golden.py`` and by container-only tests (skipped when the reference
-directory is absent).  Two shims, both described in SURVEY.md section 8(c):
+The reference is read from /root/reference in the build container and from
+``baseline/_ref`` (a verbatim, git-ignored copy made by ``__graft_entry__.build()``)
+on the GPU box.  Used by ``oracle/gen_golden.py``, by tests (skipped when neither
+directory exists) and by ``bench.py --impl reference``.  Two shims, both described in SURVEY.md section 8(c):
 
   * a stub ``gym`` module (``environment.py`` imports gym at module level; only
     ``gym.Wrapper``, ``gym.ObservationWrapper``, ``gym.spaces.Box`` and
@@ -21,7 +22,9 @@ import types
 
 import numpy as np
 
-REF_ROOT = os.environ.get("R2D2_REF", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_COPY = os.path.join(os.path.dirname(_HERE), "baseline", "_ref")        # verbatim copy made by __graft_entry__.build(); travels to the GPU box
+REF_ROOT = os.environ.get("R2D2_REF") or ("/root/reference" if os.path.isfile("/root/reference/worker.py") else _COPY)
 
 
 def available() -> bool:

@@ -68,6 +68,8 @@ SIGNATURES = {
     "r2d2_net_backward": (C.c_int, [p, p, p, p, p]),
     "r2d2_set_persistent_recurrence": (C.c_int, [C.c_int]),
     "r2d2_set_pair_gemm": (C.c_int, [C.c_int]),
+    "r2d2_set_cluster_recurrence": (C.c_int, [C.c_int]),
+    "r2d2_debug_cluster_capacity": (C.c_int, []),
     "r2d2_debug_rec_trace": (C.c_int, [p]),
     "r2d2_net_debug_ptr": (p, [p, C.c_int, C.c_char_p]),
     "r2d2_set_gemm_backend": (C.c_int, [C.c_int]),
@@ -85,6 +87,7 @@ SIGNATURES = {
     "r2d2_debug_gemm2": (C.c_int, [C.c_int] * 6 + [p] * 5 + [C.c_int, p]),
     "r2d2_debug_gemm3": (C.c_int, [C.c_int] * 5 + [p] * 5 + [C.c_int, p]),
     "r2d2_debug_shift_probe": (C.c_int, [p, p, p, C.c_int, C.c_int, p]),
+    "r2d2_debug_ts_probe": (C.c_int, [p, p, p, p]),
     "r2d2_debug_mma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, p, p]),
     "r2d2_clip_adam": (C.c_int, [p, p, p, p, i64, p, p, f32, f32, f32, f32, f32, i64, p, p]),
 }

@@ -259,3 +259,71 @@ extern "C" int r2d2_debug_mma_rate(int M, int N, int reps, int mode, int ctas, l
     R2D2_LAUNCH_CHECK();
     return R2D2_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Hardware probe for the cluster recurrence (recurrence2.cuh): tcgen05.mma with the A operand read from TENSOR MEMORY
+// (written there with tcgen05.st, two bf16 reduction indices per 32-bit column, even index in the low half) and the B
+// operand in shared memory as K-major SWIZZLE_64B tiles of [16 rows][32 k].  D[128][16] = A[128][64] . B[16][64]^T.
+namespace r2d2 {
+__global__ void __launch_bounds__(128) ts_probe_kernel(const bf16* __restrict__ A /*[128][64]*/, const bf16* __restrict__ Bm /*[16][64]*/,
+                                                       float* __restrict__ D /*[128][16]*/) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;
+    uint8_t* smem = smem_raw + pad;
+    const uint32_t sB = raw + pad;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2048);
+    uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int u = tid; u < 16 * 8; u += 128) {                 // 16 rows x 8 chunks of 8 k
+        const int r = u >> 3, ch = u & 7, tile = ch >> 2, c4 = ch & 3;
+        *reinterpret_cast<uint4*>(smem + tile * 1024 + (r >> 3) * 512 + (r & 7) * 64 + ((c4 ^ ((r >> 1) & 3)) << 4)) =
+            *reinterpret_cast<const uint4*>(Bm + r * 64 + ch * 8);
+    }
+    if (tid == 0) { mbar_init(smem_u32(bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(64) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *slot;
+    {   // A row `tid` -> TMEM lane tid, columns 0..31 (k = 2c, 2c+1)
+        const uint32_t* arow = reinterpret_cast<const uint32_t*>(A + (size_t)tid * 64);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            uint32_t r[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] = arow[h * 16 + i];
+            tmem_st16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(h * 16), r);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0) {
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+        for (int s = 0; s < 4; ++s)
+            umma_bf16_ts(tmem + 32, tmem + (uint32_t)(8 * s), umma_desc_sw64(sB + (s >> 1) * 1024 + (s & 1) * 32), idesc, s ? 1u : 0u);
+        umma_commit(smem_u32(bar));
+    }
+    mbar_wait(smem_u32(bar), 0);
+    tc_fence_after();
+    float v[16];
+    tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + 32u, v);
+    for (int i = 0; i < 16; ++i) D[tid * 16 + i] = v[i];
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64) : "memory");
+}
+}  // namespace r2d2
+
+extern "C" int r2d2_debug_ts_probe(const void* A, const void* B, float* D, void* stream) {
+    R2D2_REQUIRE(A && B && D, "bad arguments");
+    r2d2::ts_probe_kernel<<<1, 128, 2048 + 1024 + 64, r2d2::as_stream(stream)>>>((const r2d2::bf16*)A, (const r2d2::bf16*)B, D);
+    R2D2_LAUNCH_CHECK();
+    return R2D2_OK;
+}

@@ -30,8 +30,7 @@
 #include <algorithm>
 #include <map>
 
-#include "recurrence.cuh"
-#include "umma3.cuh"
+#include "recurrence2.cuh"
 #include "winconv.cuh"
 
 namespace r2d2 {
@@ -641,6 +640,10 @@ static cudaError_t wgrad3(const Mat3& a, const Mat3& b, int M, int N, int K, int
 // (umma3.cuh); 0: single-CTA cp.async kernels (umma2.cuh).  R2D2_PAIR_GEMM=0 in the environment or r2d2_set_pair_gemm.
 int g_pair_gemm = [] { const char* e = getenv("R2D2_PAIR_GEMM"); return (e && e[0] == '0') ? 0 : 1; }();
 
+// 1 (default): forward recurrence inside 16-CTA clusters (recurrence2.cuh: W_hh resident in TMEM + shared memory, h exchanged
+// over distributed shared memory); 0: the L2-flag persistent kernel of recurrence.cuh.  R2D2_CLUSTER_REC=0 / r2d2_set_cluster_recurrence.
+int g_cluster_recurrence = [] { const char* e = getenv("R2D2_CLUSTER_REC"); return (e && e[0] == '0') ? 0 : 1; }();
+namespace r2d2 { int g_rec2_ns = [] { const char* e = getenv("R2D2_REC2_NS"); return e ? atoi(e) : 0; }(); }   // sequences per recurrence cluster: 0 auto, 16, 32
 int g_persistent_recurrence = 1;
 unsigned long long* g_rec_trace = nullptr;   // debug: device buffer [T][8] of step timestamps (r2d2_debug_rec_trace)     // 0: per-step launches (also the path for B > 64)
 
@@ -1015,7 +1018,7 @@ static StepOps lstm_step_ops(r2d2_net* n, int which, const float* hidden, int t)
 // in the same launches (two independent recurrences hide each other's per-step latency).
 static int net_recurrence(r2d2_net* n, int which, const float* hidden, cudaStream_t s) {
     const int B = n->B, T = n->T;
-    if (B <= 64 && g_persistent_recurrence) {            // one cooperative launch for all T steps (recurrence.cuh)
+    if (g_persistent_recurrence && (B <= 64 || g_cluster_recurrence)) {   // one launch for all T steps
         RecFwdParams P;
         for (int k = 0; k < 2; ++k) {
             P.Whi[k] = n->pk[k].Whh_p.hi; P.Wlo[k] = n->pk[k].Whh_p.lo; P.XP[k] = n->ac[k].XP;
@@ -1026,8 +1029,12 @@ static int net_recurrence(r2d2_net* n, int which, const float* hidden, cudaStrea
         P.net_base = which == 2 ? 0 : which;
         P.fast = g_fast_math == 1;
         P.trace = g_rec_trace;
-        R2D2_CUDA_CHECK(launch_rec_fwd(P, which == 2 ? 2 : 1, s));
-        return R2D2_OK;
+        cudaError_t e = g_cluster_recurrence ? launch_rec2_fwd(P, which == 2 ? 2 : 1, s) : cudaErrorNotSupported;
+        if (e == cudaErrorNotSupported && B <= 64) e = launch_rec_fwd(P, which == 2 ? 2 : 1, s);   // device cannot host 16-CTA clusters
+        if (e != cudaErrorNotSupported) {
+            R2D2_CUDA_CHECK(e);
+            return R2D2_OK;
+        }
     }
     for (int t = 0; t < T; ++t) {
         if (which == 2) {
@@ -1253,6 +1260,16 @@ int r2d2_net_backward(r2d2_net* n, const float* params, const float* dq, float* 
         R2D2_CUDA_CHECK(n->C == 1 ? conv1_wgrad<1>(n, grads, s) : conv1_wgrad<4>(n, grads, s));
     }
     return R2D2_OK;
+}
+
+/* diagnostics: number of 16-CTA recurrence clusters the current device keeps resident at once (< 0: query failed) */
+int r2d2_debug_cluster_capacity(void) { return rec2_max_active_clusters<16>() * 100 + rec2_max_active_clusters<32>(); }
+
+/* 1 (default): forward LSTM recurrence inside 16-CTA clusters (distributed-shared-memory exchange of h); 0: L2-flag kernel. */
+int r2d2_set_cluster_recurrence(int on) {
+    int prev = g_cluster_recurrence;
+    g_cluster_recurrence = on ? 1 : 0;
+    return prev;
 }
 
 /* 1 (default): plain-matrix GEMMs of K1/K1b on CTA pairs (cta_group::2, TMA); 0: single-CTA cp.async kernels.  Returns the previous value. */

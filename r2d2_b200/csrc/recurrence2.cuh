@@ -1,0 +1,397 @@
+// Cluster-resident LSTM recurrence: the hidden state never leaves the SMs between time steps.
+//
+// recurrence.cuh exchanges h_t between its 64 CTAs per network through L2: publish -> fence -> flag -> poll -> reload,
+// four L2 traversals on the critical path of every step (5.9 us per step measured, tensor pipe 7-14 % busy).  Here one
+// thread-block CLUSTER of 16 CTAs owns a whole recurrence for 16 sequences:
+//
+//   grid = (networks x batch quarters) clusters of 16 CTAs.  CTA c of a cluster owns hidden units [32c, 32c+32), i.e. the
+//   128 gate-interleaved rows [128c, 128c+128) of W_hh, for the 16 sequences of its quarter.
+//   * W_hh slice resident for the whole kernel: the bf16 hi plane in TENSOR MEMORY (A operand of tcgen05.mma read from
+//     TMEM: 128 lanes x 256 columns), the lo plane in shared memory (128 KB, K-major SWIZZLE_128B).
+//   * per step  gates[128 x 16] = W_slice[128 x 512] . h_{t-1}[16 x 512]^T  as M=128, N=16 MMAs (bf16x3: W_hi.h_hi +
+//     W_hi.h_lo + W_lo.h_hi), consumed source-CTA by source-CTA as the pieces of h_{t-1} arrive;
+//   * h_{t-1} lives in shared memory as 16 tiles (one per source CTA) of [16 sequences][32 units] bf16 hi|lo, K-major
+//     SWIZZLE_64B.  After the cell update a CTA writes its own tile once into a staging buffer and pushes it to all 16
+//     CTAs of the cluster with 16 bulk copies over distributed shared memory (cp.async.bulk shared::cta ->
+//     shared::cluster); each copy completes on an mbarrier of the DESTINATION CTA, which is what its MMA warp waits on.
+//     No global-memory round trip, no flags, no fences: one DSMEM hop (~0.1 us) per step.
+//   * epilogue: thread = TMEM lane = gate row (4 unit + gate); a 4-lane shuffle transpose gives every thread the four
+//     gates of (unit, 4 sequences); c and h stay in registers across steps; h, c and the gates are also streamed to
+//     global memory for the heads and the backward pass (off the critical path).
+// Buffers alternate with the step parity; a CTA can run at most one step ahead of the slowest CTA of its cluster (it
+// needs everybody's h_t to produce h_{t+1}), which is what makes two buffers and two staging tiles sufficient.
+#pragma once
+#include <algorithm>
+
+#include "recurrence.cuh"
+#include "umma3.cuh"
+
+namespace r2d2 {
+
+constexpr int R2_CL = 16;                          // CTAs per cluster (non-portable size)
+constexpr int R2_EW = 16;                          // epilogue warps: 4 TMEM lane quadrants x 4 sequence groups
+constexpr int R2_THREADS = 32 * R2_EW + 32;        // + 1 MMA-issue warp
+constexpr int R2_GRP = 4;                          // source CTAs per arrival barrier (one mbarrier wait costs ~90 clk even when complete)
+
+// NS = sequences per cluster (16 or 32).  NS = 32 halves the number of clusters (a B200 keeps only 7 clusters of 16 CTAs with
+// this much shared memory resident, and 64 sequences x 2 networks at NS = 16 are 8); its h tiles are twice as large, so
+// half of the W lo plane (k < 256) moves to tensor memory next to the hi plane.
+template <int NS> struct Rec2Cfg {
+    static constexpr int kNC = NS / 16;                        // cells (sequences) per epilogue thread
+    static constexpr int kNV = NS / 4;                         // accumulator columns an epilogue warp reads (its sequence group)
+    static constexpr int kPlane = NS * 64;                     // one bf16 plane of one source tile: [NS][32 units]
+    static constexpr int kTile = 2 * kPlane;                   // hi | lo
+    static constexpr int kKT = NS == 32 ? 256 : 0;             // reduction indices of W lo that live in TMEM
+    static constexpr int kWloSmem = (512 - kKT) / 64 * 16384;  // W lo plane in shared memory: k-blocks of [128 rows][64 k]
+    static constexpr int kSH = 2 * R2_CL * kTile;              // [parity][source]
+    static constexpr int kStage = 2 * kTile;                   // [parity] own outgoing tile
+    static constexpr int kSmem = kWloSmem + kSH + kStage + 1024 + 512;
+    static constexpr int kWloCol = 256;                        // TMEM: W_hi columns [0,256), W_lo (k < kKT) [256, 256 + kKT/2)
+    static constexpr int kAccCol = 384;                        // accumulators: 2 NS columns (W_hi.h_hi | W_hi.h_lo) per parity
+    static_assert(NS == 16 || NS == 32, "sequences per cluster");
+    static_assert(kAccCol + 2 * 2 * NS <= 512 && kWloCol + kKT / 2 <= kAccCol, "TMEM budget");
+};
+
+// byte offset of (row, unit) inside a [rows][32] bf16 SWIZZLE_64B tile
+__device__ __forceinline__ uint32_t sw64_off(int row, int unit) {
+    return (uint32_t)((row >> 3) * 512 + (row & 7) * 64 + ((((unit >> 3) ^ (row >> 1)) & 3) << 4) + (unit & 7) * 2);
+}
+template <int NC, int N>
+__device__ __forceinline__ float pickq(const float (&v)[N], int q, int i) {       // v[NC q + i], q in 0..3, without dynamic register indexing
+    const float a = (q & 1) ? v[NC + i] : v[i], b = (q & 1) ? v[3 * NC + i] : v[2 * NC + i];
+    return (q & 2) ? b : a;
+}
+__device__ __forceinline__ float4 ld_nc_f4(const float* p) {                      // issued where it is written (never sunk to the use)
+    float4 r;
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+template <int N> __device__ __forceinline__ void tmem_ld_n_issue(uint32_t taddr, uint32_t (&r)[N]);
+template <> __device__ __forceinline__ void tmem_ld_n_issue<4>(uint32_t taddr, uint32_t (&r)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+}
+template <> __device__ __forceinline__ void tmem_ld_n_issue<8>(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+}
+template <int N> __device__ __forceinline__ void tmem_ld_n_wait(uint32_t (&a)[N], uint32_t (&b)[N]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < N; ++i) asm volatile("" : "+r"(a[i]), "+r"(b[i]));          // no use of the registers may move above the wait
+}
+
+template <int NS>
+__global__ void __launch_bounds__(R2_THREADS, 1) rec2_fwd_kernel(const RecFwdParams P, int nq) {
+    using Cfg = Rec2Cfg<NS>;
+    constexpr int NC = Cfg::kNC, NV = Cfg::kNV, TILE = Cfg::kTile, PLANE = Cfg::kPlane, NGRP = R2_CL / R2_GRP;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;
+    uint8_t* smem = smem_raw + pad;
+    const uint32_t sW = raw + pad;                     // W lo plane (k >= kKT)
+    const uint32_t sH = sW + Cfg::kWloSmem;            // h tiles [parity][source]
+    const uint32_t sS = sH + Cfg::kSH;                 // staging [parity]
+    uint8_t* stage_ptr = smem + Cfg::kWloSmem + Cfg::kSH;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kWloSmem + Cfg::kSH + Cfg::kStage);       // full[2][NGRP] | accf[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NGRP + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t c = cluster_ctarank();
+    const int cid = blockIdx.x / R2_CL;
+    const int net = P.net_base + cid / nq, quarter = cid % nq;
+    const int B = P.B, T = P.T;
+    const bool want_lo = !P.fast;
+
+    if (tid == 0) {
+        for (int i = 0; i < 2 * NGRP + 2; ++i) mbar_init(smem_u32(&bars[i]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == R2_EW) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // W lo plane, k >= kKT -> shared memory (all threads), K-major SWIZZLE_128B, 16 KB per k-block of 64
+    if (want_lo) {
+        constexpr int CH0 = Cfg::kKT / 8, NCH = 64 - CH0;      // 16-byte chunks per row that go to shared memory
+        for (int u = tid; u < 128 * NCH; u += R2_THREADS) {
+            const int row = u / NCH, ch = CH0 + u % NCH, kb = (ch - CH0) >> 3, jj = ch & 7;
+            const uint32_t dst = (uint32_t)(kb * 16384 + (row >> 3) * 1024 + (row & 7) * 128 + ((jj ^ (row & 7)) << 4));
+            cp_async16(sW + dst, P.Wlo[net] + (size_t)(128 * c + row) * REC_H + ch * 8, true);
+        }
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int q = warp & 3, cg = warp >> 2;            // epilogue warps: TMEM lane quadrant, sequence group
+    if (warp < R2_EW) {                                // W hi plane (and W lo, k < kKT) -> tensor memory: lane = gate row, column = k / 2
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int row = 128 * (int)c + 32 * q + lane;
+        const uint4* wrow = reinterpret_cast<const uint4*>(P.Whi[net] + (size_t)row * REC_H);
+#pragma unroll 1
+        for (int h = 4 * cg; h < 4 * cg + 4; ++h) {    // the four warps of a quadrant split the 16 column blocks
+            uint32_t r[16];
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+                const uint4 x = __ldg(wrow + h * 4 + q4);
+                r[4 * q4] = x.x; r[4 * q4 + 1] = x.y; r[4 * q4 + 2] = x.z; r[4 * q4 + 3] = x.w;
+            }
+            tmem_st16(lane_addr + (uint32_t)(h * 16), r);
+        }
+        if (want_lo && Cfg::kKT) {
+            const uint4* lrow = reinterpret_cast<const uint4*>(P.Wlo[net] + (size_t)row * REC_H);
+#pragma unroll 1
+            for (int h = cg; h < Cfg::kKT / 32; h += 4) {
+                uint32_t r[16];
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const uint4 x = __ldg(lrow + h * 4 + q4);
+                    r[4 * q4] = x.x; r[4 * q4 + 1] = x.y; r[4 * q4 + 2] = x.z; r[4 * q4 + 3] = x.w;
+                }
+                tmem_st16(lane_addr + (uint32_t)(Cfg::kWloCol + h * 16), r);
+            }
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                // every CTA's barriers exist before the first remote completion
+    tc_fence_after();
+
+    if (warp < R2_EW) {
+        // ------------------------------------------------------------------ epilogue / cell warps
+        const int j = 8 * q + (lane >> 2), g = lane & 3;           // unit inside the CTA, gate row (i, f, g, o)
+        const int unit = 32 * (int)c + j;
+        const int row0 = cg * NV + g * NC;                         // first of this thread's sequences inside the cluster's NS
+        int bq[NC], blen[NC];
+        float c_reg[NC];
+        uint32_t hb[NC], lb[NC];                                   // current h as bf16 bits (hi, lo)
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            bq[i] = NS * quarter + row0 + i;
+            const bool ok = bq[i] < B;
+            blen[i] = ok ? P.len[bq[i]] : -1;                      // -1: no such sequence (never live, nothing stored)
+            c_reg[i] = 0.f; hb[i] = 0u; lb[i] = 0u;
+            if (ok) {
+                c_reg[i] = P.c0[(size_t)bq[i] * P.ld_c0 + unit];
+                hb[i] = __bfloat16_as_ushort(P.Hhi[net][(size_t)bq[i] * REC_H + unit]);      // HsX block 0 = stored h0 (split)
+                lb[i] = __bfloat16_as_ushort(P.Hlo[net][(size_t)bq[i] * REC_H + unit]);
+            }
+        }
+        const float* xp_base = P.XP[net] + 4 * unit;
+        auto load_xp = [&](int t, float4 (&xp)[NC]) {
+#pragma unroll
+            for (int i = 0; i < NC; ++i)
+                xp[i] = (blen[i] >= 0 && t < T) ? ld_nc_f4(xp_base + ((size_t)t * B + bq[i]) * REC_G4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        // publish: own tile -> staging of parity `par`, then one bulk copy per destination CTA
+        auto publish = [&](int par, bool send) {
+            uint8_t* st = stage_ptr + par * TILE;
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                const uint32_t o = sw64_off(row0 + i, j);
+                *reinterpret_cast<uint16_t*>(st + o) = (uint16_t)hb[i];
+                *reinterpret_cast<uint16_t*>(st + PLANE + o) = (uint16_t)lb[i];
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * R2_EW) : "memory");
+            if (send && tid < R2_CL) {
+                const uint32_t dst = mapa_u32(sH + (uint32_t)((par * R2_CL + (int)c) * TILE), (uint32_t)tid);
+                const uint32_t bar = mapa_u32(smem_u32(&bars[par * NGRP + ((int)c / R2_GRP)]), (uint32_t)tid);
+                bulk_copy_to_cluster(dst, sS + par * TILE, TILE, bar);
+            }
+        };
+        publish(0, true);                              // h_{-1}
+        float4 xp[NC];
+        load_xp(0, xp);
+
+        for (int t = 0; t < T; ++t) {
+            const int par = t & 1;
+            const bool tr = P.trace && blockIdx.x == 0 && tid == 0;
+            if (tr) P.trace[t * 8 + 0] = gtime();
+            mbar_wait(smem_u32(&bars[2 * NGRP + par]), ((uint32_t)t >> 1) & 1u);
+            tc_fence_after();
+            if (tr) P.trace[t * 8 + 1] = gtime();
+            // accumulator: columns [0, NS) = W_hi.h_hi + W_lo.h_hi, [NS, 2 NS) = W_hi.h_lo; this warp reads its NV sequences
+            float v[NV];
+            {
+                const uint32_t a0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg::kAccCol + 2 * NS * par + cg * NV);
+                uint32_t ra[NV], rb[NV];
+                tmem_ld_n_issue<NV>(a0, ra);
+                tmem_ld_n_issue<NV>(a0 + NS, rb);
+                tmem_ld_n_wait<NV>(ra, rb);
+#pragma unroll
+                for (int i = 0; i < NV; ++i) v[i] = __uint_as_float(ra[i]) + (want_lo ? __uint_as_float(rb[i]) : 0.f);   // fast mode never writes the second half
+            }
+            // 4-lane transpose: lane (unit, gate g) ends with the four gates of its own NC sequences
+            float rv[3][NC];
+#pragma unroll
+            for (int off = 1; off < 4; ++off) {
+                const int gd = (g - off) & 3;                      // the lane that reads from me wants its own sequences
+                const int src = (lane & ~3) | ((g + off) & 3);
+#pragma unroll
+                for (int i = 0; i < NC; ++i) rv[off - 1][i] = __shfl_sync(0xffffffffu, pickq<NC>(v, gd, i), src);
+            }
+            float4 gact[NC];
+            bool live[NC];
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                float gt[4];
+                const float own = pickq<NC>(v, g, i);
+#pragma unroll
+                for (int G = 0; G < 4; ++G) {
+                    const int off = (G - g) & 3;                   // gate G sits `off` lanes further in the quad
+                    gt[G] = off == 0 ? own : off == 1 ? rv[0][i] : off == 2 ? rv[1][i] : rv[2][i];
+                }
+                const float gi = fast_sigmoid(gt[0] + xp[i].x);
+                const float gf = fast_sigmoid(gt[1] + xp[i].y);
+                const float gg = fast_tanh(gt[2] + xp[i].z);
+                const float go = fast_sigmoid(gt[3] + xp[i].w);
+                const float cn = gf * c_reg[i] + gi * gg;
+                const float hn = go * fast_tanh(cn);
+                gact[i] = make_float4(gi, gf, gg, go);
+                live[i] = t < blen[i];
+                if (live[i]) {
+                    c_reg[i] = cn;
+                    const bf16 hh = __float2bfloat16_rn(hn);
+                    const bf16 ll = __float2bfloat16_rn(hn - __bfloat162float(hh));
+                    hb[i] = __bfloat16_as_ushort(hh);
+                    lb[i] = __bfloat16_as_ushort(ll);
+                }
+            }
+            if (tr) P.trace[t * 8 + 2] = gtime();
+            publish(par ^ 1, t + 1 < T);               // h_t is the input of step t+1
+            if (tr) P.trace[t * 8 + 3] = gtime();
+            // ---- off the critical path: everything that goes to global memory, and the next step's input projection.
+            // (fence.proxy.async above is a MEMBAR: it waits for this thread's outstanding global accesses, so they are
+            // issued AFTER it and have a whole step to complete.)
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                if (blen[i] >= 0) {
+                    const size_t row = (size_t)t * B + bq[i];
+                    if (P.Gs[net]) *reinterpret_cast<float4*>(P.Gs[net] + row * REC_G4 + 4 * unit) = gact[i];
+                    P.Cs[net][row * REC_H + unit] = c_reg[i];
+                }
+            }
+            load_xp(t + 1, xp);
+            // h_t -> HsX block t+1 (for the heads and the backward pass): 16-byte chunks of the staged tile
+            for (int u = tid; u < NS * 8; u += 32 * R2_EW) {
+                const int plane = u / (NS * 4), row = (u >> 2) % NS, ch = u & 3;
+                const int b = NS * quarter + row;
+                if (b < B) {
+                    const uint4 x = *reinterpret_cast<const uint4*>(stage_ptr + (par ^ 1) * TILE + plane * PLANE + (row >> 3) * 512 + (row & 7) * 64 +
+                                                                   (((ch ^ (row >> 1)) & 3) << 4));
+                    bf16* dstp = (plane ? P.Hlo[net] : P.Hhi[net]) + ((size_t)(t + 1) * B + b) * REC_H + 32 * (int)c + ch * 8;
+                    *reinterpret_cast<uint4*>(dstp) = x;
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ MMA issue (whole warp loops, one lane issues)
+        constexpr uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);
+        constexpr uint32_t idesc2 = idesc_base | ((uint32_t)(2 * NS >> 3) << 17), idesc1 = idesc_base | ((uint32_t)(NS >> 3) << 17);
+        const bool leader = elect_one();
+        const uint32_t uW = __shfl_sync(0xffffffffu, sW, 0), uH = __shfl_sync(0xffffffffu, sH, 0);
+        const uint32_t uT = __shfl_sync(0xffffffffu, tmem_base, 0);
+        for (int t = 0; t < T; ++t) {
+            const int par = t & 1;
+            const uint32_t ph = ((uint32_t)t >> 1) & 1u;
+            if (leader)
+                for (int gr = 0; gr < NGRP; ++gr) mbar_arrive_expect_tx(smem_u32(&bars[par * NGRP + gr]), R2_GRP * TILE);
+            __syncwarp();
+            const uint32_t acc = uT + (uint32_t)(Cfg::kAccCol + 2 * NS * par);
+            const uint32_t hbase = uH + (uint32_t)(par * R2_CL * TILE);
+#pragma unroll
+            for (int gr = 0; gr < NGRP; ++gr) {
+                mbar_wait(smem_u32(&bars[par * NGRP + gr]), ph);
+                tc_fence_after();
+                if (P.trace && blockIdx.x == 0 && leader && gr == 0) P.trace[t * 8 + 6] = gtime();
+                if (leader) {
+#pragma unroll
+                    for (int ss = 0; ss < R2_GRP; ++ss) {
+                        const int s = gr * R2_GRP + ss;
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            const int kk = 32 * s + 16 * k;                                               // first reduction index of this MMA
+                            const uint64_t b_hl = umma_desc_sw64(hbase + (uint32_t)(s * TILE + k * 32));   // rows [0, NS) = hi plane, [NS, 2 NS) = lo plane
+                            const uint32_t a_t = uT + (uint32_t)(kk >> 1);
+                            if (want_lo) {
+                                umma_bf16_ts(acc, a_t, b_hl, idesc2, (s | k) ? 1u : 0u);                  // W_hi . [h_hi | h_lo]
+                                if (kk < Cfg::kKT) umma_bf16_ts(acc, uT + (uint32_t)(Cfg::kWloCol + (kk >> 1)), b_hl, idesc1, 1u);     // W_lo . h_hi
+                                else umma_bf16(acc, umma_desc_sw128(uW + (uint32_t)(((kk - Cfg::kKT) >> 6) * 16384 + (kk & 63) * 2)), b_hl, idesc1, 1u);
+                            } else {
+                                umma_bf16_ts(acc, a_t, b_hl, idesc1, (s | k) ? 1u : 0u);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            if (leader) umma_commit(smem_u32(&bars[2 * NGRP + par]));
+            if (P.trace && blockIdx.x == 0 && leader) P.trace[t * 8 + 7] = gtime();
+            __syncwarp();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                // nobody exits while a peer may still copy from its staging tile
+    if (warp == R2_EW) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+template <int NS>
+static inline cudaLaunchConfig_t rec2_config(int clusters, cudaStream_t s, cudaLaunchAttribute* attr) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(clusters * R2_CL);
+    cfg.blockDim = dim3(R2_THREADS);
+    cfg.dynamicSmemBytes = Rec2Cfg<NS>::kSmem;
+    cfg.stream = s;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = R2_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cfg;
+}
+
+// how many 16-CTA clusters of the recurrence kernel the device keeps resident at once (0: clusters of 16 are not schedulable)
+template <int NS>
+static inline int rec2_max_active_clusters() {
+    static int cached = -1;
+    if (cached >= 0) return cached;
+    static unsigned long long configured = 0;
+    if (ensure_dynamic_smem(rec2_fwd_kernel<NS>, Rec2Cfg<NS>::kSmem, &configured) != cudaSuccess) return 0;
+    cudaLaunchAttribute attr[1];
+    cudaLaunchConfig_t cfg = rec2_config<NS>(8, nullptr, attr);
+    int n = 0;
+    cudaError_t e = cudaFuncSetAttribute(rec2_fwd_kernel<NS>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, rec2_fwd_kernel<NS>, &cfg);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); n = 0; }
+    return cached = n;
+}
+
+extern int g_rec2_ns;     // 0 = automatic, 16 / 32 = forced sequences per cluster
+
+// Returns cudaErrorNotSupported when clusters of 16 CTAs with this much shared memory cannot be scheduled on the device.
+static inline cudaError_t launch_rec2_fwd(const RecFwdParams& P, int nets, cudaStream_t s) {
+    cudaLaunchAttribute attr[1];
+    const int cap16 = rec2_max_active_clusters<16>(), cap32 = rec2_max_active_clusters<32>();
+    const int need16 = nets * ((P.B + 15) / 16), need32 = nets * ((P.B + 31) / 32);
+    // 16 sequences per cluster has the shorter step; use it when all its clusters are resident at once
+    int ns = (cap16 >= need16 || cap32 == 0) ? 16 : 32;
+    if (g_rec2_ns == 16 || g_rec2_ns == 32) ns = g_rec2_ns;
+    if ((ns == 16 ? cap16 : cap32) < 1) return cudaErrorNotSupported;
+    if (ns == 16) {
+        cudaLaunchConfig_t cfg = rec2_config<16>(need16, s, attr);
+        return cudaLaunchKernelEx(&cfg, rec2_fwd_kernel<16>, P, (P.B + 15) / 16);
+    }
+    cudaLaunchConfig_t cfg = rec2_config<32>(need32, s, attr);
+    return cudaLaunchKernelEx(&cfg, rec2_fwd_kernel<32>, P, (P.B + 31) / 32);
+}
+
+}  // namespace r2d2

@@ -215,6 +215,7 @@ class Learner:
                  device=None):
         from .learner_core import DeviceLearner
         self.device = torch.device(device if device is not None else 'cuda')      # worker.py:283 -- no CPU fallback here
+        self._start_time = time.time()                                             # reset by run(); checkpoints record minutes since then
         self.action_dim = model.action_dim
         self.obs_shape = tuple(model.obs_shape)
         self.batch_size = config.batch_size
@@ -239,7 +240,7 @@ class Learner:
         self.env_steps = 0
         self._stager = None
         from .learner_core import WeightPublisher                        # eager: pinning 17 MB and starting the thread take
-        self._publisher = WeightPublisher(self.core.online, self.shared_model) if model is not None else None   # milliseconds
+        self._publisher = WeightPublisher(self.core.online, self.shared_model)                                # milliseconds
 
     # -- parameters ---------------------------------------------------------------------------------------------
     def state_dict(self):

@@ -58,3 +58,18 @@ def test_ss_mode_issue_rate_matches_operand_read_model():
         clk = out.item() / 8000
         model = max(128 * N / 256, (M + N) / 4)
         assert abs(clk - model) <= 0.1 * model, (M, N, clk, model)
+
+
+def test_tmem_a_operand_and_sw64_b_tiles():
+    """tcgen05.mma with A in tensor memory (written by tcgen05.st) and B as K-major SWIZZLE_64B tiles (recurrence2.cuh)."""
+    from r2d2_b200 import _lib
+    _lib.require_device()
+    g = torch.Generator(device="cuda").manual_seed(11)
+    A = torch.randn(128, 64, device="cuda", generator=g).bfloat16().contiguous()
+    B = torch.randn(16, 64, device="cuda", generator=g).bfloat16().contiguous()
+    D = torch.full((128, 16), float("nan"), device="cuda")
+    _lib.check(_lib.lib().r2d2_debug_ts_probe(_lib.ptr(A), _lib.ptr(B), _lib.ptr(D), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    ref = A.double() @ B.double().t()
+    err = (D.double() - ref).abs().max().item()
+    assert err < 1e-4, err
