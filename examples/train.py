@@ -39,11 +39,16 @@ def main():
     ap.add_argument("--gpu-actors", action="store_true",
                     help="step all actors' environments in ONE process with a batched GPU inference per step "
                          "(worker.VectorActor) instead of one CPU-inference process per actor")
+    ap.add_argument("--synthetic-env", action="store_true",
+                    help="no Atari emulator on this box: run on r2d2_b200.environment.SyntheticAtariEnv (sets R2D2_SYNTHETIC_ENV=1 "
+                         "for this process and the actor processes); without it a missing gym/ALE is an error, as upstream")
     for name in ("training_steps", "learning_starts", "buffer_capacity", "batch_size", "log_interval", "block_length",
                  "burn_in_steps", "learning_steps", "forward_steps", "save_interval"):
         ap.add_argument("--" + name.replace("_", "-"), type=int, default=None)
     args = ap.parse_args()
-    overrides = {name: val for name, val in vars(args).items() if name not in ("actors", "gpu_actors") and val is not None}
+    if args.synthetic_env:
+        os.environ["R2D2_SYNTHETIC_ENV"] = "1"
+    overrides = {name: val for name, val in vars(args).items() if name not in ("actors", "gpu_actors", "synthetic_env") and val is not None}
     for name, val in overrides.items():
         setattr(config, name, val)
 

@@ -109,5 +109,23 @@ def ptr(t) -> int:
 
 
 def stream_ptr() -> int:
+    """cudaStream_t of torch's current stream on the CURRENT device (callers run inside `on_device`)."""
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+def on_device(method):
+    """Decorator for methods of objects with a `.device`: run the body with that CUDA device current, so that the stream
+    handed to the C ABI, the kernels it launches and the buffers it touches all belong to the same device even when the
+    caller never called torch.cuda.set_device (e.g. Learner(device='cuda:1'))."""
+    import functools
+
+    @functools.wraps(method)
+    def wrapper(self, *args, **kwargs):
+        import torch
+        idx = self.device.index
+        if idx is None or torch.cuda.current_device() == idx:
+            return method(self, *args, **kwargs)
+        with torch.cuda.device(idx):
+            return method(self, *args, **kwargs)
+    return wrapper

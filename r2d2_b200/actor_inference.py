@@ -43,6 +43,7 @@ class BatchedPolicy:
         self.core.pack(0)
 
     # ---- one environment step of all actors ------------------------------------------------------------------------
+    @_lib.on_device
     def step(self, obs, last_action, last_reward, hidden: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         """obs u8 (N,C,84,84); last_action one-hot (N,A) (bool/u8/float) or indices (N,); last_reward (N,);
         hidden (N,2,512) = (h, c) per actor (zeros after a reset; None keeps the state of the previous step).

@@ -4,6 +4,12 @@ They are read both as def-time default arguments and at run time (training_steps
 learning_starts, log_interval, learning_steps, block_length, forward_steps), exactly like
 the reference, so `import config; config.x = ...` before constructing the workers behaves
 the same way.
+
+Upstream the only way to change a value is to edit config.py before starting; the equivalent here, without editing the
+package, is the environment variable R2D2_CONFIG_OVERRIDES holding a JSON object of {name: value} that is applied when
+this module is first imported (i.e. before any worker captures a def-time default), e.g.
+    R2D2_CONFIG_OVERRIDES='{"training_steps": 1000, "num_actors": 4}' python train.py
+Unknown names are an error (a typo must not silently train with the defaults).
 """
 game_name = 'MsPacman'
 obs_shape = (1, 84, 84)
@@ -42,3 +48,20 @@ hidden_dim = 512
 render = False
 save_plot = True
 test_epsilon = 0.001
+
+
+def _apply_overrides():
+    import json
+    import os
+    raw = os.environ.get("R2D2_CONFIG_OVERRIDES")
+    if not raw:
+        return
+    g = globals()
+    for name, value in json.loads(raw).items():
+        if name not in g or name.startswith("_"):
+            raise KeyError(f"R2D2_CONFIG_OVERRIDES: unknown config name {name!r}")
+        g[name] = tuple(value) if isinstance(g[name], tuple) else value
+    g["seq_len"] = g["burn_in_steps"] + g["learning_steps"] + g["forward_steps"]
+
+
+_apply_overrides()

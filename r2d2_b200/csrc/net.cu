@@ -1174,13 +1174,20 @@ int r2d2_net_backward(r2d2_net* n, const float* params, const float* dq, float* 
         R2D2_CUDA_CHECK((launch_umma2<128>(a, b, e, Rmax, H, 2 * H, 1, s)));
     }
     // ---- BPTT through all b+l steps, burn-in included (no detach anywhere in model.py:122-150)
-    if (B <= 64 && g_persistent_recurrence) {            // one cooperative launch for all T steps (recurrence.cuh)
+    bool bptt_done = false;
+    if (g_persistent_recurrence && (B <= 64 || g_cluster_recurrence)) {   // one launch for all T steps
         RecBwdParams P;
         P.WThi = pk.WhhT_p.hi; P.WTlo = pk.WhhT_p.lo; P.dH = n->dH; P.Gs = ac.Gs; P.Cs = ac.Cs;
         P.c0 = n->hidden + H; P.ld_c0 = 2 * H; P.len = n->len_learn; P.DGhi = n->DG.hi; P.DGlo = n->DG.lo;
         P.partial = n->rec_partial; P.flags = n->rec_bar + 32; P.B = B; P.T = T; P.fast = g_fast_math == 1;
-        R2D2_CUDA_CHECK(launch_rec_bwd(P, s));
-    } else {
+        cudaError_t e = g_cluster_recurrence ? launch_rec2_bwd(P, s) : cudaErrorNotSupported;     // 16-CTA clusters, DSMEM reduce-scatter
+        if (e == cudaErrorNotSupported && B <= 64) e = launch_rec_bwd(P, s);                       // L2-flag cooperative kernel
+        if (e != cudaErrorNotSupported) {
+            R2D2_CUDA_CHECK(e);
+            bptt_done = true;
+        }
+    }
+    if (!bptt_done) {
     R2D2_CUDA_CHECK(cudaMemsetAsync(n->dcrec, 0, (size_t)B * H * sizeof(float), s));
     for (int t = T - 1; t >= 0; --t) {
         const float* cprev = t ? ac.Cs + (size_t)(t - 1) * B * H : n->hidden + H;

@@ -394,4 +394,258 @@ static inline cudaError_t launch_rec2_fwd(const RecFwdParams& P, int nets, cudaS
     return cudaLaunchKernelEx(&cfg, rec2_fwd_kernel<32>, P, (P.B + 31) / 32);
 }
 
+
+// ================================================================================================
+// Cluster-resident BPTT recurrence (online network): dh_{t-1} = dgates_t . W_hh without leaving the SMs.
+//
+//   One cluster of 16 CTAs per 16 sequences.  CTA c owns hidden units [32c, 32c+32) = gate rows [128c, 128c+128):
+//   * pointwise role (512 threads = 32 units x 16 sequences): dh_t = dH[t] + sum of the 16 partials received for step
+//     t+1 (fixed order: deterministic), LSTM cell backward -> dgates_t (4 per cell), carried dc in a register;
+//     dgates_t goes to global memory (split, for the weight-gradient GEMMs) and, as bf16 hi|lo, into shared memory as
+//     the B operand [16 sequences][128 own gate rows];
+//   * GEMM role: partial[512 units][16] = W_hh[own 128 gate rows, :]^T . dgates_t  -- the K-slice of the product that
+//     this CTA can compute from its OWN dgates.  A = W_hh^T block [512 units][128 k]: hi plane resident in TENSOR
+//     MEMORY (4 M-tiles x 64 columns), lo plane in shared memory (128 KB); 64 MMAs (M=128) per step;
+//   * reduce-scatter: rows [32d, 32d+32) of the partial belong to CTA d: each epilogue thread pushes its 64 bytes
+//     straight from registers into CTA d's receive slot with st.async (distributed shared memory, completes on CTA d's
+//     mbarrier).  No global memory, flags or fences on the critical path.
+// ================================================================================================
+constexpr int RB2_WLO = 4 * 2 * 16384;             // W^T lo plane: [M-tile][k-block][128 units][64 k]
+constexpr int RB2_BOP = 2 * 4096;                  // dgates as B operand: [k-block][hi 16 rows | lo 16 rows][128 B]
+constexpr int RB2_SLOT = 2048;                     // one source's partial for my 32 units: [32][16] fp32
+constexpr int RB2_RECV = 2 * R2_CL * RB2_SLOT;     // [parity][source]
+constexpr int RB2_SMEM = RB2_WLO + RB2_BOP + RB2_RECV + 1024 + 256;
+constexpr int RB2_ACC_COL = 256;                   // TMEM: W^T hi in columns [0,256), accumulators 4 x 32 columns at 256
+
+__device__ __forceinline__ void st_async_v4(uint32_t dst, uint32_t mbar, float a, float b, float c, float d) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(dst), "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(__float_as_uint(d)), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ float ld_nc_f1(const float* p) {
+    float r;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+
+__global__ void __launch_bounds__(R2_THREADS, 1) rec2_bwd_kernel(const RecBwdParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;
+    uint8_t* smem = smem_raw + pad;
+    const uint32_t sW = raw + pad;                     // W^T lo plane
+    const uint32_t sB = sW + RB2_WLO;                  // dgates B operand
+    const uint32_t sR = sB + RB2_BOP;                  // receive slots [parity][source]
+    uint8_t* bop_ptr = smem + RB2_WLO;
+    const float* recv_ptr = reinterpret_cast<const float*>(smem + RB2_WLO + RB2_BOP);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RB2_WLO + RB2_BOP + RB2_RECV);       // recv_full[2] | accf
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t c = cluster_ctarank();
+    const int quarter = blockIdx.x / R2_CL;
+    const int B = P.B, T = P.T;
+    const bool want_lo = !P.fast;
+
+    if (tid == 0) {
+        for (int i = 0; i < 3; ++i) mbar_init(smem_u32(&bars[i]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == R2_EW) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // W^T lo plane -> shared memory: tile (m, kb) = units [128m, +128) x own gate rows [64 kb, +64), K-major SWIZZLE_128B
+    if (want_lo) {
+        for (int u = tid; u < 4 * 2 * 128 * 8; u += R2_THREADS) {
+            const int jj = u & 7, row = (u >> 3) & 127, tile = u >> 10, m = tile >> 1, kb = tile & 1;
+            const uint32_t dst = (uint32_t)(tile * 16384 + (row >> 3) * 1024 + (row & 7) * 128 + ((jj ^ (row & 7)) << 4));
+            cp_async16(sW + dst, P.WTlo + (size_t)(128 * m + row) * REC_G4 + 128 * (int)c + 64 * kb + 8 * jj, true);
+        }
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int q = warp & 3, m = warp >> 2;             // epilogue role: TMEM lane quadrant, M-tile  (destination CTA = 4 m + q)
+    if (warp < R2_EW) {                                // W^T hi plane -> tensor memory: lane = unit (within M-tile m), column = 64 m + k / 2
+        const uint4* wrow = reinterpret_cast<const uint4*>(P.WThi + (size_t)(128 * m + 32 * q + lane) * REC_G4 + 128 * (int)c);
+#pragma unroll 1
+        for (int h = 0; h < 4; ++h) {
+            uint32_t r[16];
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+                const uint4 x = __ldg(wrow + h * 4 + q4);
+                r[4 * q4] = x.x; r[4 * q4 + 1] = x.y; r[4 * q4 + 2] = x.z; r[4 * q4 + 3] = x.w;
+            }
+            tmem_st16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(64 * m + 16 * h), r);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+
+    if (warp < R2_EW) {
+        // pointwise ownership: sequence pb (fastest: conflict-free reads of the receive slots), unit pj
+        const int pb = tid & 15, pj = tid >> 4;
+        const int unit = 32 * (int)c + pj;
+        const int b = 16 * quarter + pb;
+        const bool own = b < B;
+        const int len = own ? P.len[b] : 0;
+        float dcrec = 0.f;
+        // B-operand position of this thread's 4 gate values: row pb, k = 4 pj .. 4 pj + 3 of the own 128 gate rows
+        const uint32_t bop_off = (uint32_t)((pj >> 4) * 4096 + (pb >> 3) * 1024 + (pb & 7) * 128 + (((((pj & 15) >> 1)) ^ (pb & 7)) << 4) + (pj & 1) * 8);
+        // operands of the cell backward that do not depend on the recurrence, fetched one step ahead
+        float4 g_n = make_float4(0.f, 0.f, 0.f, 0.f);
+        float dh_n = 0.f, ct_n = 0.f, cp_n = 0.f;
+        auto prefetch = [&](int t) {
+            if (own && t >= 0 && t < len) {
+                const size_t row = (size_t)t * B + b;
+                g_n = ld_nc_f4(P.Gs + row * REC_G4 + 4 * unit);
+                dh_n = ld_nc_f1(P.dH + row * REC_H + unit);
+                ct_n = ld_nc_f1(P.Cs + row * REC_H + unit);
+                cp_n = t ? ld_nc_f1(P.Cs + ((size_t)(t - 1) * B + b) * REC_H + unit) : ld_nc_f1(P.c0 + (size_t)b * P.ld_c0 + unit);
+            }
+        };
+        prefetch(T - 1);
+        for (int t = T - 1, step = 0; t >= 0; --t, ++step) {
+            const float4 g = g_n;
+            float dh = dh_n;
+            const float ct = ct_n, cp = cp_n;
+            const bool live = own && t < len;
+            if (step > 0) {                            // partials of dgates_{t+1} . W_hh for my units have landed (parity of t+1)
+                const int par = (t + 1) & 1;
+                if (tid == 0) mbar_arrive_expect_tx(smem_u32(&bars[par]), R2_CL * RB2_SLOT);
+                mbar_wait(smem_u32(&bars[par]), ((uint32_t)(step - 1) >> 1) & 1u);
+                const float* rp = recv_ptr + (size_t)par * R2_CL * (RB2_SLOT / 4) + pj * 16 + pb;
+                float acc = 0.f;
+#pragma unroll
+                for (int s = 0; s < R2_CL; ++s) acc += rp[s * (RB2_SLOT / 4)];
+                dh += acc;
+            }
+            float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+            if (live) {
+                const float tc = fast_tanh(ct);
+                const float dc = dcrec + dh * g.w * (1.f - tc * tc);
+                o0 = dc * g.z * g.x * (1.f - g.x);
+                o1 = dc * cp * g.y * (1.f - g.y);
+                o2 = dc * g.x * (1.f - g.z * g.z);
+                o3 = dh * tc * g.w * (1.f - g.w);
+                dcrec = dc * g.y;
+            }
+            uint32_t h2[2], l2[2];
+            split2(o0, o1, h2[0], l2[0]);
+            split2(o2, o3, h2[1], l2[1]);
+            if (t > 0) {
+                *reinterpret_cast<uint2*>(bop_ptr + bop_off) = make_uint2(h2[0], h2[1]);
+                *reinterpret_cast<uint2*>(bop_ptr + 2048 + bop_off) = make_uint2(l2[0], l2[1]);
+                fence_proxy_async_smem();
+            }
+            tc_fence_before();
+            asm volatile("bar.sync 2, %0;" ::"n"(R2_THREADS) : "memory");        // B operand complete -> MMA warp
+            // ---- off the critical path: dgates_t to global memory, operands of the next step
+            if (own) {
+                const size_t o = ((size_t)t * B + b) * REC_G4 + 4 * unit;
+                *reinterpret_cast<uint2*>(P.DGhi + o) = make_uint2(h2[0], h2[1]);
+                *reinterpret_cast<uint2*>(P.DGlo + o) = make_uint2(l2[0], l2[1]);
+            }
+            if (t == 0) break;                          // dh_{-1} is not needed
+            prefetch(t - 1);
+            // ---- reduce-scatter of this step's partial: warp (q, m) holds units [128 m + 32 q, +32) = CTA 4 m + q
+            mbar_wait(smem_u32(&bars[2]), (uint32_t)step & 1u);
+            tc_fence_after();
+            float v[16];
+            {
+                const uint32_t a0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(RB2_ACC_COL + 32 * m);
+                uint32_t ra[16], rb[16];
+                tmem_ld16_issue(a0, ra);
+                tmem_ld16_issue(a0 + 16, rb);
+                tmem_ld_wait(ra);
+                tmem_ld_wait(rb);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(ra[i]) + (want_lo ? __uint_as_float(rb[i]) : 0.f);
+            }
+            {
+                const int par = t & 1;
+                const uint32_t d = (uint32_t)(4 * m + q);
+                const uint32_t dst = mapa_u32(sR + (uint32_t)((par * R2_CL + (int)c) * RB2_SLOT + lane * 64), d);
+                const uint32_t bar = mapa_u32(smem_u32(&bars[par]), d);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) st_async_v4(dst + 16 * i, bar, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
+            tc_fence_before();
+        }
+    } else {
+        // ------------------------------------------------------------------ MMA issue
+        constexpr uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);
+        constexpr uint32_t idesc2 = idesc_base | ((32u >> 3) << 17), idesc1 = idesc_base | ((16u >> 3) << 17);
+        const bool leader = elect_one();
+        const uint32_t uW = __shfl_sync(0xffffffffu, sW, 0), uB = __shfl_sync(0xffffffffu, sB, 0);
+        const uint32_t uT = __shfl_sync(0xffffffffu, tmem_base, 0);
+        for (int t = T - 1; t >= 0; --t) {
+            asm volatile("bar.sync 2, %0;" ::"n"(R2_THREADS) : "memory");
+            if (t == 0) break;
+            tc_fence_after();
+            if (leader) {
+#pragma unroll
+                for (int mm = 0; mm < 4; ++mm) {
+                    const uint32_t acc = uT + (uint32_t)(RB2_ACC_COL + 32 * mm);
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk) {
+                        const uint64_t b_hl = umma_desc_sw128(uB + (uint32_t)((kk >> 2) * 4096 + (kk & 3) * 32));      // rows 0-15 hi, 16-31 lo
+                        const uint32_t a_t = uT + (uint32_t)(64 * mm + 8 * kk);
+                        if (want_lo) {
+                            umma_bf16_ts(acc, a_t, b_hl, idesc2, kk ? 1u : 0u);
+                            umma_bf16(acc, umma_desc_sw128(uW + (uint32_t)((mm * 2 + (kk >> 2)) * 16384 + (kk & 3) * 32)), b_hl, idesc1, 1u);
+                        } else {
+                            umma_bf16_ts(acc, a_t, b_hl, idesc1, kk ? 1u : 0u);
+                        }
+                    }
+                }
+                umma_commit(smem_u32(&bars[2]));
+            }
+            __syncwarp();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == R2_EW) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+static inline cudaError_t launch_rec2_bwd(const RecBwdParams& P, cudaStream_t s) {
+    static unsigned long long configured = 0;
+    static int usable = -1;
+    {
+        cudaError_t e = ensure_dynamic_smem(rec2_bwd_kernel, RB2_SMEM, &configured);
+        if (e != cudaSuccess) return e;
+    }
+    cudaLaunchAttribute attr[1];
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(((P.B + 15) / 16) * R2_CL);
+    cfg.blockDim = dim3(R2_THREADS);
+    cfg.dynamicSmemBytes = RB2_SMEM;
+    cfg.stream = s;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = R2_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (usable < 0) {
+        cudaError_t e = cudaFuncSetAttribute(rec2_bwd_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        int n = 0;
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, rec2_bwd_kernel, &cfg);
+        usable = (e == cudaSuccess && n >= 1) ? 1 : 0;
+        (void)cudaGetLastError();
+    }
+    if (!usable) return cudaErrorNotSupported;
+    return cudaLaunchKernelEx(&cfg, rec2_bwd_kernel, P);
+}
+
 }  // namespace r2d2

@@ -11,11 +11,12 @@
 // (persistent CTAs loop over pixel tiles), so L2 traffic per 128-pixel tile is one window instead of KH*KW tiles
 // plus the weight matrix.
 //
-// Warp roles: warps 0-3 producers (cp.async of the window rows), 4 or 8 epilogue warps (TMEM -> bias/ReLU -> split
-// store), one MMA-issue warp.  Two TMEM accumulators alternate between consecutive tiles so that the epilogue
+// Warp roles: warp 0 = producer (one lane issues ONE TMA load per window plane: a 2-D box of [window rows][64 channels] with
+// the 128-byte swizzle; rows outside the activation matrix are zero-filled by the TMA unit), 4 or 8 epilogue warps (TMEM ->
+// bias/ReLU -> split store), one MMA-issue warp.  Two TMEM accumulators alternate between consecutive tiles so that the epilogue
 // of tile i overlaps the MMAs of tile i+1.
 #pragma once
-#include "umma2.cuh"
+#include "umma3.cuh"
 
 namespace r2d2 {
 
@@ -35,18 +36,19 @@ struct WinCfg {
     static_assert(kStages >= 2, "not enough shared memory for two window stages");
 };
 
-// Warp roles: warps 0-3 producers (two were too few: the staging loop became the bottleneck), then EW = 4 or 8 epilogue
-// warps (warp & 3 = TMEM lane quadrant; with 8, the first four take columns [0, N/2) and the others [N/2, N)), then the
+// Warp roles: warp 0 producer (TMA; round 1 needed four cp.async warps here and ran the LSU/L1 at 56-67 % of peak), then
+// EW = 4 or 8 epilogue warps (warp & 3 = TMEM lane quadrant; with 8, two warps per quadrant split the columns), then the
 // MMA warp.  EW = 8 is for epilogue-bound layers: conv1 ran 1,170 instructions per tile on ONE epilogue warp per
 // scheduler at IPC 0.44 (ncu) -- 194 -> 156 us with two; the MMA-bound layers are faster with four (measured).
-constexpr int WC_PRODUCERS = 128;
+constexpr int WC_PRODUCERS = 32;
 // Epilogue contract: struct Pre; void prefetch(long long p, int col0, Pre&) const  (operands of columns [col0, col0 + N/2));
 // void store16(long long p, int n, const float (&v)[16], int col0, const Pre&) const
 // where p is the GRID pixel index (frame * GW*GH + gy * GW + gx); the functor drops junk pixels itself.
 template <int GW, int IC, int KH, int KW, int N, bool A_LO, bool B_LO, bool BACK, int EW, class Epi>
 __global__ void __launch_bounds__(WC_PRODUCERS + 32 * EW + 32, 1)
-winconv_kernel(const bf16* __restrict__ Xhi, const bf16* __restrict__ Xlo, long long R /* total grid pixels */,
-               const bf16* __restrict__ Whi, const bf16* __restrict__ Wlo /* [N][taps*IC], k = tap*IC + c */, const Epi ep) {
+winconv_kernel(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl /* X[pixel][channel] planes, box {64, window rows} */,
+               long long R /* total grid pixels */, const bf16* __restrict__ Whi, const bf16* __restrict__ Wlo /* [N][taps*IC], k = tap*IC + c */,
+               const Epi ep) {
     using Cfg = WinCfg<GW, IC, KH, KW, N, A_LO, B_LO>;
     constexpr int S = Cfg::kStages, KB = Cfg::kKB, TAPS = Cfg::kTaps, KTOT = TAPS * IC;
     constexpr int WC_THREADS = WC_PRODUCERS + 32 * EW + 32, WC_MMA_WARP = WC_PRODUCERS / 32 + EW;
@@ -63,7 +65,7 @@ winconv_kernel(const bf16* __restrict__ Xhi, const bf16* __restrict__ Xlo, long 
     const long long ntiles = (R + 127) / 128;
 
     if (tid == 0) {
-        for (int s = 0; s < S; ++s) { mbar_init(smem_u32(&bars[s]), WC_PRODUCERS / 32); mbar_init(smem_u32(&bars[S + s]), 1); }
+        for (int s = 0; s < S; ++s) { mbar_init(smem_u32(&bars[s]), 1); mbar_init(smem_u32(&bars[S + s]), 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&bars[2 * S + a]), 1); mbar_init(smem_u32(&bars[2 * S + 2 + a]), EW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -95,39 +97,26 @@ winconv_kernel(const bf16* __restrict__ Xhi, const bf16* __restrict__ Xlo, long 
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < WC_PRODUCERS / 32) {
-        // ------------------------------------------------------------------ producers: window rows -> smem
-        long long it = 0;
-        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const long long p0 = tile * 128;
-            for (int kb = 0; kb < KB; ++kb, ++it) {
-                const int s = (int)(it % S);
-                const uint32_t ph = (uint32_t)(it / S) & 1u;
-                mbar_wait(smem_u32(&bars[S + s]), ph ^ 1u);
-                const uint32_t st = sA + s * Cfg::kAStage;
-                for (int u = tid; u < Cfg::kWinRows * 8; u += WC_PRODUCERS) {
-                    const int row = u >> 3, j = u & 7;
-                    const long long p = p0 + row - (BACK ? Cfg::kHalo : 0);
-                    const bool ok = p >= 0 && p < R;
-                    const size_t src = ok ? (size_t)p * IC + kb * 64 + j * 8 : 0;
-                    const uint32_t dst = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((j ^ (row & 7)) << 4));
-                    cp_async16(st + dst, Xhi + src, ok);
-                    if (A_LO) cp_async16(st + Cfg::kWinBytes + dst, Xlo + src, ok);
-                }
-                cp_async_commit();
-                if (it > 0) {                                                   // hand over the PREVIOUS stage: two groups stay in flight per thread
-                    cp_async_wait<1>();
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&bars[(int)((it - 1) % S)]));
+        // ------------------------------------------------------------------ producer: one TMA box per window plane
+        if (lane == 0) {
+            tma_prefetch_desc(&tmXh);
+            if (A_LO) tma_prefetch_desc(&tmXl);
+            long long it = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int p_first = (int)(tile * 128) - (BACK ? Cfg::kHalo : 0);        // may be negative / run past R: zero fill
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const int s = (int)(it % S);
+                    const uint32_t ph = (uint32_t)(it / S) & 1u;
+                    mbar_wait(smem_u32(&bars[S + s]), ph ^ 1u);
+                    const uint32_t st = sA + s * Cfg::kAStage;
+                    const uint32_t full = smem_u32(&bars[s]);
+                    mbar_arrive_expect_tx(full, (uint32_t)Cfg::kAStage);
+                    tma_load_2d(st, &tmXh, full, kb * 64, p_first);
+                    if (A_LO) tma_load_2d(st + Cfg::kWinBytes, &tmXl, full, kb * 64, p_first);
                 }
             }
         }
-        if (it > 0) {
-            cp_async_wait<0>();
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&bars[(int)((it - 1) % S)]));
-        }
+        __syncwarp();
     } else if (warp < WC_MMA_WARP) {
         // ------------------------------------------------------------------ epilogue (8 warps: lane quadrant x column half)
         constexpr int GRP = N * 4 / EW;                                         // columns per epilogue warp
@@ -233,7 +222,11 @@ static inline cudaError_t launch_winconv_inst(SplitC X, long long R, SplitC W, c
     }
     const long long ntiles = (R + 127) / 128;
     const int grid = (int)(ntiles < kNumSMs ? ntiles : kNumSMs);
-    kern<<<grid, WC_PRODUCERS + 32 * EW + 32, Cfg::kSmem, s>>>(X.hi, X.lo, R, W.hi, W.lo, ep);
+    if (R >= (1ll << 31) - 256) return cudaErrorInvalidValue;                        // TMA coordinates are int32
+    const CUtensorMap* mh = tmap_2d(X.hi, IC, (uint64_t)R, IC, 64, Cfg::kWinRows);
+    const CUtensorMap* ml = A_LO ? tmap_2d(X.lo, IC, (uint64_t)R, IC, 64, Cfg::kWinRows) : mh;
+    if (!mh || !ml) return cudaErrorInvalidValue;
+    kern<<<grid, WC_PRODUCERS + 32 * EW + 32, Cfg::kSmem, s>>>(*mh, *ml, R, W.hi, W.lo, ep);
     return cudaGetLastError();
 }
 

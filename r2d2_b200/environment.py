@@ -1,11 +1,17 @@
 """``create_env`` -- the reference's ``environment`` module surface (environment.py:66-74 upstream).
 
 The emulator is outside the learner hot path.  When gym + ALE are importable the reference's
-environment is reproduced (grayscale, frameskip 4, 84x84 INTER_AREA warp, no-op starts); otherwise
--- as in this image, which has neither -- a deterministic synthetic stand-in with the same interface
-(``action_space.n``, ``reset() -> (1,84,84) u8``, ``step(a) -> (obs, reward, done, info)``) is returned
-so that train.py-style pipelines and the benchmarks can run.
+environment is reproduced (grayscale, frameskip 4, 84x84 INTER_AREA warp, no-op starts).  Like the
+reference, ``create_env`` RAISES when the emulator cannot be created (missing package or ROM, wrong game
+name ...): training on noise by accident is worse than not starting.  Only when the caller opts in
+explicitly -- ``R2D2_SYNTHETIC_ENV=1`` in the environment or ``create_env(..., synthetic=True)`` -- and gym /
+ALE are not importable, a synthetic stand-in with the same interface (``action_space.n``,
+``reset() -> (1,84,84) u8``, ``step(a) -> (obs, reward, done, info)``) is returned, with a warning, so that
+train.py-style pipelines and the benchmarks can run on a box without an emulator (this image has none).
 """
+import os
+import warnings
+
 import numpy as np
 
 from . import config
@@ -65,13 +71,23 @@ def _make_ale(env_name, noop_start):
                     obs = self.env.reset(**kwargs)
             return obs
 
-    env = WarpFrame(gym.make(f'ALE/{env_name}-v5', obs_type='grayscale', frameskip=4, repeat_action_probability=0,
-                             full_action_space=False))
-    return NoopReset(env) if noop_start else env
+    env = gym.make(f'ALE/{env_name}-v5', obs_type='grayscale', frameskip=4, repeat_action_probability=0, full_action_space=False)
+    env = WarpFrame(env)
+    if noop_start:
+        assert env.unwrapped.get_action_meanings()[0] == 'NOOP'          # environment.py:24 upstream
+        env = NoopReset(env)
+    return env
 
 
-def create_env(env_name=config.game_name, noop_start=True):
+def create_env(env_name=config.game_name, noop_start=True, synthetic=None):
+    if synthetic is None:
+        synthetic = os.environ.get("R2D2_SYNTHETIC_ENV") == "1"
     try:
         return _make_ale(env_name, noop_start)
-    except Exception:
+    except ImportError as e:                                             # gym / ale_py / cv2 not installed
+        if not synthetic:
+            raise ImportError(f"{e}; no Atari emulator in this environment -- set R2D2_SYNTHETIC_ENV=1 (or pass synthetic=True) "
+                              f"to run on a synthetic random-frame environment instead") from e
+        warnings.warn(f"create_env({env_name!r}): gym/ALE not importable ({e}); using SyntheticAtariEnv (random frames, 9 actions)",
+                      RuntimeWarning, stacklevel=2)
         return SyntheticAtariEnv(seed=np.random.randint(0, 2 ** 31 - 1))

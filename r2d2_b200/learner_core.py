@@ -153,6 +153,11 @@ class BatchStager:
     def _as_u8(t):
         return t.view(torch.uint8) if t.dtype == torch.bool else (t if t.dtype == torch.uint8 else (t != 0).to(torch.uint8))
 
+    @property
+    def device(self):
+        return self.core.device
+
+    @_lib.on_device
     def stage(self, fields: dict) -> int:
         """Enqueue the copies of one batch (dict with the 14-tuple's learner-visible fields); returns a slot handle."""
         i = self._next
@@ -242,16 +247,19 @@ class DeviceLearner:
             self._h = None
 
     # ------------------------------------------------------------------ parameters
+    @_lib.on_device
     def load_state_dict(self, sd, target_sd=None) -> None:
         self.online.load(sd)
         self.target.load(target_sd if target_sd is not None else sd)
         self.pack(0)
         self.pack(1)
 
+    @_lib.on_device
     def sync_target(self) -> None:                      # worker.py:376-377
         self.target.flat.copy_(self.online.flat)
         self.pack(1)
 
+    @_lib.on_device
     def pack(self, which: int) -> None:
         flat = self.online.flat if which == 0 else self.target.flat
         _lib.check(_lib.lib().r2d2_net_pack(self._h, which, _lib.ptr(flat), _lib.stream_ptr()))
@@ -290,6 +298,7 @@ class DeviceLearner:
             out["is_weights"] = t(batch["is_weights"]).float().contiguous()
         return out
 
+    @_lib.on_device
     def forward(self, which: int, b: dict, q_learn: Optional[torch.Tensor], q_shift: Optional[torch.Tensor]) -> None:
         flat = self.online.flat if which == 0 else self.target.flat
         p = _lib.ptr
@@ -298,11 +307,13 @@ class DeviceLearner:
                                                p(b["last_reward"]), p(b["hidden"]), p(b["burn_in"]), p(b["learning"]),
                                                p(b["forward"]), p(q_learn), p(q_shift), _lib.stream_ptr()))
 
+    @_lib.on_device
     def backward(self, dq: torch.Tensor) -> None:
         p = _lib.ptr
         _lib.check(_lib.lib().r2d2_net_backward(self._h, p(self.online.flat), p(dq), p(self.grads.flat),
                                                 _lib.stream_ptr()))
 
+    @_lib.on_device
     def compute_forward(self, b: dict) -> None:
         """worker.py:345-357: the three Q tensors, then TD / loss / priorities / dLoss/dQ (K1 + K2)."""
         self._live = b                                   # keep obs/hidden alive until backward ran
@@ -316,6 +327,7 @@ class DeviceLearner:
                                            self.B, self.A, p(self.td), p(self.prio), p(self.loss_sum), p(self.rows),
                                            p(self.dq), _lib.stream_ptr()))
 
+    @_lib.on_device
     def compute_gradients(self, b: dict) -> None:
         """worker.py:345-363: Q passes, TD/loss/priorities, backward.  Results stay on device in
         self.td / self.prio / self.loss_sum / self.rows / self.grads (grads of loss_sum)."""
@@ -323,6 +335,7 @@ class DeviceLearner:
         self.backward(self.dq)
         torch.reciprocal(self.rows.float(), out=self.grad_scale)      # mean over rows (worker.py:354)
 
+    @_lib.on_device
     def apply_gradients(self) -> None:
         """worker.py:364-365 (+ re-pack of the online weights)."""
         self.num_updates += 1
@@ -334,6 +347,7 @@ class DeviceLearner:
                                              self.num_updates, p(self.norm), _lib.stream_ptr()))
         self.pack(0)
 
+    @_lib.on_device
     def update(self, b: dict) -> None:
         self.compute_gradients(b)
         if self.grad_hook is not None:

@@ -109,6 +109,7 @@ class DeviceReplay:
         put("num_seq", np.array([block.num_sequences], dtype=np.int32), np.int32)
         return self.blob_bytes
 
+    @_lib.on_device
     def add(self, block, priority: np.ndarray, episode_reward: Optional[float] = None) -> None:
         slot = self._slot
         self._slot = (slot + 1) % len(self._staging)
@@ -138,6 +139,7 @@ class DeviceReplay:
             self.num_episodes += 1
 
     # ------------------------------------------------------------------ sample_batch (worker.py:163-240), on device
+    @_lib.on_device
     def sample(self, unit_uniforms: Optional[torch.Tensor] = None, fuse_into=None):
         """Returns (batch dict of device tensors, idxes int64 device, old_ptr).  With fuse_into = a DeviceLearner whose
         shape matches, frames are written straight into its space-to-depth staging buffer and batch["obs"] is None."""
@@ -167,5 +169,6 @@ class DeviceReplay:
         return b
 
     # ------------------------------------------------------------------ update_priorities (worker.py:242-261)
+    @_lib.on_device
     def update_priorities(self, idxes: torch.Tensor, priorities: torch.Tensor, old_ptr: int) -> None:
         self.tree.update_device(idxes, priorities, old_ptr=old_ptr, cur_ptr=self.block_ptr, seq_per_block=self.seq_per_block)

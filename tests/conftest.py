@@ -8,6 +8,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+# no Atari emulator on the test boxes: actors are allowed to fall back to the synthetic environment (opt-in, environment.py)
+os.environ.setdefault("R2D2_SYNTHETIC_ENV", "1")
 
 
 def pytest_configure(config):
