@@ -145,6 +145,8 @@ int r2d2_net_backward(r2d2_net* n, const float* params, const float* dq, float* 
  * gradients): 1 (default) = CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles, TMA-fed: csrc/umma3.cuh); 0 = single-CTA
  * 128 x 128 tiles fed by cp.async (csrc/umma2.cuh).  Same results to fp32 rounding.  Returns the previous value. */
 int r2d2_set_pair_gemm(int on);
+/* Incremented by every r2d2_set_* call: a caller that caches launch sequences (CUDA graphs of an update) keys them on it. */
+int r2d2_config_epoch(void);
 /* Forward recurrence: 1 (default) = one thread-block cluster of 16 CTAs per (network, 16 sequences): W_hh resident in tensor
  * memory + shared memory, h_t exchanged over distributed shared memory (csrc/recurrence2.cuh); 0 = the persistent kernel
  * that exchanges h_t through L2 flags (csrc/recurrence.cuh).  Returns the previous value. */
@@ -190,16 +192,6 @@ int r2d2_replay_gather_s2d(r2d2_replay* r, const int64_t* idx, const float* isw,
                            float* last_reward, float* hidden, uint8_t* action, float* n_step_reward, float* gamma, uint8_t* burn,
                            uint8_t* learn, uint8_t* fwd, float* is_weights_rows, int32_t* rows_out, void* stream);
 
-/* GEMM backend of every contraction in K1/K1b: 0 = fp32 CUDA-core FFMA (on-device numerical
- * reference), 1 = tcgen05 bf16x3 split (hi*hi + hi*lo + lo*hi, fp32 accumulate in TMEM: parity mode,
- * default), 2 = tcgen05 plain bf16 (fast mode).  Process-wide; returns the previous value. */
-int r2d2_set_gemm_backend(int backend);
-/* Test entry: C[M][N] = A x B^T on plain fp32 matrices through the chosen backend / tile width.
- * a_major, b_major: 0 = [rows][K] storage, 1 = [K][rows] storage.  splits > 1 leaves split-K
- * partials [splits][M][N] in C. */
-int r2d2_debug_gemm(int backend, int ubn, int a_major, int b_major, int M, int N, int K, const float* A, const float* B,
-                    float* C, int splits, void* stream);
-
 /* Precision mode of the tensor-core path: 0 = strict (bf16x3 split products everywhere, default), 1 = fast (plain
  * bf16 products), 2 = balanced (hi+lo only for the weight operands of the encoder contractions; recurrence, input
  * projection and dueling head stay strict).  Returns the previous mode. */
@@ -232,6 +224,12 @@ int r2d2_debug_mma_rate(int M, int N, int reps, int mode, int ctas, long long* c
 int r2d2_clip_adam(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                    const float* grad_scale, double* partial_ws, float max_norm, float lr, float beta1, float beta2,
                    float eps, int64_t step, float* norm_out, void* stream);
+/* Same update with nothing host-variable in the argument list (CUDA-graph replay): the 1-based update count is read from
+ * device memory (step_dev, int64, incremented by the caller on the same stream) and the gradient scale may come from a
+ * device row count (rows_dev, int32: scale = 1 / rows, overrides grad_scale; NULL = use grad_scale). */
+int r2d2_clip_adam_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                       const float* grad_scale, const int32_t* rows_dev, double* partial_ws, float max_norm, float lr, float beta1,
+                       float beta2, float eps, const int64_t* step_dev, float* norm_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -70,10 +70,9 @@ SIGNATURES = {
     "r2d2_set_pair_gemm": (C.c_int, [C.c_int]),
     "r2d2_set_cluster_recurrence": (C.c_int, [C.c_int]),
     "r2d2_debug_cluster_capacity": (C.c_int, []),
+    "r2d2_config_epoch": (C.c_int, []),
     "r2d2_debug_rec_trace": (C.c_int, [p]),
     "r2d2_net_debug_ptr": (p, [p, C.c_int, C.c_char_p]),
-    "r2d2_set_gemm_backend": (C.c_int, [C.c_int]),
-    "r2d2_debug_gemm": (C.c_int, [C.c_int] * 7 + [p, p, p, C.c_int, p]),
     "r2d2_replay_create": (C.c_int, [C.c_int] * 8 + [C.POINTER(p)]),
     "r2d2_replay_destroy": (C.c_int, [p]),
     "r2d2_replay_layout": (C.c_int, [p, C.POINTER(i64)]),
@@ -90,6 +89,7 @@ SIGNATURES = {
     "r2d2_debug_ts_probe": (C.c_int, [p, p, p, p]),
     "r2d2_debug_mma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, p, p]),
     "r2d2_clip_adam": (C.c_int, [p, p, p, p, i64, p, p, f32, f32, f32, f32, f32, i64, p, p]),
+    "r2d2_clip_adam_dev": (C.c_int, [p, p, p, p, i64, p, p, p, f32, f32, f32, f32, f32, p, p, p]),
 }
 
 

@@ -1,55 +1,22 @@
-// Test entry point: plain-matrix instances of the gather-GEMM on either backend, so the tcgen05
-// path (descriptors, swizzle, pipeline, TMEM epilogue) can be validated against the fp32 FFMA path
-// and a host reference independently of the network.
+// Test entry points: plain-matrix instances of the GEMM kernels (umma2.cuh single CTA / cp.async, umma3.cuh CTA pairs / TMA)
+// so descriptors, swizzle, pipeline and TMEM epilogue can be validated against a host fp64 product independently of the
+// network, plus the hardware-semantics probes the kernels rely on.
 #include "umma3.cuh"
 
 namespace r2d2 {
-enum GemmBackend { GEMM_FFMA = 0, GEMM_UMMA_BF16X3 = 1, GEMM_UMMA_BF16 = 2 };
-}
-
-namespace r2d2 {
-int g_gemm_backend = GEMM_UMMA_BF16X3;
 int g_fast_math = 0;
-
-template <class AL, class BL>
-static cudaError_t debug_run(int backend, int ubn, const AL& a, const BL& b, float* C, int M, int N, int K, int splits,
-                             float* ws, cudaStream_t s) {
-    EpiBias<false> e{C, nullptr, M, N, N, 1.f};
-    EpiPartial ep{ws, M, N};
-    const bool part = splits > 1;
-#define R2D2_DBG(UBN)                                                                                           \
-    if (backend == GEMM_FFMA) return part ? launch_gemm<128, 128, 16>(a, b, ep, M, N, K, splits, s)            \
-                                          : launch_gemm<128, 128, 16>(a, b, e, M, N, K, 1, s);                 \
-    if (backend == GEMM_UMMA_BF16X3) return part ? launch_umma<UBN, 3>(a, b, ep, M, N, K, splits, s)           \
-                                                 : launch_umma<UBN, 3>(a, b, e, M, N, K, 1, s);                \
-    return part ? launch_umma<UBN, 1>(a, b, ep, M, N, K, splits, s) : launch_umma<UBN, 1>(a, b, e, M, N, K, 1, s);
-    switch (ubn) {
-        case 16: { R2D2_DBG(16) }
-        case 32: { R2D2_DBG(32) }
-        case 64: { R2D2_DBG(64) }
-        case 128: { R2D2_DBG(128) }
-        default: { R2D2_DBG(256) }
-    }
-#undef R2D2_DBG
-}
+extern int g_config_epoch;
 }  // namespace r2d2
 
 using namespace r2d2;
 
 extern "C" {
 
-/* 0 = fp32 FFMA (numerical reference), 1 = tcgen05 bf16x3 split (parity mode, default),
- * 2 = tcgen05 plain bf16 (fast mode).  Process-wide; returns the previous value. */
-int r2d2_set_gemm_backend(int backend) {
-    int prev = g_gemm_backend;
-    if (backend >= 0 && backend <= 2) g_gemm_backend = backend;
-    return prev;
-}
-
 /* Precision mode of the tensor-core path: 0 = strict (bf16x3 split products everywhere, default), 1 = fast (plain
  * bf16 products), 2 = balanced (hi+lo only for weight operands of the encoder contractions; recurrence, input
  * projection and head stay strict).  Returns the previous mode. */
 int r2d2_set_fast_math(int mode) {
+    ++g_config_epoch;
     int prev = g_fast_math;
     if (mode >= 0 && mode <= 2) g_fast_math = mode;
     return prev;
@@ -100,22 +67,6 @@ int r2d2_debug_gemm3(int a_major, int b_major, int M, int N, int K, const void* 
     else if (a_major && !b_major) e = launch_umma3<true, false>(A, B, ep, M, N, K, splits, s);
     else if (!a_major && b_major) e = launch_umma3<false, true>(A, B, ep, M, N, K, splits, s);
     else e = launch_umma3<true, true>(A, B, ep, M, N, K, splits, s);
-    R2D2_CUDA_CHECK(e);
-    return R2D2_OK;
-}
-
-/* C[M][N] = A x B^T for plain fp32 matrices.  a_major/b_major: 0 = K-major ([rows][K]), 1 = transposed
- * storage ([K][rows]).  splits > 1: C must hold splits*M*N floats (partials, caller reduces). */
-int r2d2_debug_gemm(int backend, int ubn, int a_major, int b_major, int M, int N, int K, const float* A, const float* B,
-                    float* C, int splits, void* stream) {
-    R2D2_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0 && splits >= 1, "bad arguments");
-    R2D2_REQUIRE(N % 4 == 0 && (a_major == 0 ? K % 4 == 0 : M % 4 == 0) && (b_major == 0 ? K % 4 == 0 : N % 4 == 0), "alignment");
-    cudaStream_t s = as_stream(stream);
-    cudaError_t e;
-    if (a_major == 0 && b_major == 0) e = debug_run(backend, ubn, MatK{A, M, K, K}, MatK{B, N, K, K}, C, M, N, K, splits, C, s);
-    else if (a_major == 0) e = debug_run(backend, ubn, MatK{A, M, K, K}, MatM{B, N, K, N}, C, M, N, K, splits, C, s);
-    else if (b_major == 0) e = debug_run(backend, ubn, MatM{A, M, K, M}, MatK{B, N, K, K}, C, M, N, K, splits, C, s);
-    else e = debug_run(backend, ubn, MatM{A, M, K, M}, MatM{B, N, K, N}, C, M, N, K, splits, C, s);
     R2D2_CUDA_CHECK(e);
     return R2D2_OK;
 }

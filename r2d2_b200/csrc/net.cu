@@ -40,6 +40,7 @@ constexpr int G4 = 4 * H;
 constexpr int LATENT = 512;
 constexpr int FLAT3 = 3136;     // 7*7*64
 constexpr int NPARAM = 20;
+constexpr int kDW = 32;          // slots per row of d(dueling output): A advantage gradients + 1 value gradient, A <= 31
 constexpr int kRecSplits = 8;   // split-K of the BPTT recurrence GEMM (K = 2048) across CTAs
 
 enum ParamId {
@@ -66,6 +67,13 @@ struct Acts {
 };
 static inline SplitC ro(const SplitW& w) { return SplitC{w.hi, w.lo}; }
 
+// One pending gradient reduction: `splits` partial tensors [M][N] (weights: routed into the reference layout by `kind`;
+// biases: M = 1, kind = kFinBias + BiasKind).  All reductions of a backward pass are deferred into ONE launch per group
+// (dense layers, conv layers) of finalize_grads_kernel instead of one or two small launches per parameter tensor.
+constexpr int kFinMax = 20, kFinBias = 100;
+struct FinSeg { const float* part; int splits, M, N, kind, sl, block0; float scale; long long o0, o1; };
+struct FinArgs { FinSeg seg[kFinMax]; int nseg, nblocks; };
+
 }  // namespace r2d2
 
 struct r2d2_net {
@@ -80,7 +88,8 @@ struct r2d2_net {
     // backward scratch
     r2d2::SplitW dhid, DG, dlat, dpre3, dpre2, dpre1g;   // dpre*: pre-activation grads on the layer's INPUT grid (9x9x64, 10x10x64, 21x21x32), junk pixels stay 0
     float *dH, *dhrec, *dcrec, *dout16, *ws, *colws, *rec_partial;
-    size_t ws_floats, colws_floats;
+    size_t ws_floats, colws_floats, ws_used, colws_used;     // ws / colws are bump-allocated per backward pass (one region per pending reduction)
+    r2d2::FinArgs pend;                                       // reductions launched by the next flush
     void* dense_grads_event;         // optional cudaEvent_t recorded in r2d2_net_backward once every non-conv gradient is final
     const float* hidden;             // last forward's stored state (caller-owned, alive until backward)
 };
@@ -182,7 +191,7 @@ __global__ void s2d_kernel(const uint8_t* __restrict__ obs, bf16* __restrict__ s
 
 // row maps + sequence lengths (block 0) + split copy of h0 (other blocks).  model.py:102-111 (shifted rows) and model.py:143.
 __global__ void prep_rows_kernel(const uint8_t* __restrict__ burn, const uint8_t* __restrict__ learn,
-                                 const uint8_t* __restrict__ fwd, const float* __restrict__ hidden, SplitW h0a, SplitW h0b, int B, int F,
+                                 const uint8_t* __restrict__ fwd, const float* __restrict__ hidden, SplitW h0a, SplitW h0b, int B, int T, int F,
                                  int Rmax, int* __restrict__ row_src, int* __restrict__ len_full, int* __restrict__ len_learn,
                                  int* __restrict__ d_rows) {
     extern __shared__ int s_off[];
@@ -204,11 +213,12 @@ __global__ void prep_rows_kernel(const uint8_t* __restrict__ burn, const uint8_t
     __syncthreads();
     for (int n = threadIdx.x; n < B; n += blockDim.x) {
         const int b = burn[n], l = learn[n], f = fwd[n];
-        len_full[n] = b + l + f;
-        len_learn[n] = b + l;
-        for (int i = 0; i < l; ++i) {
-            row_src[s_off[n] + i] = (b + i) * B + n;
-            row_src[Rmax + s_off[n] + i] = min(b + F + i, b + l + f - 1) * B + n;
+        const int tot = min(b + l + f, T);                           // a sequence longer than the workspace is truncated, never read past it
+        len_full[n] = tot;
+        len_learn[n] = min(b + l, T);
+        for (int i = 0; i < l && s_off[n] + i < Rmax; ++i) {
+            row_src[s_off[n] + i] = min(b + i, T - 1) * B + n;
+            row_src[Rmax + s_off[n] + i] = max(0, min(b + F + i, tot - 1)) * B + n;
         }
     }
 }
@@ -224,8 +234,8 @@ __global__ void state_after_kernel(SplitC Hs, const float* __restrict__ Cs, int 
 }
 
 // U side columns: one-hot last action, last reward, zero pad  (model.py:92)
-__global__ void side_columns_kernel(SplitW U, const uint8_t* __restrict__ last_action, const float* __restrict__ last_reward,
-                                    int B, int T, int A, int KU) {
+__global__ void side_columns_kernel(SplitW U, SplitW U2 /* second slot or {nullptr, nullptr} */, const uint8_t* __restrict__ last_action,
+                                    const float* __restrict__ last_reward, int B, int T, int A, int KU) {
     const int row = blockIdx.x;                 // time-major row t*B + b
     const int t = row / B, b = row % B;
     const int f = b * T + t;
@@ -234,13 +244,19 @@ __global__ void side_columns_kernel(SplitW U, const uint8_t* __restrict__ last_a
         if (k < LATENT + A) v = last_action[(size_t)f * A + (k - LATENT)] ? 1.f : 0.f;
         else if (k == LATENT + A) v = last_reward[f];
         put_split(U, (size_t)row * KU + k, v);
+        if (U2.hi) put_split(U2, (size_t)row * KU + k, v);
     }
 }
 
 // dueling output layer: one warp per row.  model.py:115-117
-__global__ void head_out_kernel(SplitC hid, size_t row_offset, const float* __restrict__ Wa2, const float* __restrict__ ba2,
-                                const float* __restrict__ Wv2, const float* __restrict__ bv2, int rows_cap, int A,
-                                float* __restrict__ q_out) {
+struct HeadJob { SplitC hid; size_t row_offset; const float *Wa2, *ba2, *Wv2, *bv2; float* q_out; };
+struct HeadJobs { HeadJob job[3]; };
+__global__ void head_out_kernel(const HeadJobs jobs, int rows_cap, int A) {
+    const HeadJob& jb = jobs.job[blockIdx.y];
+    const SplitC hid = jb.hid;
+    const size_t row_offset = jb.row_offset;
+    const float *Wa2 = jb.Wa2, *ba2 = jb.ba2, *Wv2 = jb.Wv2, *bv2 = jb.bv2;
+    float* q_out = jb.q_out;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= rows_cap) return;
     const size_t base = (row_offset + warp) * 2 * H;
@@ -251,8 +267,7 @@ __global__ void head_out_kernel(SplitC hid, size_t row_offset, const float* __re
     split_load8(hid.hi, hid.lo, base + lane * PER + 8, ha + 8);
     split_load8(hid.hi, hid.lo, base + H + lane * PER, hv);
     split_load8(hid.hi, hid.lo, base + H + lane * PER + 8, hv + 8);
-    float adv[16];
-    float sum = 0.f;
+    float mine = 0.f, sum = 0.f;                                      // lane a keeps advantage a (A <= 32)
     for (int a = 0; a < A; ++a) {
         float s = 0.f;
         const float4* w = reinterpret_cast<const float4*>(Wa2 + a * H + lane * PER);
@@ -263,8 +278,9 @@ __global__ void head_out_kernel(SplitC hid, size_t row_offset, const float* __re
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        adv[a] = s + ba2[a];
-        sum += adv[a];
+        s += ba2[a];
+        if (lane == a) mine = s;
+        sum += s;
     }
     float v = 0.f;
     {
@@ -279,8 +295,7 @@ __global__ void head_out_kernel(SplitC hid, size_t row_offset, const float* __re
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     v += bv2[0];
     const float mean = sum / (float)A;
-    if (lane == 0)
-        for (int a = 0; a < A; ++a) q_out[(size_t)warp * A + a] = v + adv[a] - mean;
+    if (lane < A) q_out[(size_t)warp * A + lane] = v + mine - mean;
 }
 
 // backward of the dueling output layer: dq -> (dadv | dval) and masked d(hidden layer)
@@ -288,9 +303,9 @@ __global__ void head_out_bwd_kernel(const float* __restrict__ dq, SplitC hid, co
                                     const float* __restrict__ Wv2, const int* __restrict__ d_rows, int A,
                                     float* __restrict__ dout16, SplitW dhid) {
     const int r = blockIdx.x;
-    __shared__ float s_d[16];
+    __shared__ float s_d[kDW];
     const bool live = r < *d_rows;
-    if (threadIdx.x < 16) {
+    if (threadIdx.x < kDW) {
         float v = 0.f;
         if (live) {
             float tot = 0.f;
@@ -300,7 +315,7 @@ __global__ void head_out_bwd_kernel(const float* __restrict__ dq, SplitC hid, co
             else if (a == A) v = tot;                                   // d val
         }
         s_d[threadIdx.x] = v;
-        dout16[(size_t)r * 16 + threadIdx.x] = v;
+        dout16[(size_t)r * kDW + threadIdx.x] = v;
     }
     __syncthreads();
     for (int j = threadIdx.x; j < 2 * H; j += blockDim.x) {
@@ -314,26 +329,26 @@ __global__ void head_out_bwd_kernel(const float* __restrict__ dq, SplitC hid, co
     }
 }
 
-// layer-2 head weight gradients: [A+1][1024] = dout16^T . hid  (42 MFLOP: CUDA cores, row-chunk partials)
+// layer-2 head weight gradients: [A+1 (padded to kDW)][1024] = dout^T . hid  (CUDA cores, row-chunk partials)
 __global__ void head_w2_grad_kernel(const float* __restrict__ dout16, SplitC hid, int Rmax, int chunk, float* __restrict__ ws) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;          // column of hid, 0..1023
     const int p = blockIdx.y;
     const int r0 = p * chunk, r1 = min(Rmax, r0 + chunk);
-    float acc[16];
+    float acc[kDW];
 #pragma unroll
-    for (int a = 0; a < 16; ++a) acc[a] = 0.f;
+    for (int a = 0; a < kDW; ++a) acc[a] = 0.f;
     for (int r = r0; r < r1; ++r) {
         const float h = split_load(hid.hi, hid.lo, (size_t)r * 2 * H + j);
-        const float4* d = reinterpret_cast<const float4*>(dout16 + (size_t)r * 16);
+        const float4* d = reinterpret_cast<const float4*>(dout16 + (size_t)r * kDW);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < kDW / 4; ++q) {
             const float4 dv = __ldg(d + q);
             acc[4 * q] = fmaf(dv.x, h, acc[4 * q]); acc[4 * q + 1] = fmaf(dv.y, h, acc[4 * q + 1]);
             acc[4 * q + 2] = fmaf(dv.z, h, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(dv.w, h, acc[4 * q + 3]);
         }
     }
 #pragma unroll
-    for (int a = 0; a < 16; ++a) ws[((size_t)p * 16 + a) * 2 * H + j] = acc[a];
+    for (int a = 0; a < kDW; ++a) ws[((size_t)p * kDW + a) * 2 * H + j] = acc[a];
 }
 
 // LSTM cell epilogue fused into the recurrent GEMM (gate-interleaved columns: n = 4*j + gate)
@@ -467,35 +482,10 @@ struct Epi2ScatterRows {
     }
 };
 
-// split-K reduce + routing of a weight gradient into the reference's parameter layout
+// routing of a reduced weight-gradient entry (m, n) into the reference's parameter layout
 enum RouteKind { R_C1, R_C2, R_C3, R_FC, R_WIH, R_WHH, R_H0, R_H2, R_C1W, R_C2W, R_C3W };   // R_C*W: window wgrad partials [tap*IC + c][out channel]
-// SL = 8: block = 32 consecutive outputs x 8 slices of the split index (many splits, few outputs: the window wgrads);
-// SL = 1: one thread per output.  Fixed summation order either way.
-template <int SL>
-__global__ void __launch_bounds__(256) reduce_route_kernel(const float* __restrict__ ws, int splits, int M, int N, int kind, float* __restrict__ g,
-                                                           const int64_t* __restrict__ off, int A, int C, float scale) {
-    int64_t i;
-    float s = 0.f;
-    if constexpr (SL == 1) {
-        i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-        if (i >= (int64_t)M * N) return;
-        for (int z = 0; z < splits; ++z) s += ws[(size_t)z * M * N + i];
-    } else {
-        __shared__ float sm[SL][33];
-        const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-        i = blockIdx.x * 32ll + tx;
-        const bool in = i < (int64_t)M * N;
-        float acc = 0.f;
-        if (in)
-            for (int z = ty; z < splits; z += SL) acc += ws[(size_t)z * M * N + i];
-        sm[ty][tx] = acc;
-        __syncthreads();
-        if (ty != 0 || !in) return;
-#pragma unroll
-        for (int y = 0; y < SL; ++y) s += sm[y][tx];
-    }
-    int m = i / N, n = i % N;
-    s *= scale;
+enum BiasKind { B_PLAIN, B_LSTM, B_H0, B_H2 };
+__device__ __forceinline__ void route_weight(int kind, int m, int n, float s, float* __restrict__ g, const int64_t* __restrict__ off, int A, int C) {
     if (kind >= R_C1W) { const int t = m; m = n; n = t; kind = kind == R_C1W ? R_C1 : kind == R_C2W ? R_C2 : R_C3; }   // (k, out) -> (out, k)
     const int KIH = LATENT + A + 1;
     switch (kind) {
@@ -514,6 +504,58 @@ __global__ void __launch_bounds__(256) reduce_route_kernel(const float* __restri
         case R_H0: { if (m < H) g[off[P_A0W] + (int64_t)m * H + n] = s; else g[off[P_V0W] + (int64_t)(m - H) * H + n] = s; } break;
         case R_H2: { if (m < A && n < H) g[off[P_A2W] + m * H + n] = s; else if (m == A && n >= H) g[off[P_V2W] + n - H] = s; } break;
     }
+}
+__device__ __forceinline__ void route_bias(int kind, int n, float s, float* __restrict__ g, int64_t o0, int64_t o1, int A) {
+    switch (kind) {
+        case B_PLAIN: g[o0 + n] = s; break;
+        case B_LSTM: { const int row = (n & 3) * H + (n >> 2); g[o0 + row] = s; g[o1 + row] = s; } break;   // b_ih and b_hh
+        case B_H0: { if (n < H) g[o0 + n] = s; else g[o1 + n - H] = s; } break;
+        case B_H2: { if (n < A) g[o0 + n] = s; else if (n == A) g[o1] = s; } break;
+    }
+}
+// All pending split reductions of one group in one launch.  Block -> segment through the block0 table; sl = 8: a block
+// reduces 32 outputs x 8 slices of the split index (many splits, few outputs: the window wgrads and every bias), sl = 1:
+// one thread per output.  Fixed summation order either way (deterministic).
+__global__ void __launch_bounds__(256) finalize_grads_kernel(const FinArgs fa, float* __restrict__ g, const int64_t* __restrict__ off, int A, int C) {
+    int si = 0;
+    for (int i = 1; i < fa.nseg; ++i)
+        if ((int)blockIdx.x >= fa.seg[i].block0) si = i;
+    const FinSeg& sg = fa.seg[si];
+    const int blk = blockIdx.x - sg.block0;
+    const int64_t MN = (int64_t)sg.M * sg.N;
+    int64_t i;
+    float s = 0.f;
+    if (sg.sl == 1) {
+        i = blk * 256ll + threadIdx.x;
+        if (i >= MN) return;
+#pragma unroll 4
+        for (int z = 0; z < sg.splits; ++z) s += __ldcs(sg.part + (size_t)z * MN + i);
+    } else {
+        __shared__ float sm[8][33];
+        const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+        i = blk * 32ll + tx;
+        const bool in = i < MN;
+        float acc = 0.f;
+        if (in) {                                   // eight independent loads in flight per thread (the chain is latency-bound otherwise)
+            const float* pp = sg.part + i;
+            float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            int z = ty;
+            for (; z + 56 < sg.splits; z += 64) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) a[u] += __ldcs(pp + (size_t)(z + 8 * u) * MN);
+            }
+            for (; z < sg.splits; z += 8) a[0] += __ldcs(pp + (size_t)z * MN);
+            acc = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+        }
+        sm[ty][tx] = acc;
+        __syncthreads();
+        if (ty != 0 || !in) return;
+#pragma unroll
+        for (int y = 0; y < 8; ++y) s += sm[y][tx];
+    }
+    s *= sg.scale;
+    if (sg.kind >= kFinBias) route_bias(sg.kind - kFinBias, (int)i, s, g, sg.o0, sg.o1, A);
+    else route_weight(sg.kind, (int)(i / sg.N), (int)(i % sg.N), s, g, off, A, C);
 }
 
 // deterministic column sums of a (split or fp32) [M][N] tensor: partial[p][n] over row chunk p, then final routing.
@@ -564,76 +606,83 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __rest
         }
     }
 }
-enum BiasKind { B_PLAIN, B_LSTM, B_H0, B_H2 };
-// final fixed-order reduction of P partial rows; block = 32 columns x 8 slices of the partial index
-__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ part, int P, int N, int kind, float* __restrict__ g,
-                                                           int64_t o0, int64_t o1, int A) {
-    __shared__ float sm[8][33];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int n = blockIdx.x * 32 + tx;
-    float acc = 0.f;
-    if (n < N)
-        for (int p = ty; p < P; p += 8) acc += part[(size_t)p * N + n];
-    sm[ty][tx] = acc;
-    __syncthreads();
-    if (ty != 0 || n >= N) return;
-    float s = 0.f;
-#pragma unroll
-    for (int y = 0; y < 8; ++y) s += sm[y][tx];
-    switch (kind) {
-        case B_PLAIN: g[o0 + n] = s; break;
-        case B_LSTM: { const int row = (n & 3) * H + (n >> 2); g[o0 + row] = s; g[o1 + row] = s; } break;   // b_ih and b_hh
-        case B_H0: { if (n < H) g[o0 + n] = s; else g[o1 + n - H] = s; } break;
-        case B_H2: { if (n < A) g[o0 + n] = s; else if (n == A) g[o1] = s; } break;
-    }
-}
-
 constexpr int kColP = 128;
-static cudaError_t colsum_split(SplitC S, int M, int N, int kind, float* g, int64_t o0, int64_t o1, int A, float* colws, cudaStream_t s) {
-    const int chunk = (M + kColP - 1) / kColP;
-    const int groups = N / 8, gpb = groups < 32 ? groups : 32;
-    dim3 grid((groups + gpb - 1) / gpb, kColP);
-    colsum_partial_kernel<true><<<grid, 256, 0, s>>>(nullptr, S, M, N, chunk, colws);
-    colsum_final_kernel<<<(N + 31) / 32, 256, 0, s>>>(colws, kColP, N, kind, g, o0, o1, A);
-    return cudaGetLastError();
-}
-static cudaError_t colsum_f32(const float* X, int M, int N, int kind, float* g, int64_t o0, int64_t o1, int A, float* colws, cudaStream_t s) {
-    const int chunk = (M + kColP - 1) / kColP;
-    dim3 grid((N + 31) / 32, kColP);
-    colsum_partial_kernel<false><<<grid, 256, 0, s>>>(X, SplitC{nullptr, nullptr}, M, N, chunk, colws);
-    colsum_final_kernel<<<(N + 31) / 32, 256, 0, s>>>(colws, kColP, N, kind, g, o0, o1, A);
-    return cudaGetLastError();
-}
 
 }  // namespace r2d2
 
 using namespace r2d2;
 
-template <int UBN, int POL = LO_STRICT, class AS, class BS>
-static cudaError_t wgrad2(const AS& a, const BS& b, int M, int N, int K, int splits, int kind, r2d2_net* net, float* grads,
-                          const int64_t* d_off, float scale, cudaStream_t s) {
-    if ((size_t)splits * M * N > net->ws_floats) return cudaErrorInvalidValue;
-    Epi2Partial ep{net->ws, M, N};
-    cudaError_t e = launch_umma2<UBN, POL>(a, b, ep, M, N, K, splits, s);
-    if (e != cudaSuccess) return e;
-    const int64_t tot = (int64_t)M * N;
-    if (splits >= 16) reduce_route_kernel<8><<<cdiv(tot, 32), 256, 0, s>>>(net->ws, splits, M, N, kind, grads, d_off, net->A, net->C, scale);
-    else reduce_route_kernel<1><<<cdiv(tot, 256), 256, 0, s>>>(net->ws, splits, M, N, kind, grads, d_off, net->A, net->C, scale);
+// ---- deferred reductions: bump allocation of the partial workspaces + the pending-segment list of a handle
+static float* ws_take(r2d2_net* n, size_t floats) {
+    const size_t a = (n->ws_used + 63) & ~(size_t)63;
+    if (a + floats > n->ws_floats) return nullptr;
+    n->ws_used = a + floats;
+    return n->ws + a;
+}
+static float* colws_take(r2d2_net* n, size_t floats) {
+    const size_t a = (n->colws_used + 63) & ~(size_t)63;
+    if (a + floats > n->colws_floats) return nullptr;
+    n->colws_used = a + floats;
+    return n->colws + a;
+}
+static cudaError_t fin_add(r2d2_net* n, const float* part, int splits, int M, int N, int kind, float scale, int64_t o0 = 0, int64_t o1 = 0) {
+    FinArgs& fa = n->pend;
+    if (fa.nseg >= kFinMax) return cudaErrorInvalidValue;
+    const int sl = (splits >= 16 || kind >= kFinBias) ? 8 : 1;
+    FinSeg& sg = fa.seg[fa.nseg++];
+    sg = FinSeg{part, splits, M, N, kind, sl, fa.nblocks, scale, (long long)o0, (long long)o1};
+    fa.nblocks += cdiv((int64_t)M * N, sl == 8 ? 32 : 256);
+    return cudaSuccess;
+}
+static cudaError_t fin_flush(r2d2_net* n, float* grads, const int64_t* d_off, cudaStream_t s) {
+    FinArgs& fa = n->pend;
+    if (fa.nseg == 0) return cudaSuccess;
+    finalize_grads_kernel<<<fa.nblocks, 256, 0, s>>>(fa, grads, d_off, n->A, n->C);
+    fa.nseg = 0;
+    fa.nblocks = 0;
     return cudaGetLastError();
+}
+static void fin_begin(r2d2_net* n) { n->ws_used = 0; n->colws_used = 0; n->pend.nseg = 0; n->pend.nblocks = 0; }
+
+// column sums (bias gradients) of a split / fp32 [M][N] tensor: partial rows now, final reduction deferred
+static cudaError_t colsum_split(SplitC S, int M, int N, int kind, int64_t o0, int64_t o1, r2d2_net* n, cudaStream_t s) {
+    float* part = colws_take(n, (size_t)kColP * N);
+    if (!part) return cudaErrorInvalidValue;
+    const int chunk = (M + kColP - 1) / kColP;
+    const int groups = N / 8, gpb = groups < 32 ? groups : 32;
+    dim3 grid((groups + gpb - 1) / gpb, kColP);
+    colsum_partial_kernel<true><<<grid, 256, 0, s>>>(nullptr, S, M, N, chunk, part);
+    cudaError_t e = cudaGetLastError();
+    return e != cudaSuccess ? e : fin_add(n, part, kColP, 1, N, kFinBias + kind, 1.f, o0, o1);
+}
+static cudaError_t colsum_f32(const float* X, int M, int N, int kind, int64_t o0, int64_t o1, r2d2_net* n, cudaStream_t s) {
+    float* part = colws_take(n, (size_t)kColP * N);
+    if (!part) return cudaErrorInvalidValue;
+    const int chunk = (M + kColP - 1) / kColP;
+    dim3 grid((N + 31) / 32, kColP);
+    colsum_partial_kernel<false><<<grid, 256, 0, s>>>(X, SplitC{nullptr, nullptr}, M, N, chunk, part);
+    cudaError_t e = cudaGetLastError();
+    return e != cudaSuccess ? e : fin_add(n, part, kColP, 1, N, kFinBias + kind, 1.f, o0, o1);
+}
+
+template <int UBN, int POL = LO_STRICT, class AS, class BS>
+static cudaError_t wgrad2(const AS& a, const BS& b, int M, int N, int K, int splits, int kind, r2d2_net* net, float scale, cudaStream_t s) {
+    float* ws = ws_take(net, (size_t)splits * M * N);
+    if (!ws) return cudaErrorInvalidValue;
+    Epi2Partial ep{ws, M, N};
+    cudaError_t e = launch_umma2<UBN, POL>(a, b, ep, M, N, K, splits, s);
+    return e != cudaSuccess ? e : fin_add(net, ws, splits, M, N, kind, scale);
 }
 
 // plain-matrix weight gradient on CTA pairs (umma3.cuh): both operands MN-major ([K][rows] storage)
 template <int POL = LO_STRICT>
-static cudaError_t wgrad3(const Mat3& a, const Mat3& b, int M, int N, int K, int splits, int kind, r2d2_net* net, float* grads,
-                          const int64_t* d_off, float scale, cudaStream_t s) {
+static cudaError_t wgrad3(const Mat3& a, const Mat3& b, int M, int N, int K, int splits, int kind, r2d2_net* net, float scale, cudaStream_t s) {
     splits = umma3_effective_splits(K, splits);
-    if ((size_t)splits * M * N > net->ws_floats) return cudaErrorInvalidValue;
-    Epi2Partial ep{net->ws, M, N};
+    float* ws = ws_take(net, (size_t)splits * M * N);
+    if (!ws) return cudaErrorInvalidValue;
+    Epi2Partial ep{ws, M, N};
     cudaError_t e = launch_umma3<true, true, POL>(a, b, ep, M, N, K, splits, s);
-    if (e != cudaSuccess) return e;
-    const int64_t tot = (int64_t)M * N;
-    reduce_route_kernel<1><<<cdiv(tot, 256), 256, 0, s>>>(net->ws, splits, M, N, kind, grads, d_off, net->A, net->C, scale);
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : fin_add(net, ws, splits, M, N, kind, scale);
 }
 
 // 1 (default): the plain-matrix GEMMs (FC, input projection, their data / weight gradients) run on CTA pairs with TMA
@@ -643,6 +692,7 @@ int g_pair_gemm = [] { const char* e = getenv("R2D2_PAIR_GEMM"); return (e && e[
 // 1 (default): forward recurrence inside 16-CTA clusters (recurrence2.cuh: W_hh resident in TMEM + shared memory, h exchanged
 // over distributed shared memory); 0: the L2-flag persistent kernel of recurrence.cuh.  R2D2_CLUSTER_REC=0 / r2d2_set_cluster_recurrence.
 int g_cluster_recurrence = [] { const char* e = getenv("R2D2_CLUSTER_REC"); return (e && e[0] == '0') ? 0 : 1; }();
+namespace r2d2 { int g_config_epoch = 0; }
 namespace r2d2 { int g_rec2_ns = [] { const char* e = getenv("R2D2_REC2_NS"); return e ? atoi(e) : 0; }(); }   // sequences per recurrence cluster: 0 auto, 16, 32
 int g_persistent_recurrence = 1;
 unsigned long long* g_rec_trace = nullptr;   // debug: device buffer [T][8] of step timestamps (r2d2_debug_rec_trace)     // 0: per-step launches (also the path for B > 64)
@@ -667,7 +717,7 @@ static void free_s(SplitW& w) { cudaFree(w.hi); cudaFree(w.lo); }
 extern "C" {
 
 int r2d2_net_param_layout(int A, int C, int64_t* offsets_out /* [21] */) {
-    R2D2_REQUIRE(offsets_out && A >= 1 && A <= 32 && C >= 1 && C <= 16, "bad arguments");
+    R2D2_REQUIRE(offsets_out && A >= 1 && A <= 31 && C >= 1 && C <= 16, "bad arguments");
     int64_t n[NPARAM];
     param_sizes(A, C, n);
     int64_t o = 0;
@@ -677,9 +727,9 @@ int r2d2_net_param_layout(int A, int C, int64_t* offsets_out /* [21] */) {
 }
 
 int r2d2_net_create(int B, int T, int C, int A, int Lmax, int max_forward, r2d2_net** out) {
-    R2D2_REQUIRE(out && B >= 1 && B <= 4096 && T >= 1 && T <= 255 && (C == 1 || C == 4) && A >= 1 && A <= 15 && Lmax >= 1 &&
+    R2D2_REQUIRE(out && B >= 1 && B <= 4096 && T >= 1 && T <= 255 && (C == 1 || C == 4) && A >= 1 && A <= 31 && Lmax >= 1 &&
                      Lmax <= T && max_forward >= 0,
-                 "bad shape (frame channels must be 1 or 4, action_dim <= 15)");
+                 "bad shape (frame channels must be 1 or 4, action_dim <= 31: the full ALE action set has 18)");
     r2d2_net* n = new r2d2_net();
     memset(n, 0, sizeof(*n));
     n->B = B; n->T = T; n->C = C; n->A = A; n->Lmax = Lmax; n->F = max_forward;
@@ -718,17 +768,18 @@ int r2d2_net_create(int B, int T, int C, int A, int Lmax, int max_forward, r2d2_
     rc |= alloc_s(&n->dhid, (size_t)n->Rmax * 2 * H); rc |= alloc_s(&n->DG, TB * G4); rc |= alloc_s(&n->dlat, NF * LATENT);
     rc |= alloc_s(&n->dpre3, NF * 5184); rc |= alloc_s(&n->dpre2, NF * 6400); rc |= alloc_s(&n->dpre1g, NF * 14112);   // gradient grids (see struct)
     rc |= alloc_f(&n->dH, TB * H); rc |= alloc_f(&n->dhrec, (size_t)kRecSplits * B * H); rc |= alloc_f(&n->dcrec, (size_t)B * H);
-    rc |= alloc_f(&n->dout16, (size_t)n->Rmax * 16); rc |= alloc_f(&n->rec_partial, 2ull * 8 * 64 * H);
-    {   // split-K / chunk-partial workspace: 128 MB covers the batch-64 shapes; the conv weight-gradient kernels write one
-        // partial per <= 4096-pixel chunk, so very large batches need more (sized here, checked again at launch)
+    rc |= alloc_f(&n->dout16, (size_t)n->Rmax * kDW); rc |= alloc_f(&n->rec_partial, 2ull * 8 * 64 * H);
+    {   // partial workspaces of one backward pass: every pending reduction keeps its own region until the flush (sizes as in
+        // r2d2_net_backward: split counts of the dense weight gradients, one partial per <= 4096-pixel chunk of the conv ones)
         auto chunks = [](size_t rows, size_t chunk) { return (rows + chunk - 1) / chunk; };
-        size_t need = 32ull << 20;
-        need = std::max(need, chunks(NF * 441, 4096) * 256 * 32);        // conv1: [taps*64][32] per chunk
-        need = std::max(need, chunks(NF * 100, 3712) * 512 * 64);        // conv2
-        need = std::max(need, chunks(NF * 81, 3072) * 576 * 64);         // conv3
-        need = std::max(need, chunks(NF * 441, 4096) * 32 * 64 * (size_t)C);   // conv1 at C = 1 (im2col split-K)
-        n->ws_floats = need;
-        n->colws_floats = std::max((size_t)kColP * 4096, chunks(NF * 100, 3712) * 64 + chunks(NF * 441, 4096) * 64);
+        auto up = [](size_t x) { return (x + 63) & ~(size_t)63; };
+        const size_t spl = std::max<size_t>(4, chunks(TB, 4096));
+        size_t need = up(128ull * kDW * 2 * H) + up(4ull * 2 * H * H) + up(spl * G4 * H) + up(spl * G4 * n->KU) + up(spl * LATENT * FLAT3);
+        need += up(chunks(NF * 81, 3072) * 576 * 64) + up(chunks(NF * 100, 3712) * 512 * 64);
+        need += up(std::max(chunks(NF * 441, 4096) * 256 * 32, chunks(NF * 441, 4096) * 32 * 64 * (size_t)C));
+        n->ws_floats = need + 1024;
+        n->colws_floats = up((size_t)kColP * kDW) + up((size_t)kColP * 2 * H) + up((size_t)kColP * G4) + up((size_t)kColP * LATENT) + up((size_t)kColP * 32) +
+                          up(chunks(NF * 81, 3072) * 64) + up(chunks(NF * 100, 3712) * 64) + up(chunks(NF * 441, 4096) * 32) + 1024;
     }
     rc |= alloc_f(&n->ws, n->ws_floats); rc |= alloc_f(&n->colws, n->colws_floats);
     if (rc) return rc;
@@ -867,16 +918,16 @@ struct EpiWinDgrad2 {
 // window weight gradient + split reduction into the reference layout
 // (+ the layer's bias gradient = column sums of G, from the same kernel)
 template <int GW, int IC, int KH, int KW, int TG, int NO, bool X_HAS_LO, int KP>
-static cudaError_t winwgrad(SplitC X, SplitC G, long long R, int chunk, int kind, int64_t bias_off, r2d2_net* net, float* grads,
-                            const int64_t* d_off, float scale, cudaStream_t s) {
+static cudaError_t winwgrad(SplitC X, SplitC G, long long R, int chunk, int kind, int64_t bias_off, r2d2_net* net, float scale, cudaStream_t s) {
     constexpr int M = KH * KW * IC;
     const int splits = (int)((R + chunk - 1) / chunk);
-    if ((size_t)splits * M * NO > net->ws_floats || (size_t)splits * NO > net->colws_floats || chunk % KP) return cudaErrorInvalidValue;
-    cudaError_t e = launch_winwgrad<GW, IC, KH, KW, TG, NO, X_HAS_LO, KP, true>(X, G, R, chunk, net->ws, net->colws, s);
+    float* ws = ws_take(net, (size_t)splits * M * NO);
+    float* bws = colws_take(net, (size_t)splits * NO);
+    if (!ws || !bws || chunk % KP) return cudaErrorInvalidValue;
+    cudaError_t e = launch_winwgrad<GW, IC, KH, KW, TG, NO, X_HAS_LO, KP, true>(X, G, R, chunk, ws, bws, s);
     if (e != cudaSuccess) return e;
-    reduce_route_kernel<8><<<cdiv((int64_t)M * NO, 32), 256, 0, s>>>(net->ws, splits, M, NO, kind, grads, d_off, net->A, net->C, scale);
-    colsum_final_kernel<<<(NO + 31) / 32, 256, 0, s>>>(net->colws, splits, NO, B_PLAIN, grads, bias_off, 0, net->A);
-    return cudaGetLastError();
+    e = fin_add(net, ws, splits, M, NO, kind, scale);
+    return e != cudaSuccess ? e : fin_add(net, bws, splits, 1, NO, kFinBias + B_PLAIN, 1.f, bias_off, 0);
 }
 
 struct FwdArgs {
@@ -924,24 +975,24 @@ static cudaError_t conv1_forward_pair(r2d2_net* n, const float* p0, const float*
     return launch_umma2<64, LO_WEIGHT_B>(a, b, e, n->NF * 400, 64, 64 * CH, 1, s);
 }
 template <int CH>
-static cudaError_t conv1_wgrad(r2d2_net* n, float* grads, cudaStream_t s) {
+static cudaError_t conv1_wgrad(r2d2_net* n, cudaStream_t s) {
     const long long NP = (long long)n->NF * 441;               // dpre1g lives on the 21x21 s2d grid (junk row/column are zero)
     if constexpr (CH == 4) {
-        return winwgrad<21, 64, 2, 2, 4, 32, false, 128>(SplitC{n->s2d, nullptr}, ro(n->dpre1g), NP, 4096, R_C1W, n->off[P_C1B], n, grads, g_doff[n], 1.f / 255.f, s);
+        return winwgrad<21, 64, 2, 2, 4, 32, false, 128>(SplitC{n->s2d, nullptr}, ro(n->dpre1g), NP, 4096, R_C1W, n->off[P_C1B], n, 1.f / 255.f, s);
     } else {
         SrcMatMN a{n->dpre1g.hi, n->dpre1g.lo, 32, (int)NP, 32};
         SrcConvMN<21, 21, 16 * CH, 21, 21, 2, 2, 1, false> b{n->s2d, nullptr, n->NF};       // junk pixels read the slack rows: finite x 0
         const int splits = (int)((NP + 4095) / 4096);
-        cudaError_t e = wgrad2<64, LO_NO_WEIGHT>(a, b, 32, 64 * CH, (int)NP, splits, R_C1, n, grads, g_doff[n], 1.f / 255.f, s);
+        cudaError_t e = wgrad2<64, LO_NO_WEIGHT>(a, b, 32, 64 * CH, (int)NP, splits, R_C1, n, 1.f / 255.f, s);
         if (e != cudaSuccess) return e;
-        return colsum_split(ro(n->dpre1g), (int)NP, 32, B_PLAIN, grads, n->off[P_C1B], 0, n->A, n->colws, s);
+        return colsum_split(ro(n->dpre1g), (int)NP, 32, B_PLAIN, n->off[P_C1B], 0, n, s);
     }
 }
 
 // frames -> space-to-depth bf16 (once per batch, shared by both slots) + row maps + h0 split
 static int net_prep(r2d2_net* n, const uint8_t* obs, const float* hidden, const uint8_t* burn, const uint8_t* learn,
                     const uint8_t* fwd, cudaStream_t s) {
-    prep_rows_kernel<<<1 + 32, 256, (n->B + 1) * sizeof(int), s>>>(burn, learn, fwd, hidden, n->ac[0].HsX, n->ac[1].HsX, n->B, n->F, n->Rmax, n->row_src,
+    prep_rows_kernel<<<1 + 32, 256, (n->B + 1) * sizeof(int), s>>>(burn, learn, fwd, hidden, n->ac[0].HsX, n->ac[1].HsX, n->B, n->T, n->F, n->Rmax, n->row_src,
                                                              n->len_full, n->len_learn, n->d_rows);
     if (obs) {                                             // obs == NULL: the frames were staged by r2d2_replay_gather_s2d
         const int64_t total = (int64_t)n->NF * n->C * 441;
@@ -958,8 +1009,10 @@ static int net_encode(r2d2_net* n, int which, const FwdArgs& fa, cudaStream_t s,
     Acts& ac = n->ac[which];
     const int64_t* off = n->off;
     const float* params = fa.params;
-    side_columns_kernel<<<T * B, 32, 0, s>>>(ac.U, fa.last_action, fa.last_reward, B, T, A, KU);
-    R2D2_LAUNCH_CHECK();
+    if (!conv1_done || which == 0) {     // pair forward: slot 0's call fills the side columns of both slots (same batch)
+        side_columns_kernel<<<T * B, 32, 0, s>>>(ac.U, conv1_done ? n->ac[1].U : SplitW{nullptr, nullptr}, fa.last_action, fa.last_reward, B, T, A, KU);
+        R2D2_LAUNCH_CHECK();
+    }
     if (!conv1_done) R2D2_CUDA_CHECK(n->C == 1 ? conv1_forward<1>(n, which, params, s) : conv1_forward<4>(n, which, params, s));
     if (g_window_conv) {   // conv2 = 2x2 stride-1 window conv over the 10x10 s2d-by-2 grid of act1 (128 channels)
         EpiWinBiasSplit<10, 10, 9, 9> e{ac.act2, params + off[P_C2B]};
@@ -1051,24 +1104,25 @@ static int net_recurrence(r2d2_net* n, int which, const float* hidden, cudaStrea
 }
 
 // dueling head on the gathered rows (model.py:102-117, 143-148)
-static int net_heads(r2d2_net* n, int which, const float* params, float* q_learn_out, float* q_shift_out, cudaStream_t s) {
+static int net_heads(r2d2_net* n, int which, const float* params, float* q_learn_out, float* q_shift_out, cudaStream_t s, bool launch_out = true) {
     const int A = n->A, Rmax = n->Rmax;
     Packed& pk = n->pk[which];
     Acts& ac = n->ac[which];
     const int64_t* off = n->off;
-    {
-        SrcRowGatherK a{ac.Hs.hi, ac.Hs.lo, n->row_src, 2 * Rmax, H, H};
+    {   // rows [0, Rmax) = learning positions (q), [Rmax, 2 Rmax) = n-step-shifted positions; the target network needs only the latter
+        const int r0 = q_learn_out ? 0 : Rmax, nr = 2 * Rmax - r0;
+        SrcRowGatherK a{ac.Hs.hi, ac.Hs.lo, n->row_src + r0, nr, H, H};
         SrcMatK b{pk.Wh0.hi, pk.Wh0.lo, 2 * H, H, H};
-        Epi2BiasSplit<true> e{ac.hid, pk.bh0, 2 * Rmax, 2 * H, 2 * H, 1.f};
-        R2D2_CUDA_CHECK((launch_umma2<128>(a, b, e, 2 * Rmax, 2 * H, H, 1, s)));
+        Epi2BiasSplit<true> e{SplitW{ac.hid.hi + (size_t)r0 * 2 * H, ac.hid.lo + (size_t)r0 * 2 * H}, pk.bh0, nr, 2 * H, 2 * H, 1.f};
+        R2D2_CUDA_CHECK((launch_umma2<128>(a, b, e, nr, 2 * H, H, 1, s)));
     }
-    if (q_learn_out)
-        head_out_kernel<<<cdiv((int64_t)Rmax * 32, 256), 256, 0, s>>>(ro(ac.hid), 0, params + off[P_A2W], params + off[P_A2B],
-                                                                     params + off[P_V2W], params + off[P_V2B], Rmax, A, q_learn_out);
-    if (q_shift_out)
-        head_out_kernel<<<cdiv((int64_t)Rmax * 32, 256), 256, 0, s>>>(ro(ac.hid), (size_t)Rmax, params + off[P_A2W],
-                                                                     params + off[P_A2B], params + off[P_V2W], params + off[P_V2B],
-                                                                     Rmax, A, q_shift_out);
+    if (!launch_out) return R2D2_OK;                // the caller issues one head_out launch for several networks (net_head_out)
+    HeadJobs jobs;
+    int nj = 0;
+    const HeadJob base{ro(ac.hid), 0, params + off[P_A2W], params + off[P_A2B], params + off[P_V2W], params + off[P_V2B], nullptr};
+    if (q_learn_out) { jobs.job[nj] = base; jobs.job[nj].q_out = q_learn_out; ++nj; }
+    if (q_shift_out) { jobs.job[nj] = base; jobs.job[nj].row_offset = (size_t)Rmax; jobs.job[nj].q_out = q_shift_out; ++nj; }
+    if (nj) head_out_kernel<<<dim3(cdiv((int64_t)Rmax * 32, 256), nj), 256, 0, s>>>(jobs, Rmax, A);
     R2D2_LAUNCH_CHECK();
     return R2D2_OK;
 }
@@ -1132,8 +1186,18 @@ int r2d2_net_forward_pair(r2d2_net* n, const float* params_online, const float* 
     if (!rc) rc = net_encode(n, 0, f0, s, true);
     if (!rc) rc = net_encode(n, 1, f1, s, true);
     if (!rc) rc = net_recurrence(n, 2, hidden, s);
-    if (!rc) rc = net_heads(n, 0, params_online, q_learn_out, qn_online_out, s);
-    if (!rc) rc = net_heads(n, 1, params_target, nullptr, qn_target_out, s);
+    if (!rc) rc = net_heads(n, 0, params_online, q_learn_out, qn_online_out, s, false);
+    if (!rc) rc = net_heads(n, 1, params_target, nullptr, qn_target_out, s, false);
+    if (!rc) {      // the three Q tensors (worker.py:346,347,352) from one launch of the dueling output layer
+        const int64_t* off = n->off;
+        const int Rmax = n->Rmax;
+        auto mk = [&](int k, const float* p, size_t row0, float* out) {
+            return HeadJob{ro(n->ac[k].hid), row0, p + off[P_A2W], p + off[P_A2B], p + off[P_V2W], p + off[P_V2B], out};
+        };
+        HeadJobs jobs{{mk(0, params_online, 0, q_learn_out), mk(0, params_online, (size_t)Rmax, qn_online_out), mk(1, params_target, (size_t)Rmax, qn_target_out)}};
+        head_out_kernel<<<dim3(cdiv((int64_t)Rmax * 32, 256), 3), 256, 0, s>>>(jobs, Rmax, n->A);
+        R2D2_LAUNCH_CHECK();
+    }
     return rc;
 }
 
@@ -1150,21 +1214,25 @@ int r2d2_net_backward(r2d2_net* n, const float* params, const float* dq, float* 
     const int64_t* d_off = g_doff[n];
     const size_t TB = (size_t)T * B;
 
+    fin_begin(n);
     // ---- head
     head_out_bwd_kernel<<<Rmax, 256, 0, s>>>(dq, ro(ac.hid), params + off[P_A2W], params + off[P_V2W], n->d_rows, A, n->dout16,
                                             n->dhid);
     R2D2_LAUNCH_CHECK();
     {   // layer-2 weights: [A+1 (pad 16)] x [1024] = dout16^T . hid   (tiny: CUDA cores)
         const int P = 128, chunk = (Rmax + P - 1) / P;
-        head_w2_grad_kernel<<<dim3(2 * H / 128, P), 128, 0, s>>>(n->dout16, ro(ac.hid), Rmax, chunk, n->ws);
-        reduce_route_kernel<8><<<cdiv(16 * 2 * H, 32), 256, 0, s>>>(n->ws, P, 16, 2 * H, R_H2, grads, d_off, A, n->C, 1.f);
-        R2D2_CUDA_CHECK(colsum_f32(n->dout16, Rmax, 16, B_H2, grads, off[P_A2B], off[P_V2B], A, n->colws, s));
+        float* ws = ws_take(n, (size_t)P * kDW * 2 * H);
+        R2D2_REQUIRE(ws, "gradient workspace exhausted");
+        head_w2_grad_kernel<<<dim3(2 * H / 128, P), 128, 0, s>>>(n->dout16, ro(ac.hid), Rmax, chunk, ws);
+        R2D2_LAUNCH_CHECK();
+        R2D2_CUDA_CHECK(fin_add(n, ws, P, kDW, 2 * H, R_H2, 1.f));
+        R2D2_CUDA_CHECK(colsum_f32(n->dout16, Rmax, kDW, B_H2, off[P_A2B], off[P_V2B], n, s));
     }
     {   // layer-0 weights: [1024] x [512] = dhid^T . Hsel
         SrcMatMN a{n->dhid.hi, n->dhid.lo, 2 * H, Rmax, 2 * H};
         SrcRowGatherMN b{ac.Hs.hi, ac.Hs.lo, n->row_src, H, Rmax, H};
-        R2D2_CUDA_CHECK((wgrad2<128>(a, b, 2 * H, H, Rmax, 4, R_H0, n, grads, d_off, 1.f, s)));
-        R2D2_CUDA_CHECK(colsum_split(ro(n->dhid), Rmax, 2 * H, B_H0, grads, off[P_A0B], off[P_V0B], A, n->colws, s));
+        R2D2_CUDA_CHECK((wgrad2<128>(a, b, 2 * H, H, Rmax, 4, R_H0, n, 1.f, s)));
+        R2D2_CUDA_CHECK(colsum_split(ro(n->dhid), Rmax, 2 * H, B_H0, off[P_A0B], off[P_V0B], n, s));
     }
     R2D2_CUDA_CHECK(cudaMemsetAsync(n->dH, 0, TB * H * sizeof(float), s));
     {   // d hidden rows -> dH[t][b]
@@ -1211,13 +1279,13 @@ int r2d2_net_backward(r2d2_net* n, const float* params, const float* dq, float* 
         if (g_pair_gemm) {       // 8 x 2 (x 3) pair tiles: split K so that one wave of 74 pairs is (nearly) full, K <= 4096 per partial
             const Mat3 dg{n->DG.hi, n->DG.lo, G4, (int)TB, G4};
             const int sp = std::max(4, cdiv((long long)TB, 4096));
-            R2D2_CUDA_CHECK((wgrad3<>(dg, Mat3{ac.HsX.hi, ac.HsX.lo, H, (int)TB, H}, G4, H, (int)TB, sp, R_WHH, n, grads, d_off, 1.f, s)));
-            R2D2_CUDA_CHECK((wgrad3<>(dg, Mat3{ac.U.hi, ac.U.lo, KU, (int)TB, KU}, G4, KU, (int)TB, std::max(3, cdiv((long long)TB, 4096)), R_WIH, n, grads, d_off, 1.f, s)));
+            R2D2_CUDA_CHECK((wgrad3<>(dg, Mat3{ac.HsX.hi, ac.HsX.lo, H, (int)TB, H}, G4, H, (int)TB, sp, R_WHH, n, 1.f, s)));
+            R2D2_CUDA_CHECK((wgrad3<>(dg, Mat3{ac.U.hi, ac.U.lo, KU, (int)TB, KU}, G4, KU, (int)TB, std::max(3, cdiv((long long)TB, 4096)), R_WIH, n, 1.f, s)));
         } else {
-        R2D2_CUDA_CHECK((wgrad2<128>(a, bh, G4, H, (int)TB, 2, R_WHH, n, grads, d_off, 1.f, s)));
-        R2D2_CUDA_CHECK((wgrad2<128>(a, bu, G4, KU, (int)TB, 2, R_WIH, n, grads, d_off, 1.f, s)));
+        R2D2_CUDA_CHECK((wgrad2<128>(a, bh, G4, H, (int)TB, 2, R_WHH, n, 1.f, s)));
+        R2D2_CUDA_CHECK((wgrad2<128>(a, bu, G4, KU, (int)TB, 2, R_WIH, n, 1.f, s)));
         }
-        R2D2_CUDA_CHECK(colsum_split(ro(n->DG), (int)TB, G4, B_LSTM, grads, off[P_BIH], off[P_BHH], A, n->colws, s));
+        R2D2_CUDA_CHECK(colsum_split(ro(n->DG), (int)TB, G4, B_LSTM, off[P_BIH], off[P_BHH], n, s));
     }
     {   // d latent (ReLU-masked), frame-major
         SrcMatK a{n->DG.hi, n->DG.lo, (int)TB, G4, G4};
@@ -1234,10 +1302,11 @@ int r2d2_net_backward(r2d2_net* n, const float* params, const float* dq, float* 
         SrcMatMN b{ac.act3.hi, ac.act3.lo, FLAT3, NF, FLAT3};
         if (g_pair_gemm)     // 2 x 13 pair tiles x 2 splits: one wave
             R2D2_CUDA_CHECK((wgrad3<LO_NO_WEIGHT>(Mat3{n->dlat.hi, n->dlat.lo, LATENT, NF, LATENT}, Mat3{ac.act3.hi, ac.act3.lo, FLAT3, NF, FLAT3}, LATENT, FLAT3, NF,
-                                                  std::max(2, cdiv(NF, 4096)), R_FC, n, grads, d_off, 1.f, s)));
+                                                  std::max(2, cdiv(NF, 4096)), R_FC, n, 1.f, s)));
         else
-        R2D2_CUDA_CHECK((wgrad2<128, LO_NO_WEIGHT>(a, b, LATENT, FLAT3, NF, 2, R_FC, n, grads, d_off, 1.f, s)));
-        R2D2_CUDA_CHECK(colsum_split(ro(n->dlat), NF, LATENT, B_PLAIN, grads, off[P_FCB], 0, A, n->colws, s));
+        R2D2_CUDA_CHECK((wgrad2<128, LO_NO_WEIGHT>(a, b, LATENT, FLAT3, NF, 2, R_FC, n, 1.f, s)));
+        R2D2_CUDA_CHECK(colsum_split(ro(n->dlat), NF, LATENT, B_PLAIN, off[P_FCB], 0, n, s));
+        R2D2_CUDA_CHECK(fin_flush(n, grads, d_off, s));            // every dense-layer gradient (heads, LSTM, FC) in one reduction launch
         // every gradient from feature.7.weight to the end of the flat layout (FC, LSTM, heads: 98 % of the bytes) is final:
         // a data-parallel caller can start reducing that range while the conv layers' backward still runs
         if (n->dense_grads_event) R2D2_CUDA_CHECK(cudaEventRecord((cudaEvent_t)n->dense_grads_event, s));
@@ -1253,27 +1322,32 @@ int r2d2_net_backward(r2d2_net* n, const float* params, const float* dq, float* 
     // The conv layers run as window convolutions (winconv.cuh): gradients live on each layer's input grid.
     {   // conv3: weights from act2 (9x9 grid) x dpre3 (same grid); data gradient = 3x3 window conv of dpre3 with flipped taps
         const long long R3 = (long long)NF * 81;
-        R2D2_CUDA_CHECK((winwgrad<9, 64, 3, 3, 9, 64, true, 64>(ro(ac.act2), ro(n->dpre3), R3, 3072, R_C3W, off[P_C3B], n, grads, d_off, 1.f, s)));
+        R2D2_CUDA_CHECK((winwgrad<9, 64, 3, 3, 9, 64, true, 64>(ro(ac.act2), ro(n->dpre3), R3, 3072, R_C3W, off[P_C3B], n, 1.f, s)));
         EpiWinDgrad3 e{n->dpre2, ro(ac.act2)};
         R2D2_CUDA_CHECK((launch_winconv<9, 64, 3, 3, 64, true, true>(ro(n->dpre3), R3, SplitC{pk.W3d.hi, pk.W3d.lo}, e, s)));
     }
     {   // conv2 on the 10x10 s2d-by-2 grid of act1
         const long long R2 = (long long)NF * 100;
-        R2D2_CUDA_CHECK((winwgrad<10, 128, 2, 2, 4, 64, true, 64>(ro(ac.act1), ro(n->dpre2), R2, 3712, R_C2W, off[P_C2B], n, grads, d_off, 1.f, s)));
+        R2D2_CUDA_CHECK((winwgrad<10, 128, 2, 2, 4, 64, true, 64>(ro(ac.act1), ro(n->dpre2), R2, 3712, R_C2W, off[P_C2B], n, 1.f, s)));
         EpiWinDgrad2 e{n->dpre1g, ro(ac.act1)};
         R2D2_CUDA_CHECK((launch_winconv<10, 64, 2, 2, 128, true, true>(ro(n->dpre2), R2, SplitC{pk.W2q.hi, pk.W2q.lo}, e, s)));
     }
     {   // conv1 (weights only; frames need no gradient)
-        R2D2_CUDA_CHECK(n->C == 1 ? conv1_wgrad<1>(n, grads, s) : conv1_wgrad<4>(n, grads, s));
+        R2D2_CUDA_CHECK(n->C == 1 ? conv1_wgrad<1>(n, s) : conv1_wgrad<4>(n, s));
     }
+    R2D2_CUDA_CHECK(fin_flush(n, grads, d_off, s));                // conv weights and biases
     return R2D2_OK;
 }
+
+/* Incremented by every r2d2_set_* knob: lets a caller that caches launch sequences (CUDA graphs) notice a mode change. */
+int r2d2_config_epoch(void) { return g_config_epoch; }
 
 /* diagnostics: number of 16-CTA recurrence clusters the current device keeps resident at once (< 0: query failed) */
 int r2d2_debug_cluster_capacity(void) { return rec2_max_active_clusters<16>() * 100 + rec2_max_active_clusters<32>(); }
 
 /* 1 (default): forward LSTM recurrence inside 16-CTA clusters (distributed-shared-memory exchange of h); 0: L2-flag kernel. */
 int r2d2_set_cluster_recurrence(int on) {
+    ++g_config_epoch;
     int prev = g_cluster_recurrence;
     g_cluster_recurrence = on ? 1 : 0;
     return prev;
@@ -1281,6 +1355,7 @@ int r2d2_set_cluster_recurrence(int on) {
 
 /* 1 (default): plain-matrix GEMMs of K1/K1b on CTA pairs (cta_group::2, TMA); 0: single-CTA cp.async kernels.  Returns the previous value. */
 int r2d2_set_pair_gemm(int on) {
+    ++g_config_epoch;
     int prev = g_pair_gemm;
     g_pair_gemm = on ? 1 : 0;
     return prev;
@@ -1288,6 +1363,7 @@ int r2d2_set_pair_gemm(int on) {
 
 /* 1 (default): the T-step recurrence runs as one persistent cooperative kernel when B <= 64; 0: per-step launches. */
 int r2d2_set_persistent_recurrence(int on) {
+    ++g_config_epoch;
     int prev = g_persistent_recurrence;
     g_persistent_recurrence = on ? 1 : 0;
     return prev;
@@ -1295,6 +1371,7 @@ int r2d2_set_persistent_recurrence(int on) {
 
 /* debug: attach a device buffer of T*8 uint64 receiving globaltimer stamps of CTA 0 of the persistent recurrence */
 int r2d2_debug_rec_trace(void* device_buffer) {
+    ++g_config_epoch;
     g_rec_trace = (unsigned long long*)device_buffer;
     return R2D2_OK;
 }

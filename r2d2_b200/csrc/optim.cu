@@ -40,8 +40,14 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ p, c
                                                         float* __restrict__ m, float* __restrict__ v, int64_t n,
                                                         const double* __restrict__ partial, const float* __restrict__ grad_scale,
                                                         float max_norm, float lr, float beta1, float beta2, float eps,
-                                                        float bc1, float bc2_sqrt, float* __restrict__ norm_out) {
+                                                        float bc1, float bc2_sqrt, float* __restrict__ norm_out,
+                                                        const int64_t* __restrict__ step_dev, const int32_t* __restrict__ rows_dev) {
     __shared__ double s_tot;
+    if (step_dev) {                                          // device-resident update count (CUDA-graph replays): same formulas as the host path
+        const double st = (double)*step_dev;
+        bc1 = (float)(1.0 - pow((double)beta1, st));
+        bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, st));
+    }
     if (threadIdx.x < 32) {
         double t = 0.0;
         for (int i = threadIdx.x; i < kNormBlocks; i += 32) t += partial[i];
@@ -50,7 +56,7 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ p, c
         if (threadIdx.x == 0) s_tot = t;
     }
     __syncthreads();
-    const float scale = grad_scale ? *grad_scale : 1.f;
+    const float scale = rows_dev ? __fdiv_rn(1.f, (float)*rows_dev) : (grad_scale ? *grad_scale : 1.f);
     const float total_norm = (float)sqrt(s_tot) * fabsf(scale);
     // torch.nn.utils.clip_grad_norm_: coef = max_norm / (norm + 1e-6), clamped to 1
     const float coef = fminf(max_norm / (total_norm + 1e-6f), 1.f) * scale;
@@ -100,7 +106,23 @@ int r2d2_clip_adam(float* params, const float* grads, float* exp_avg, float* exp
     const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
     const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
     clip_adam_kernel<<<kNormBlocks, 256, 0, s>>>(params, grads, exp_avg, exp_avg_sq, n, partial_ws, grad_scale, max_norm, lr,
-                                               beta1, beta2, eps, bc1, bc2_sqrt, norm_out);
+                                               beta1, beta2, eps, bc1, bc2_sqrt, norm_out, nullptr, nullptr);
+    R2D2_LAUNCH_CHECK();
+    return R2D2_OK;
+}
+
+/* The same update with the update count read from DEVICE memory (step_dev: int64, 1-based, already incremented by the
+ * caller on the same stream) and, optionally, the gradient scale derived from a device row count (rows_dev: int32,
+ * scale = 1 / rows; overrides grad_scale).  Nothing in the argument list changes between updates, so the whole learner
+ * update can be captured once in a CUDA graph and replayed. */
+int r2d2_clip_adam_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                       const float* grad_scale, const int32_t* rows_dev, double* partial_ws, float max_norm, float lr, float beta1,
+                       float beta2, float eps, const int64_t* step_dev, float* norm_out, void* stream) {
+    R2D2_REQUIRE(params && grads && exp_avg && exp_avg_sq && partial_ws && n > 0 && step_dev, "bad arguments");
+    cudaStream_t s = as_stream(stream);
+    sumsq_partial_kernel<<<kNormBlocks, kNormThreads, 0, s>>>(grads, n, partial_ws);
+    clip_adam_kernel<<<kNormBlocks, 256, 0, s>>>(params, grads, exp_avg, exp_avg_sq, n, partial_ws, grad_scale, max_norm, lr,
+                                               beta1, beta2, eps, 1.f, 1.f, norm_out, step_dev, rows_dev);
     R2D2_LAUNCH_CHECK();
     return R2D2_OK;
 }

@@ -42,12 +42,14 @@ struct r2d2_replay {
 
 namespace r2d2 {
 
-__global__ void replay_meta_kernel(const uint8_t* __restrict__ store, ReplayLayout lay, int spb, const int64_t* __restrict__ idx,
+__global__ void replay_meta_kernel(const uint8_t* __restrict__ store, ReplayLayout lay, int spb, int num_blocks, const int64_t* __restrict__ idx,
                                    int B, SeqDesc* __restrict__ desc, uint8_t* __restrict__ burn_out, uint8_t* __restrict__ learn_out,
                                    uint8_t* __restrict__ fwd_out, int32_t* __restrict__ rows_out) {
     extern __shared__ int s_l[];
     for (int n = threadIdx.x; n < B; n += blockDim.x) {
-        const int64_t slot = idx[n];
+        int64_t slot = idx[n];
+        const bool valid = slot >= 0 && slot < (int64_t)num_blocks * spb;     // a stale / corrupt index yields an EMPTY sequence, never an
+        if (!valid) slot = 0;                                                  // out-of-bounds read (the reference raises IndexError here)
         const int64_t blk = slot / spb;
         const int s = (int)(slot - blk * spb);
         const uint8_t* blob = store + blk * lay.total;
@@ -57,7 +59,7 @@ __global__ void replay_meta_kernel(const uint8_t* __restrict__ store, ReplayLayo
         for (int i = 0; i < s; ++i) before += learn[i];
         SeqDesc d;
         d.blob = blk * lay.total;
-        d.b = burn[s]; d.l = learn[s]; d.f = blob[lay.fwd + s];
+        d.b = valid ? burn[s] : 0; d.l = valid ? learn[s] : 0; d.f = valid ? blob[lay.fwd + s] : 0;
         d.start = (int)burn[0] + before - d.b;           // window [start-b, start+l+f) with start = burn[0] + before
         d.seq = s;
         d.act_off = before;
@@ -233,7 +235,7 @@ static int replay_gather_impl(r2d2_replay* r, const int64_t* idx, const float* i
         r->desc_cap = B;
     }
     cudaStream_t s = as_stream(stream);
-    replay_meta_kernel<<<1, 256, B * sizeof(int), s>>>(r->store, r->lay, r->spb, idx, B, r->desc, burn, learn, fwd, rows_out);
+    replay_meta_kernel<<<1, 256, B * sizeof(int), s>>>(r->store, r->lay, r->spb, r->num_blocks, idx, B, r->desc, burn, learn, fwd, rows_out);
     replay_copy_kernel<<<dim3(T, B), 256, 0, s>>>(r->store, r->lay, r->desc, isw, T, r->C, r->A, r->H, r->frame_bytes, obs,
                                                   (__nv_bfloat16*)s2d, last_action,
                                                   last_reward, hidden, action, n_step_reward, gamma, is_weights_rows);

@@ -44,6 +44,10 @@ namespace r2d2 {
 
 constexpr int kSmallN = 1024;  // one CTA handles the whole call (the learner's n = 64 case)
 
+// Indices come from the host surface (PriorityTree.update, ReplayBuffer.update_priorities): anything outside the leaf range
+// [0, leaf_base] is dropped here instead of becoming an out-of-bounds access (NumPy raises IndexError in the reference).
+__device__ __forceinline__ bool slot_in_tree(int64_t slot, int64_t leaf_base) { return slot >= 0 && slot <= leaf_base; }
+
 __device__ __forceinline__ bool keep_slot(int64_t slot, int64_t old_ptr, int64_t cur_ptr, int64_t spb) {
     // worker.py:247-256: drop slots whose block was overwritten since the batch was sampled
     if (old_ptr < 0 || cur_ptr == old_ptr) return true;
@@ -69,7 +73,7 @@ __global__ void __launch_bounds__(kSmallN) tree_update_small(double* __restrict_
     bool keep = false;
     if (i < n) {
         slot = idx[i];
-        keep = keep_slot(slot, old_ptr, cur_ptr, spb);
+        keep = slot_in_tree(slot, leaf_base) && keep_slot(slot, old_ptr, cur_ptr, spb);
         if (keep) atomicMax(&owner[slot], i);
     }
     __syncthreads();
@@ -92,12 +96,12 @@ __global__ void __launch_bounds__(kSmallN) tree_update_small(double* __restrict_
 }
 
 // ---------------------------------------------------------------------------- update, large n
-__global__ void tree_mark(int* __restrict__ owner, const int64_t* __restrict__ idx, int64_t n, int64_t old_ptr,
+__global__ void tree_mark(int* __restrict__ owner, const int64_t* __restrict__ idx, int64_t n, int64_t leaf_base, int64_t old_ptr,
                           int64_t cur_ptr, int64_t spb) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     int64_t slot = idx[i];
-    if (keep_slot(slot, old_ptr, cur_ptr, spb)) atomicMax(&owner[slot], (int)i);
+    if (slot_in_tree(slot, leaf_base) && keep_slot(slot, old_ptr, cur_ptr, spb)) atomicMax(&owner[slot], (int)i);
 }
 
 template <bool kFromTd>
@@ -109,7 +113,7 @@ __global__ void tree_write_leaves(double* __restrict__ nodes, int* __restrict__ 
     if (i >= n) return;
     int64_t slot = idx[i];
     int64_t node = -1;
-    if (keep_slot(slot, old_ptr, cur_ptr, spb) && __ldcg(&owner[slot]) == (int)i) {
+    if (slot_in_tree(slot, leaf_base) && keep_slot(slot, old_ptr, cur_ptr, spb) && __ldcg(&owner[slot]) == (int)i) {
         node = leaf_base + slot;
         nodes[node] = kFromTd ? leaf_from_td(td[i], alpha) : leaf_in[i];
     }
@@ -262,7 +266,7 @@ static int tree_update_impl(r2d2_tree* t, const int64_t* idx, const float* td, c
     int rc = ensure_scratch(t, n);
     if (rc) return rc;
     const int threads = 256, blocks = cdiv(n, threads);
-    tree_mark<<<blocks, threads, 0, s>>>(t->owner, idx, n, old_ptr, cur_ptr, spb);
+    tree_mark<<<blocks, threads, 0, s>>>(t->owner, idx, n, t->leaf_base, old_ptr, cur_ptr, spb);
     tree_write_leaves<kFromTd><<<blocks, threads, 0, s>>>(t->nodes, t->owner, t->cur, idx, td, leaf, n, t->leaf_base,
                                                         t->alpha_f32, old_ptr, cur_ptr, spb);
     tree_reset_owner<<<blocks, threads, 0, s>>>(t->owner, t->cur, n, t->leaf_base);

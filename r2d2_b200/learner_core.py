@@ -21,6 +21,7 @@ PARAM_NAMES = [
     "value.0.weight", "value.0.bias", "value.2.weight", "value.2.bias",
 ]
 HIDDEN = 512
+_BATCH_KEYS = ("obs", "last_action", "last_reward", "hidden", "action", "n_step_reward", "gamma", "burn_in", "learning", "forward", "is_weights")
 
 
 def param_shapes(action_dim: int, in_channels: int = 1):
@@ -213,7 +214,7 @@ class DeviceLearner:
         self.grads = FlatParams(action_dim, in_channels, self.device)
         self.exp_avg = torch.zeros_like(self.online.flat)
         self.exp_avg_sq = torch.zeros_like(self.online.flat)
-        self.num_updates = 0
+        self._num_updates = 0
         h = C.c_void_p()
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().r2d2_net_create(batch_size, seq_frames, in_channels, action_dim, max_learning,
@@ -234,6 +235,12 @@ class DeviceLearner:
         self.grad_scale = torch.ones(1, device=d)
         self.norm = torch.zeros(1, device=d)
         self._norm_ws = torch.zeros(592, dtype=torch.float64, device=d)
+        self._step_dev = torch.zeros(1, dtype=torch.int64, device=d)     # device mirror of num_updates (Adam bias correction)
+        # CUDA-graph replay of update(): captured per set of batch buffers the second time that set is seen (persistent
+        # staging slots / the replay's gather buffers); R2D2_CUDA_GRAPH=0 keeps every update eager
+        import os
+        self.use_graph = os.environ.get("R2D2_CUDA_GRAPH", "1") != "0"
+        self._graphs, self._graph_seen = {}, {}
         # hook called between backward and the optimizer: (learner) -> None, e.g. NCCL all-reduce
         self.grad_hook: Optional[Callable[["DeviceLearner"], None]] = None
 
@@ -245,6 +252,15 @@ class DeviceLearner:
             except Exception:
                 pass
             self._h = None
+
+    @property
+    def num_updates(self) -> int:
+        return self._num_updates
+
+    @num_updates.setter
+    def num_updates(self, v: int) -> None:
+        self._num_updates = int(v)
+        self._step_dev.fill_(int(v))
 
     # ------------------------------------------------------------------ parameters
     @_lib.on_device
@@ -333,26 +349,58 @@ class DeviceLearner:
         self.td / self.prio / self.loss_sum / self.rows / self.grads (grads of loss_sum)."""
         self.compute_forward(b)
         self.backward(self.dq)
-        torch.reciprocal(self.rows.float(), out=self.grad_scale)      # mean over rows (worker.py:354)
 
     @_lib.on_device
-    def apply_gradients(self) -> None:
-        """worker.py:364-365 (+ re-pack of the online weights)."""
-        self.num_updates += 1
+    def apply_gradients(self, _count: bool = True) -> None:
+        """worker.py:364-365 (+ re-pack of the online weights).  The mean over rows of worker.py:354 is applied here: with
+        a grad_hook (data parallel) the hook leaves 1/global_rows in self.grad_scale, otherwise the kernel divides by
+        this batch's device-side row count."""
+        if _count:
+            self._num_updates += 1
+        self._step_dev.add_(1)
         p = _lib.ptr
         b1, b2 = self.betas
-        _lib.check(_lib.lib().r2d2_clip_adam(p(self.online.flat), p(self.grads.flat), p(self.exp_avg), p(self.exp_avg_sq),
-                                             self.online.flat.numel(), p(self.grad_scale), p(self._norm_ws),
-                                             float(self.grad_norm), float(self.lr), float(b1), float(b2), float(self.eps),
-                                             self.num_updates, p(self.norm), _lib.stream_ptr()))
+        hooked = self.grad_hook is not None
+        _lib.check(_lib.lib().r2d2_clip_adam_dev(p(self.online.flat), p(self.grads.flat), p(self.exp_avg), p(self.exp_avg_sq),
+                                                 self.online.flat.numel(), p(self.grad_scale) if hooked else None,
+                                                 None if hooked else p(self.rows), p(self._norm_ws), float(self.grad_norm),
+                                                 float(self.lr), float(b1), float(b2), float(self.eps), p(self._step_dev),
+                                                 p(self.norm), _lib.stream_ptr()))
         self.pack(0)
 
-    @_lib.on_device
-    def update(self, b: dict) -> None:
+    def _update_eager(self, b: dict, _count: bool = True) -> None:
         self.compute_gradients(b)
         if self.grad_hook is not None:
             self.grad_hook(self)
-        self.apply_gradients()
+        self.apply_gradients(_count)
+
+    @_lib.on_device
+    def update(self, b: dict) -> None:
+        """One learner update on prepared device buffers.  Nothing in the launch sequence depends on host values that change
+        between updates (update count and row count live on the device), so for a recurring set of buffers the ~45 launches
+        are captured once in a CUDA graph and replayed."""
+        if not self.use_graph or self.grad_hook is not None:
+            return self._update_eager(b)
+        key = (_lib.lib().r2d2_config_epoch(),) + tuple(None if v is None else (v.data_ptr() if isinstance(v, torch.Tensor) else v)
+                                                      for v in (b.get(k) for k in _BATCH_KEYS))
+        g = self._graphs.get(key)
+        if g is None:
+            if len(self._graph_seen) > 256:
+                self._graph_seen.clear()
+            seen = self._graph_seen.get(key, 0) + 1
+            self._graph_seen[key] = seen
+            if seen < 2:
+                return self._update_eager(b)                 # also the run that sets per-function attributes (not capturable)
+            if len(self._graphs) >= 8:
+                self._graphs.clear()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._update_eager(b, _count=False)
+            self._graphs[key] = (g, b)                       # the graph reads these buffers: keep them alive with it
+            g = self._graphs[key]
+        self._live = g[1]
+        self._num_updates += 1
+        g[0].replay()
 
     # ------------------------------------------------------------------ debug
     def debug_split(self, which: int, name: str, numel: int) -> torch.Tensor:

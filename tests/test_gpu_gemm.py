@@ -1,4 +1,4 @@
-"""tcgen05 gather-GEMM core vs float64 matmul (and vs the fp32 FFMA path) on plain matrices."""
+"""tcgen05 GEMM kernels (single-CTA cp.async path, CTA-pair TMA path) vs float64 matmul on plain matrices."""
 import itertools
 import os
 
@@ -7,48 +7,6 @@ import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
-
-SHAPES = [(128, 128, 64), (256, 256, 512), (300, 64, 576), (64, 2048, 512), (1000, 32, 256), (130, 528, 528),
-          (128, 16, 2560), (5440, 512, 3136)]
-
-
-def _run(backend, ubn, am, bm, M, N, K, A, B, splits=1):
-    from r2d2_b200 import _lib
-    C = torch.full((splits, M, N), float("nan"), device="cuda")
-    _lib.check(_lib.lib().r2d2_debug_gemm(backend, ubn, am, bm, M, N, K, _lib.ptr(A), _lib.ptr(B), _lib.ptr(C), splits,
-                                          _lib.stream_ptr()))
-    torch.cuda.synchronize()
-    return C.sum(0) if splits > 1 else C[0]
-
-
-@pytest.mark.parametrize("M,N,K", SHAPES)
-def test_umma_matches_fp64(M, N, K):
-    from r2d2_b200 import _lib
-    _lib.require_device()
-    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
-    lines = []
-    for am, bm in itertools.product((0, 1), (0, 1)):
-        if (am == 1 and M % 4) or (bm == 1 and N % 4):
-            continue
-        A = torch.randn((M, K) if am == 0 else (K, M), device="cuda", generator=g)
-        B = torch.randn((N, K) if bm == 0 else (K, N), device="cuda", generator=g)
-        Ad = (A if am == 0 else A.t()).double()
-        Bd = (B if bm == 0 else B.t()).double()
-        ref = Ad @ Bd.t()
-        scale = ref.abs().max().item()
-        for ubn in ((16, 32, 64, 128, 256) if (M, N, K) in SHAPES[:4] else (64, 128)):
-            for backend, tol in ((0, 4e-6), (1, 3e-5), (2, 2e-2)):
-                for splits in ((1, 3) if K >= 512 else (1,)):
-                    C = _run(backend, ubn, am, bm, M, N, K, A, B, splits)
-                    assert torch.isfinite(C).all(), (backend, ubn, am, bm, splits)
-                    err = (C.double() - ref).abs().max().item() / scale
-                    lines.append(f"M{M} N{N} K{K} am{am} bm{bm} ubn{ubn} be{backend} sp{splits}: rel err {err:.2e}")
-                    assert err < tol, lines[-1]
-    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
-    os.makedirs(out, exist_ok=True)
-    with open(os.path.join(out, "gemm_diag.txt"), "a") as f:
-        f.write("\n".join(lines) + "\n")
-
 
 def _split(x):
     hi = x.bfloat16()

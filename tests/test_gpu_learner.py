@@ -192,10 +192,11 @@ def test_full_size_batch_td_parity(mode):
         _lib.lib().r2d2_set_fast_math(prev)
 
 
-@pytest.mark.parametrize("B,C,A_,burn,learn,fwd", [(72, 1, 9, 4, 3, 2), (5, 4, 9, 6, 5, 3), (6, 1, 4, 5, 4, 2), (6, 1, 15, 5, 4, 2)])
+@pytest.mark.parametrize("B,C,A_,burn,learn,fwd", [(72, 1, 9, 4, 3, 2), (5, 4, 9, 6, 5, 3), (6, 1, 4, 5, 4, 2), (6, 1, 15, 5, 4, 2), (6, 1, 18, 5, 4, 2), (5, 4, 18, 6, 5, 3),
+                                                   (4, 1, 31, 5, 4, 2)])
 def test_shape_sweep_vs_oracle(B, C, A_, burn, learn, fwd):
     """Other shapes of the same kernels: B > 64 (per-step recurrence path, several M tiles), 4-channel frames
-    (BASELINE.json's 84x84x4), smallest / largest supported action counts."""
+    (BASELINE.json's 84x84x4), small / the full ALE (18) / largest supported (31) action counts."""
     torch.set_num_threads(min(32, os.cpu_count() or 8))
     from r2d2_b200.learner_core import DeviceLearner
     params = init_params(A_, in_channels=C, seed=11)
