@@ -1343,7 +1343,7 @@ int r2d2_net_backward(r2d2_net* n, const float* params, const float* dq, float* 
 int r2d2_config_epoch(void) { return g_config_epoch; }
 
 /* diagnostics: number of 16-CTA recurrence clusters the current device keeps resident at once (< 0: query failed) */
-int r2d2_debug_cluster_capacity(void) { return rec2_max_active_clusters<16>() * 100 + rec2_max_active_clusters<32>(); }
+int r2d2_debug_cluster_capacity(void) { return rec2_max_active_clusters<1>() * 100 + rec2_max_active_clusters<2>(); }
 
 /* 1 (default): forward LSTM recurrence inside 16-CTA clusters (distributed-shared-memory exchange of h); 0: L2-flag kernel. */
 int r2d2_set_cluster_recurrence(int on) {

@@ -33,23 +33,25 @@ constexpr int R2_EW = 16;                          // epilogue warps: 4 TMEM lan
 constexpr int R2_THREADS = 32 * R2_EW + 32;        // + 1 MMA-issue warp
 constexpr int R2_GRP = 4;                          // source CTAs per arrival barrier (one mbarrier wait costs ~90 clk even when complete)
 
-// NS = sequences per cluster (16 or 32).  NS = 32 halves the number of clusters (a B200 keeps only 7 clusters of 16 CTAs with
-// this much shared memory resident, and 64 sequences x 2 networks at NS = 16 are 8); its h tiles are twice as large, so
-// half of the W lo plane (k < 256) moves to tensor memory next to the hi plane.
-template <int NS> struct Rec2Cfg {
-    static constexpr int kNC = NS / 16;                        // cells (sequences) per epilogue thread
-    static constexpr int kNV = NS / 4;                         // accumulator columns an epilogue warp reads (its sequence group)
-    static constexpr int kPlane = NS * 64;                     // one bf16 plane of one source tile: [NS][32 units]
+// A cluster runs NSTR independent recurrences ("streams") of 16 sequences each, sharing the resident W_hh slice.
+// NSTR = 1: 16 sequences per cluster.  A B200 keeps only 7 such clusters resident, and 64 sequences x 2 networks are 8,
+// so the default for full batches is NSTR = 2: 32 sequences per cluster as two streams whose steps interleave -- while
+// the cell warps work on stream 0, the MMA warp already multiplies stream 1 -- which hides most of the per-step latency
+// chain (MMA -> cell -> DSMEM exchange) of one stream behind the other.  Its h buffers are twice as large, so half of the
+// W lo plane (k < 256) moves to tensor memory next to the hi plane.
+template <int NSTR> struct Rec2Cfg {
+    static constexpr int NS = 16;                              // sequences per stream
+    static constexpr int kPlane = NS * 64;                     // one bf16 plane of one source tile: [16][32 units]
     static constexpr int kTile = 2 * kPlane;                   // hi | lo
-    static constexpr int kKT = NS == 32 ? 256 : 0;             // reduction indices of W lo that live in TMEM
+    static constexpr int kKT = NSTR == 2 ? 256 : 0;            // reduction indices of W lo that live in TMEM
     static constexpr int kWloSmem = (512 - kKT) / 64 * 16384;  // W lo plane in shared memory: k-blocks of [128 rows][64 k]
-    static constexpr int kSH = 2 * R2_CL * kTile;              // [parity][source]
-    static constexpr int kStage = 2 * kTile;                   // [parity] own outgoing tile
+    static constexpr int kSH = NSTR * 2 * R2_CL * kTile;       // [stream][parity][source]
+    static constexpr int kStage = NSTR * 2 * kTile;            // [stream][parity] own outgoing tile
     static constexpr int kSmem = kWloSmem + kSH + kStage + 1024 + 512;
     static constexpr int kWloCol = 256;                        // TMEM: W_hi columns [0,256), W_lo (k < kKT) [256, 256 + kKT/2)
-    static constexpr int kAccCol = 384;                        // accumulators: 2 NS columns (W_hi.h_hi | W_hi.h_lo) per parity
-    static_assert(NS == 16 || NS == 32, "sequences per cluster");
-    static_assert(kAccCol + 2 * 2 * NS <= 512 && kWloCol + kKT / 2 <= kAccCol, "TMEM budget");
+    static constexpr int kAccCol = 384;                        // accumulators: 32 columns (W_hi.h_hi | W_hi.h_lo) per (stream, parity)
+    static_assert(NSTR == 1 || NSTR == 2, "streams per cluster");
+    static_assert(kAccCol + NSTR * 2 * 2 * NS <= 512 && kWloCol + kKT / 2 <= kAccCol, "TMEM budget");
 };
 
 // byte offset of (row, unit) inside a [rows][32] bf16 SWIZZLE_64B tile
@@ -80,30 +82,32 @@ template <int N> __device__ __forceinline__ void tmem_ld_n_wait(uint32_t (&a)[N]
     for (int i = 0; i < N; ++i) asm volatile("" : "+r"(a[i]), "+r"(b[i]));          // no use of the registers may move above the wait
 }
 
-template <int NS>
+template <int NSTR>
 __global__ void __launch_bounds__(R2_THREADS, 1) rec2_fwd_kernel(const RecFwdParams P, int nq) {
-    using Cfg = Rec2Cfg<NS>;
-    constexpr int NC = Cfg::kNC, NV = Cfg::kNV, TILE = Cfg::kTile, PLANE = Cfg::kPlane, NGRP = R2_CL / R2_GRP;
+    using Cfg = Rec2Cfg<NSTR>;
+    constexpr int NS = 16, TILE = Cfg::kTile, PLANE = Cfg::kPlane, NGRP = R2_CL / R2_GRP;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;
     uint8_t* smem = smem_raw + pad;
     const uint32_t sW = raw + pad;                     // W lo plane (k >= kKT)
-    const uint32_t sH = sW + Cfg::kWloSmem;            // h tiles [parity][source]
-    const uint32_t sS = sH + Cfg::kSH;                 // staging [parity]
+    const uint32_t sH = sW + Cfg::kWloSmem;            // h tiles [stream][parity][source]
+    const uint32_t sS = sH + Cfg::kSH;                 // staging [stream][parity]
     uint8_t* stage_ptr = smem + Cfg::kWloSmem + Cfg::kSH;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kWloSmem + Cfg::kSH + Cfg::kStage);       // full[2][NGRP] | accf[2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NGRP + 2);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kWloSmem + Cfg::kSH + Cfg::kStage);       // full[stream][2][NGRP] | accf[stream][2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NSTR * (2 * NGRP + 2));
+    auto bar_full = [&](int st, int par, int gr) { return smem_u32(&bars[(st * 2 + par) * NGRP + gr]); };
+    auto bar_acc = [&](int st, int par) { return smem_u32(&bars[NSTR * 2 * NGRP + st * 2 + par]); };
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t c = cluster_ctarank();
     const int cid = blockIdx.x / R2_CL;
-    const int net = P.net_base + cid / nq, quarter = cid % nq;
+    const int net = P.net_base + cid / nq, quarter = cid % nq;      // quarter: which group of NSTR * 16 sequences
     const int B = P.B, T = P.T;
     const bool want_lo = !P.fast;
 
     if (tid == 0) {
-        for (int i = 0; i < 2 * NGRP + 2; ++i) mbar_init(smem_u32(&bars[i]), 1);
+        for (int i = 0; i < NSTR * (2 * NGRP + 2); ++i) mbar_init(smem_u32(&bars[i]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == R2_EW) {
@@ -126,7 +130,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) rec2_fwd_kernel(const RecFwdPar
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int q = warp & 3, cg = warp >> 2;            // epilogue warps: TMEM lane quadrant, sequence group
+    const int q = warp & 3, cg = warp >> 2;            // epilogue warps: TMEM lane quadrant, sequence group (4 sequences)
     if (warp < R2_EW) {                                // W hi plane (and W lo, k < kKT) -> tensor memory: lane = gate row, column = k / 2
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         const int row = 128 * (int)c + 32 * q + lane;
@@ -162,131 +166,117 @@ __global__ void __launch_bounds__(R2_THREADS, 1) rec2_fwd_kernel(const RecFwdPar
     tc_fence_after();
 
     if (warp < R2_EW) {
-        // ------------------------------------------------------------------ epilogue / cell warps
+        // ------------------------------------------------------------------ epilogue / cell warps: one cell per thread and stream
         const int j = 8 * q + (lane >> 2), g = lane & 3;           // unit inside the CTA, gate row (i, f, g, o)
         const int unit = 32 * (int)c + j;
-        const int row0 = cg * NV + g * NC;                         // first of this thread's sequences inside the cluster's NS
-        int bq[NC], blen[NC];
-        float c_reg[NC];
-        uint32_t hb[NC], lb[NC];                                   // current h as bf16 bits (hi, lo)
-#pragma unroll
-        for (int i = 0; i < NC; ++i) {
-            bq[i] = NS * quarter + row0 + i;
-            const bool ok = bq[i] < B;
-            blen[i] = ok ? P.len[bq[i]] : -1;                      // -1: no such sequence (never live, nothing stored)
-            c_reg[i] = 0.f; hb[i] = 0u; lb[i] = 0u;
-            if (ok) {
-                c_reg[i] = P.c0[(size_t)bq[i] * P.ld_c0 + unit];
-                hb[i] = __bfloat16_as_ushort(P.Hhi[net][(size_t)bq[i] * REC_H + unit]);      // HsX block 0 = stored h0 (split)
-                lb[i] = __bfloat16_as_ushort(P.Hlo[net][(size_t)bq[i] * REC_H + unit]);
-            }
-        }
+        const int row0 = cg * 4 + g;                               // this thread's sequence inside a stream
+        int bq[NSTR], blen[NSTR];
+        float c_reg[NSTR];
+        uint32_t hb[NSTR], lb[NSTR];                               // current h as bf16 bits (hi, lo)
+        float4 xp[NSTR];
         const float* xp_base = P.XP[net] + 4 * unit;
-        auto load_xp = [&](int t, float4 (&xp)[NC]) {
-#pragma unroll
-            for (int i = 0; i < NC; ++i)
-                xp[i] = (blen[i] >= 0 && t < T) ? ld_nc_f4(xp_base + ((size_t)t * B + bq[i]) * REC_G4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        auto load_xp = [&](int st, int t) {
+            xp[st] = (blen[st] >= 0 && t < T) ? ld_nc_f4(xp_base + ((size_t)t * B + bq[st]) * REC_G4) : make_float4(0.f, 0.f, 0.f, 0.f);
         };
-        // publish: own tile -> staging of parity `par`, then one bulk copy per destination CTA
-        auto publish = [&](int par, bool send) {
-            uint8_t* st = stage_ptr + par * TILE;
-#pragma unroll
-            for (int i = 0; i < NC; ++i) {
-                const uint32_t o = sw64_off(row0 + i, j);
-                *reinterpret_cast<uint16_t*>(st + o) = (uint16_t)hb[i];
-                *reinterpret_cast<uint16_t*>(st + PLANE + o) = (uint16_t)lb[i];
-            }
+        // publish: own tile -> staging of (stream, parity), then one bulk copy per destination CTA
+        auto publish = [&](int st, int par, bool send) {
+            uint8_t* sp = stage_ptr + (st * 2 + par) * TILE;
+            const uint32_t o = sw64_off(row0, j);
+            *reinterpret_cast<uint16_t*>(sp + o) = (uint16_t)hb[st];
+            *reinterpret_cast<uint16_t*>(sp + PLANE + o) = (uint16_t)lb[st];
             fence_proxy_async_smem();
             tc_fence_before();
             asm volatile("bar.sync 1, %0;" ::"n"(32 * R2_EW) : "memory");
             if (send && tid < R2_CL) {
-                const uint32_t dst = mapa_u32(sH + (uint32_t)((par * R2_CL + (int)c) * TILE), (uint32_t)tid);
-                const uint32_t bar = mapa_u32(smem_u32(&bars[par * NGRP + ((int)c / R2_GRP)]), (uint32_t)tid);
-                bulk_copy_to_cluster(dst, sS + par * TILE, TILE, bar);
+                const uint32_t dst = mapa_u32(sH + (uint32_t)(((st * 2 + par) * R2_CL + (int)c) * TILE), (uint32_t)tid);
+                const uint32_t bar = mapa_u32(bar_full(st, par, (int)c / R2_GRP), (uint32_t)tid);
+                bulk_copy_to_cluster(dst, sS + (st * 2 + par) * TILE, TILE, bar);
             }
         };
-        publish(0, true);                              // h_{-1}
-        float4 xp[NC];
-        load_xp(0, xp);
+#pragma unroll
+        for (int st = 0; st < NSTR; ++st) {
+            bq[st] = NSTR * NS * quarter + NS * st + row0;
+            const bool ok = bq[st] < B;
+            blen[st] = ok ? P.len[bq[st]] : -1;                    // -1: no such sequence (never live, nothing stored)
+            c_reg[st] = 0.f; hb[st] = 0u; lb[st] = 0u;
+            if (ok) {
+                c_reg[st] = P.c0[(size_t)bq[st] * P.ld_c0 + unit];
+                hb[st] = __bfloat16_as_ushort(P.Hhi[net][(size_t)bq[st] * REC_H + unit]);      // HsX block 0 = stored h0 (split)
+                lb[st] = __bfloat16_as_ushort(P.Hlo[net][(size_t)bq[st] * REC_H + unit]);
+            }
+            publish(st, 0, true);                                  // h_{-1}
+            load_xp(st, 0);
+        }
 
         for (int t = 0; t < T; ++t) {
             const int par = t & 1;
-            const bool tr = P.trace && blockIdx.x == 0 && tid == 0;
-            if (tr) P.trace[t * 8 + 0] = gtime();
-            mbar_wait(smem_u32(&bars[2 * NGRP + par]), ((uint32_t)t >> 1) & 1u);
-            tc_fence_after();
-            if (tr) P.trace[t * 8 + 1] = gtime();
-            // accumulator: columns [0, NS) = W_hi.h_hi + W_lo.h_hi, [NS, 2 NS) = W_hi.h_lo; this warp reads its NV sequences
-            float v[NV];
-            {
-                const uint32_t a0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg::kAccCol + 2 * NS * par + cg * NV);
-                uint32_t ra[NV], rb[NV];
-                tmem_ld_n_issue<NV>(a0, ra);
-                tmem_ld_n_issue<NV>(a0 + NS, rb);
-                tmem_ld_n_wait<NV>(ra, rb);
 #pragma unroll
-                for (int i = 0; i < NV; ++i) v[i] = __uint_as_float(ra[i]) + (want_lo ? __uint_as_float(rb[i]) : 0.f);   // fast mode never writes the second half
-            }
-            // 4-lane transpose: lane (unit, gate g) ends with the four gates of its own NC sequences
-            float rv[3][NC];
+            for (int st = 0; st < NSTR; ++st) {
+                const bool tr = P.trace && blockIdx.x == 0 && tid == 0 && st == 0;
+                if (tr) P.trace[t * 8 + 0] = gtime();
+                mbar_wait(bar_acc(st, par), ((uint32_t)t >> 1) & 1u);
+                tc_fence_after();
+                if (tr) P.trace[t * 8 + 1] = gtime();
+                // accumulator: columns [0, 16) = W_hi.h_hi + W_lo.h_hi, [16, 32) = W_hi.h_lo; this warp reads its 4 sequences
+                float v[4];
+                {
+                    const uint32_t a0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg::kAccCol + 32 * (st * 2 + par) + cg * 4);
+                    uint32_t ra[4], rb[4];
+                    tmem_ld_n_issue<4>(a0, ra);
+                    tmem_ld_n_issue<4>(a0 + NS, rb);
+                    tmem_ld_n_wait<4>(ra, rb);
 #pragma unroll
-            for (int off = 1; off < 4; ++off) {
-                const int gd = (g - off) & 3;                      // the lane that reads from me wants its own sequences
-                const int src = (lane & ~3) | ((g + off) & 3);
+                    for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(ra[i]) + (want_lo ? __uint_as_float(rb[i]) : 0.f);   // fast mode never writes the second half
+                }
+                // 4-lane transpose: lane (unit, gate g) ends with the four gates of its own sequence
+                float rv[3];
 #pragma unroll
-                for (int i = 0; i < NC; ++i) rv[off - 1][i] = __shfl_sync(0xffffffffu, pickq<NC>(v, gd, i), src);
-            }
-            float4 gact[NC];
-            bool live[NC];
-#pragma unroll
-            for (int i = 0; i < NC; ++i) {
+                for (int off = 1; off < 4; ++off) {
+                    const int gd = (g - off) & 3;                  // the lane that reads from me wants its own sequence
+                    rv[off - 1] = __shfl_sync(0xffffffffu, pickq<1>(v, gd, 0), (lane & ~3) | ((g + off) & 3));
+                }
                 float gt[4];
-                const float own = pickq<NC>(v, g, i);
+                const float own = pickq<1>(v, g, 0);
 #pragma unroll
                 for (int G = 0; G < 4; ++G) {
                     const int off = (G - g) & 3;                   // gate G sits `off` lanes further in the quad
-                    gt[G] = off == 0 ? own : off == 1 ? rv[0][i] : off == 2 ? rv[1][i] : rv[2][i];
+                    gt[G] = off == 0 ? own : off == 1 ? rv[0] : off == 2 ? rv[1] : rv[2];
                 }
-                const float gi = fast_sigmoid(gt[0] + xp[i].x);
-                const float gf = fast_sigmoid(gt[1] + xp[i].y);
-                const float gg = fast_tanh(gt[2] + xp[i].z);
-                const float go = fast_sigmoid(gt[3] + xp[i].w);
-                const float cn = gf * c_reg[i] + gi * gg;
+                const float gi = fast_sigmoid(gt[0] + xp[st].x);
+                const float gf = fast_sigmoid(gt[1] + xp[st].y);
+                const float gg = fast_tanh(gt[2] + xp[st].z);
+                const float go = fast_sigmoid(gt[3] + xp[st].w);
+                const float cn = gf * c_reg[st] + gi * gg;
                 const float hn = go * fast_tanh(cn);
-                gact[i] = make_float4(gi, gf, gg, go);
-                live[i] = t < blen[i];
-                if (live[i]) {
-                    c_reg[i] = cn;
+                if (t < blen[st]) {
+                    c_reg[st] = cn;
                     const bf16 hh = __float2bfloat16_rn(hn);
                     const bf16 ll = __float2bfloat16_rn(hn - __bfloat162float(hh));
-                    hb[i] = __bfloat16_as_ushort(hh);
-                    lb[i] = __bfloat16_as_ushort(ll);
+                    hb[st] = __bfloat16_as_ushort(hh);
+                    lb[st] = __bfloat16_as_ushort(ll);
                 }
-            }
-            if (tr) P.trace[t * 8 + 2] = gtime();
-            publish(par ^ 1, t + 1 < T);               // h_t is the input of step t+1
-            if (tr) P.trace[t * 8 + 3] = gtime();
-            // ---- off the critical path: everything that goes to global memory, and the next step's input projection.
-            // (fence.proxy.async above is a MEMBAR: it waits for this thread's outstanding global accesses, so they are
-            // issued AFTER it and have a whole step to complete.)
-#pragma unroll
-            for (int i = 0; i < NC; ++i) {
-                if (blen[i] >= 0) {
-                    const size_t row = (size_t)t * B + bq[i];
-                    if (P.Gs[net]) *reinterpret_cast<float4*>(P.Gs[net] + row * REC_G4 + 4 * unit) = gact[i];
-                    P.Cs[net][row * REC_H + unit] = c_reg[i];
+                if (tr) P.trace[t * 8 + 2] = gtime();
+                publish(st, par ^ 1, t + 1 < T);       // h_t is the input of step t+1
+                if (tr) P.trace[t * 8 + 3] = gtime();
+                // ---- off the critical path: everything that goes to global memory, and the next step's input projection.
+                // (fence.proxy.async above is a MEMBAR: it waits for this thread's outstanding global accesses, so they are
+                // issued AFTER it and have a whole step to complete.)
+                if (blen[st] >= 0) {
+                    const size_t row = (size_t)t * B + bq[st];
+                    if (P.Gs[net]) *reinterpret_cast<float4*>(P.Gs[net] + row * REC_G4 + 4 * unit) = make_float4(gi, gf, gg, go);
+                    P.Cs[net][row * REC_H + unit] = c_reg[st];
                 }
-            }
-            load_xp(t + 1, xp);
-            // h_t -> HsX block t+1 (for the heads and the backward pass): 16-byte chunks of the staged tile
-            for (int u = tid; u < NS * 8; u += 32 * R2_EW) {
-                const int plane = u / (NS * 4), row = (u >> 2) % NS, ch = u & 3;
-                const int b = NS * quarter + row;
-                if (b < B) {
-                    const uint4 x = *reinterpret_cast<const uint4*>(stage_ptr + (par ^ 1) * TILE + plane * PLANE + (row >> 3) * 512 + (row & 7) * 64 +
-                                                                   (((ch ^ (row >> 1)) & 3) << 4));
-                    bf16* dstp = (plane ? P.Hlo[net] : P.Hhi[net]) + ((size_t)(t + 1) * B + b) * REC_H + 32 * (int)c + ch * 8;
-                    *reinterpret_cast<uint4*>(dstp) = x;
+                load_xp(st, t + 1);
+                // h_t -> HsX block t+1 (for the heads and the backward pass): 16-byte chunks of the staged tile
+                if (tid < NS * 8) {
+                    const int plane = tid / (NS * 4), row = (tid >> 2) % NS, ch = tid & 3;
+                    const int b = NSTR * NS * quarter + NS * st + row;
+                    if (b < B) {
+                        const uint4 x = *reinterpret_cast<const uint4*>(stage_ptr + (st * 2 + (par ^ 1)) * TILE + plane * PLANE + (row >> 3) * 512 + (row & 7) * 64 +
+                                                                       (((ch ^ (row >> 1)) & 3) << 4));
+                        bf16* dstp = (plane ? P.Hlo[net] : P.Hhi[net]) + ((size_t)(t + 1) * B + b) * REC_H + 32 * (int)c + ch * 8;
+                        *reinterpret_cast<uint4*>(dstp) = x;
+                    }
                 }
             }
         }
@@ -300,40 +290,43 @@ __global__ void __launch_bounds__(R2_THREADS, 1) rec2_fwd_kernel(const RecFwdPar
         for (int t = 0; t < T; ++t) {
             const int par = t & 1;
             const uint32_t ph = ((uint32_t)t >> 1) & 1u;
-            if (leader)
-                for (int gr = 0; gr < NGRP; ++gr) mbar_arrive_expect_tx(smem_u32(&bars[par * NGRP + gr]), R2_GRP * TILE);
-            __syncwarp();
-            const uint32_t acc = uT + (uint32_t)(Cfg::kAccCol + 2 * NS * par);
-            const uint32_t hbase = uH + (uint32_t)(par * R2_CL * TILE);
 #pragma unroll
-            for (int gr = 0; gr < NGRP; ++gr) {
-                mbar_wait(smem_u32(&bars[par * NGRP + gr]), ph);
-                tc_fence_after();
-                if (P.trace && blockIdx.x == 0 && leader && gr == 0) P.trace[t * 8 + 6] = gtime();
-                if (leader) {
+            for (int st = 0; st < NSTR; ++st) {
+                if (leader)
+                    for (int gr = 0; gr < NGRP; ++gr) mbar_arrive_expect_tx(bar_full(st, par, gr), R2_GRP * TILE);
+                __syncwarp();
+                const uint32_t acc = uT + (uint32_t)(Cfg::kAccCol + 32 * (st * 2 + par));
+                const uint32_t hbase = uH + (uint32_t)((st * 2 + par) * R2_CL * TILE);
 #pragma unroll
-                    for (int ss = 0; ss < R2_GRP; ++ss) {
-                        const int s = gr * R2_GRP + ss;
+                for (int gr = 0; gr < NGRP; ++gr) {
+                    mbar_wait(bar_full(st, par, gr), ph);
+                    tc_fence_after();
+                    if (P.trace && blockIdx.x == 0 && leader && gr == 0 && st == 0) P.trace[t * 8 + 6] = gtime();
+                    if (leader) {
 #pragma unroll
-                        for (int k = 0; k < 2; ++k) {
-                            const int kk = 32 * s + 16 * k;                                               // first reduction index of this MMA
-                            const uint64_t b_hl = umma_desc_sw64(hbase + (uint32_t)(s * TILE + k * 32));   // rows [0, NS) = hi plane, [NS, 2 NS) = lo plane
-                            const uint32_t a_t = uT + (uint32_t)(kk >> 1);
-                            if (want_lo) {
-                                umma_bf16_ts(acc, a_t, b_hl, idesc2, (s | k) ? 1u : 0u);                  // W_hi . [h_hi | h_lo]
-                                if (kk < Cfg::kKT) umma_bf16_ts(acc, uT + (uint32_t)(Cfg::kWloCol + (kk >> 1)), b_hl, idesc1, 1u);     // W_lo . h_hi
-                                else umma_bf16(acc, umma_desc_sw128(uW + (uint32_t)(((kk - Cfg::kKT) >> 6) * 16384 + (kk & 63) * 2)), b_hl, idesc1, 1u);
-                            } else {
-                                umma_bf16_ts(acc, a_t, b_hl, idesc1, (s | k) ? 1u : 0u);
+                        for (int ss = 0; ss < R2_GRP; ++ss) {
+                            const int s = gr * R2_GRP + ss;
+#pragma unroll
+                            for (int k = 0; k < 2; ++k) {
+                                const int kk = 32 * s + 16 * k;                                               // first reduction index of this MMA
+                                const uint64_t b_hl = umma_desc_sw64(hbase + (uint32_t)(s * TILE + k * 32));   // rows [0, 16) = hi plane, [16, 32) = lo plane
+                                const uint32_t a_t = uT + (uint32_t)(kk >> 1);
+                                if (want_lo) {
+                                    umma_bf16_ts(acc, a_t, b_hl, idesc2, (s | k) ? 1u : 0u);                  // W_hi . [h_hi | h_lo]
+                                    if (kk < Cfg::kKT) umma_bf16_ts(acc, uT + (uint32_t)(Cfg::kWloCol + (kk >> 1)), b_hl, idesc1, 1u);     // W_lo . h_hi
+                                    else umma_bf16(acc, umma_desc_sw128(uW + (uint32_t)(((kk - Cfg::kKT) >> 6) * 16384 + (kk & 63) * 2)), b_hl, idesc1, 1u);
+                                } else {
+                                    umma_bf16_ts(acc, a_t, b_hl, idesc1, (s | k) ? 1u : 0u);
+                                }
                             }
                         }
                     }
+                    __syncwarp();
                 }
+                if (leader) umma_commit(bar_acc(st, par));
+                if (P.trace && blockIdx.x == 0 && leader && st == 0) P.trace[t * 8 + 7] = gtime();
                 __syncwarp();
             }
-            if (leader) umma_commit(smem_u32(&bars[2 * NGRP + par]));
-            if (P.trace && blockIdx.x == 0 && leader) P.trace[t * 8 + 7] = gtime();
-            __syncwarp();
         }
     }
     tc_fence_before();
@@ -345,12 +338,12 @@ __global__ void __launch_bounds__(R2_THREADS, 1) rec2_fwd_kernel(const RecFwdPar
     }
 }
 
-template <int NS>
+template <int NSTR>
 static inline cudaLaunchConfig_t rec2_config(int clusters, cudaStream_t s, cudaLaunchAttribute* attr) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(clusters * R2_CL);
     cfg.blockDim = dim3(R2_THREADS);
-    cfg.dynamicSmemBytes = Rec2Cfg<NS>::kSmem;
+    cfg.dynamicSmemBytes = Rec2Cfg<NSTR>::kSmem;
     cfg.stream = s;
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = R2_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -360,40 +353,41 @@ static inline cudaLaunchConfig_t rec2_config(int clusters, cudaStream_t s, cudaL
 }
 
 // how many 16-CTA clusters of the recurrence kernel the device keeps resident at once (0: clusters of 16 are not schedulable)
-template <int NS>
+template <int NSTR>
 static inline int rec2_max_active_clusters() {
     static int cached = -1;
     if (cached >= 0) return cached;
     static unsigned long long configured = 0;
-    if (ensure_dynamic_smem(rec2_fwd_kernel<NS>, Rec2Cfg<NS>::kSmem, &configured) != cudaSuccess) return 0;
+    if (ensure_dynamic_smem(rec2_fwd_kernel<NSTR>, Rec2Cfg<NSTR>::kSmem, &configured) != cudaSuccess) return 0;
     cudaLaunchAttribute attr[1];
-    cudaLaunchConfig_t cfg = rec2_config<NS>(8, nullptr, attr);
+    cudaLaunchConfig_t cfg = rec2_config<NSTR>(8, nullptr, attr);
     int n = 0;
-    cudaError_t e = cudaFuncSetAttribute(rec2_fwd_kernel<NS>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, rec2_fwd_kernel<NS>, &cfg);
+    cudaError_t e = cudaFuncSetAttribute(rec2_fwd_kernel<NSTR>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, rec2_fwd_kernel<NSTR>, &cfg);
     if (e != cudaSuccess) { (void)cudaGetLastError(); n = 0; }
     return cached = n;
 }
 
-extern int g_rec2_ns;     // 0 = automatic, 16 / 32 = forced sequences per cluster
+extern int g_rec2_ns;     // 0 = automatic, 16 / 32 = forced sequences per cluster (1 / 2 interleaved streams of 16)
 
 // Returns cudaErrorNotSupported when clusters of 16 CTAs with this much shared memory cannot be scheduled on the device.
 static inline cudaError_t launch_rec2_fwd(const RecFwdParams& P, int nets, cudaStream_t s) {
     cudaLaunchAttribute attr[1];
-    const int cap16 = rec2_max_active_clusters<16>(), cap32 = rec2_max_active_clusters<32>();
-    const int need16 = nets * ((P.B + 15) / 16), need32 = nets * ((P.B + 31) / 32);
-    // 16 sequences per cluster has the shorter step; use it when all its clusters are resident at once
-    int ns = (cap16 >= need16 || cap32 == 0) ? 16 : 32;
-    if (g_rec2_ns == 16 || g_rec2_ns == 32) ns = g_rec2_ns;
-    if ((ns == 16 ? cap16 : cap32) < 1) return cudaErrorNotSupported;
-    if (ns == 16) {
-        cudaLaunchConfig_t cfg = rec2_config<16>(need16, s, attr);
-        return cudaLaunchKernelEx(&cfg, rec2_fwd_kernel<16>, P, (P.B + 15) / 16);
+    const int cap1 = rec2_max_active_clusters<1>(), cap2 = rec2_max_active_clusters<2>();
+    const int need1 = nets * ((P.B + 15) / 16), need2 = nets * ((P.B + 31) / 32);
+    // one stream per cluster has the shorter step; use it when all its clusters are resident at once (or a batch leaves the
+    // second stream empty anyway), otherwise interleave two streams per cluster
+    int nstr = (cap1 >= need1 || cap2 == 0 || P.B <= 16) ? 1 : 2;
+    if (g_rec2_ns == 16) nstr = 1;
+    if (g_rec2_ns == 32) nstr = 2;
+    if ((nstr == 1 ? cap1 : cap2) < 1) return cudaErrorNotSupported;
+    if (nstr == 1) {
+        cudaLaunchConfig_t cfg = rec2_config<1>(need1, s, attr);
+        return cudaLaunchKernelEx(&cfg, rec2_fwd_kernel<1>, P, (P.B + 15) / 16);
     }
-    cudaLaunchConfig_t cfg = rec2_config<32>(need32, s, attr);
-    return cudaLaunchKernelEx(&cfg, rec2_fwd_kernel<32>, P, (P.B + 31) / 32);
+    cudaLaunchConfig_t cfg = rec2_config<2>(need2, s, attr);
+    return cudaLaunchKernelEx(&cfg, rec2_fwd_kernel<2>, P, (P.B + 31) / 32);
 }
-
 
 // ================================================================================================
 // Cluster-resident BPTT recurrence (online network): dh_{t-1} = dgates_t . W_hh without leaving the SMs.

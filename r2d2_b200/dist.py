@@ -2,8 +2,8 @@
 
 The reference has one learner and no collectives; this is the one exchange step the
 multi-GPU learner adds.  Replay blocks are sharded by actor -> rank (each rank owns an HBM block store and
-a sum tree over its own slots), every rank samples its local batch, and per update there is exactly one
-gradient all-reduce plus a scalar row-count reduction:
+a sum tree over its own slots), every rank samples its local batch, and per update there is one gradient
+all-reduce (issued in two pieces by the overlapped hook) that also carries the row count:
 
     grads   <- SUM over ranks of d(loss_sum_rank)          (4.33 M fp32 = 17.3 MB)
     rows    <- SUM over ranks of rows_rank
@@ -11,8 +11,9 @@ gradient all-reduce plus a scalar row-count reduction:
 
 which is exactly the gradient of the reference's ``(is_w * (q - target)**2).mean()`` (worker.py:354) taken over
 the GLOBAL batch, also when ranks hold different numbers of learning rows (ragged sequences).
-Priority updates stay shard-local; IS weights are normalised by the local batch minimum (documented deviation:
-per-shard stratification).
+Priority updates stay shard-local.  Importance weights: GlobalISWeights rescales each rank's weights by one scalar so
+that they equal the weights of a single prioritized sampler over all shards (one MIN all-reduce of a float64, on a
+side stream); what remains of the sharding is stratification (every rank contributes exactly B sequences).
 """
 from __future__ import annotations
 
@@ -41,27 +42,47 @@ def shard_of_actor(actor_id: int, world: int) -> int:
     return actor_id % world
 
 
+def _rows_slot(learner):
+    """Index of a padding slot of the flat gradient layout inside the dense range (value.2.bias holds one element and is
+    padded to four): the row count travels there, inside the gradient all-reduce, instead of in a collective of its own.
+    None for objects without a layout (the CPU stand-in of the gloo test)."""
+    off = getattr(learner.grads, "offsets", None)
+    if off is None or off[-1] - off[-2] < 2:
+        return None
+    return off[-1] - 1
+
+
 def make_grad_hook(group=None):
-    """grad_hook for DeviceLearner: global-mean gradient across ranks (see module docstring)."""
+    """grad_hook for DeviceLearner: global-mean gradient across ranks (see module docstring) with ONE all-reduce: the
+    local row count rides in a padding slot of the flat gradient buffer (zeroed again before the optimizer sees it)."""
     state = {}
 
     def hook(learner):
-        rows_g = state.get("rows")
-        if rows_g is None or rows_g.device != learner.grads.flat.device:
-            rows_g = state["rows"] = torch.zeros(1, dtype=torch.float32, device=learner.grads.flat.device)
-        work = dist.all_reduce(learner.grads.flat, op=dist.ReduceOp.SUM, group=group, async_op=True)
-        rows_g.copy_(learner.rows)
-        dist.all_reduce(rows_g, op=dist.ReduceOp.SUM, group=group)
-        work.wait()
-        torch.reciprocal(rows_g, out=learner.grad_scale)
+        flat = learner.grads.flat
+        slot = _rows_slot(learner)
+        if slot is None:                                      # no layout information: separate scalar reduction
+            rows_g = state.get("rows")
+            if rows_g is None or rows_g.device != flat.device:
+                rows_g = state["rows"] = torch.zeros(1, dtype=torch.float32, device=flat.device)
+            work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True)
+            rows_g.copy_(learner.rows)
+            dist.all_reduce(rows_g, op=dist.ReduceOp.SUM, group=group)
+            work.wait()
+            torch.reciprocal(rows_g, out=learner.grad_scale)
+            return
+        flat[slot:slot + 1].copy_(learner.rows)
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        torch.reciprocal(flat[slot:slot + 1], out=learner.grad_scale)
+        flat[slot:slot + 1].zero_()
     return hook
 
 
 def make_overlapped_grad_hook(learner, group=None):
     """Same reduction as make_grad_hook, but the FC/LSTM/head range of the flat gradient (98 % of the bytes) is all-reduced
     from a side stream as soon as r2d2_net_backward has finished it (r2d2_net_set_dense_grads_event), i.e. WHILE the conv
-    layers' data/weight gradients are still being computed; only the 0.3 MB conv range and the row count are reduced after
-    the backward pass.  NCCL backend only (the collectives are ordered by CUDA streams)."""
+    layers' data/weight gradients are still being computed; only the 0.3 MB conv range is reduced after the backward pass.
+    Two collectives per update (the row count rides in a padding slot of the dense range).  NCCL backend only (the
+    collectives are ordered by CUDA streams)."""
     from . import _lib
     from .learner_core import PARAM_NAMES
     dev = learner.grads.flat.device
@@ -70,22 +91,59 @@ def make_overlapped_grad_hook(learner, group=None):
     ev.record(torch.cuda.current_stream(dev))                 # materialise the cudaEvent_t
     _lib.check(_lib.lib().r2d2_net_set_dense_grads_event(learner._h, ev.cuda_event))
     dense_off = learner.grads.offsets[PARAM_NAMES.index("feature.7.weight")]
-    rows_g = torch.zeros(1, dtype=torch.float32, device=dev)
+    slot = _rows_slot(learner)
+    assert slot is not None and slot >= dense_off
     keep = {"event": ev, "stream": side}                      # owned by the hook: the library only borrows the event
 
     def hook(lrn):
         assert lrn is learner and keep
         flat = lrn.grads.flat
         with torch.cuda.stream(side):
-            side.wait_event(ev)                               # recorded inside the backward call that just returned
+            side.wait_event(ev)                               # recorded inside the backward call that just returned; the row
+            flat[slot:slot + 1].copy_(lrn.rows)               # count (K2, before the backward pass) is final by then as well
             w_dense = dist.all_reduce(flat[dense_off:], op=dist.ReduceOp.SUM, group=group, async_op=True)
         w_conv = dist.all_reduce(flat[:dense_off], op=dist.ReduceOp.SUM, group=group, async_op=True)
-        rows_g.copy_(lrn.rows)
-        dist.all_reduce(rows_g, op=dist.ReduceOp.SUM, group=group)
         w_dense.wait()
         w_conv.wait()
-        torch.reciprocal(rows_g, out=lrn.grad_scale)
+        torch.reciprocal(flat[slot:slot + 1], out=lrn.grad_scale)
+        flat[slot:slot + 1].zero_()                           # padding must be zero again: the global norm runs over the flat buffer
     return hook
+
+
+def global_is_factor(local_min_over_root: torch.Tensor, beta: float, group=None) -> torch.Tensor:
+    """Correction that turns shard-local importance weights into the weights of ONE prioritized sampler over all shards.
+
+    Rank s samples its part of the global batch with probability p_i / root_s from its own tree and normalises by its
+    own batch minimum: w_i = (p_i / min_s)^-beta (priority_tree.py:39-41).  Sampled jointly, the weight of i would be
+    ((p_i / root_s) / m)^-beta with m = min over the GLOBAL batch of p_j / root_s(j).  The two differ by the per-rank
+    scalar ((min_s / root_s) / m)^-beta <= 1, which needs one MIN all-reduce of one float64."""
+    m = local_min_over_root.detach().clone()
+    dist.all_reduce(m, op=dist.ReduceOp.MIN, group=group)
+    return torch.pow(local_min_over_root / m, -float(beta))
+
+
+class GlobalISWeights:
+    """Applies global_is_factor to a sampled batch on a side stream: the scalar reduction and the in-place scaling of
+    batch['is_weights'] overlap the forward unroll; `wait` (installed as DeviceLearner.pre_td_hook) joins before K2."""
+
+    def __init__(self, device, beta: float, group=None):
+        self.beta, self.group = beta, group
+        self.side = torch.cuda.Stream(device=device)
+        self.ev = torch.cuda.Event()
+        self.device = device
+
+    def correct(self, replay, batch, idx) -> None:
+        main = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self.side):
+            self.side.wait_stream(main)                       # after the sample / gather kernels
+            nodes = replay.tree.nodes_device()
+            leaf_base = (1 << (replay.tree.num_layers - 1)) - 1
+            m = (nodes[leaf_base + idx].min() / nodes[0]).reshape(1)
+            batch["is_weights"].mul_(global_is_factor(m, self.beta, self.group).to(torch.float32))
+            self.ev.record(self.side)
+
+    def wait(self, learner=None) -> None:
+        torch.cuda.current_stream(self.device).wait_event(self.ev)
 
 
 def broadcast_parameters(learner, src: int = 0, group=None) -> None:

@@ -243,6 +243,8 @@ class DeviceLearner:
         self._graphs, self._graph_seen = {}, {}
         # hook called between backward and the optimizer: (learner) -> None, e.g. NCCL all-reduce
         self.grad_hook: Optional[Callable[["DeviceLearner"], None]] = None
+        # hook called between the forward unroll and the TD kernel (e.g. join a side stream that rescales is_weights)
+        self.pre_td_hook: Optional[Callable[["DeviceLearner"], None]] = None
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -338,6 +340,8 @@ class DeviceLearner:
                                                     p(b["last_action"]), p(b["last_reward"]), p(b["hidden"]),
                                                     p(b["burn_in"]), p(b["learning"]), p(b["forward"]), p(self.q),
                                                     p(self.qn_online), p(self.qn_target), _lib.stream_ptr()))
+        if self.pre_td_hook is not None:
+            self.pre_td_hook(self)
         _lib.check(_lib.lib().r2d2_td_loss(p(self.q), p(self.qn_online), p(self.qn_target), p(b["action"]),
                                            p(b["n_step_reward"]), p(b["gamma"]), p(b["is_weights"]), p(b["learning"]),
                                            self.B, self.A, p(self.td), p(self.prio), p(self.loss_sum), p(self.rows),
@@ -379,7 +383,7 @@ class DeviceLearner:
         """One learner update on prepared device buffers.  Nothing in the launch sequence depends on host values that change
         between updates (update count and row count live on the device), so for a recurring set of buffers the ~45 launches
         are captured once in a CUDA graph and replayed."""
-        if not self.use_graph or self.grad_hook is not None:
+        if not self.use_graph or self.grad_hook is not None or self.pre_td_hook is not None:
             return self._update_eager(b)
         key = (_lib.lib().r2d2_config_epoch(),) + tuple(None if v is None else (v.data_ptr() if isinstance(v, torch.Tensor) else v)
                                                       for v in (b.get(k) for k in _BATCH_KEYS))

@@ -235,6 +235,7 @@ class Learner:
         self.shared_model = model
         self.game_name = game_name
         self.replay = None                     # DeviceReplay, created on the first forwarded block
+        self.is_weight_sync = None             # dist.GlobalISWeights in data-parallel runs
         self._results = None                   # two pinned result slots (priorities, loss) for enqueue_update/collect
         self._sum_loss = 0.0
         self.env_steps = 0
@@ -310,6 +311,8 @@ class Learner:
     # -- one update from the HBM-resident replay (sample -> update -> priority update, no host round trip) --------
     def update_from_replay(self):
         batch, idx, old_ptr = self.replay.sample(fuse_into=self.core)     # frames go straight into conv1's staging layout
+        if self.is_weight_sync is not None:                               # data parallel: weights of one sampler over all shards
+            self.is_weight_sync.correct(self.replay, batch, idx)
         self.core.update(batch)
         self.replay.update_priorities(idx, self.core.prio, old_ptr)
         self.env_steps = self.replay.env_steps
