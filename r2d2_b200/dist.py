@@ -107,6 +107,9 @@ def make_overlapped_grad_hook(learner, group=None):
         w_conv.wait()
         torch.reciprocal(flat[slot:slot + 1], out=lrn.grad_scale)
         flat[slot:slot + 1].zero_()                           # padding must be zero again: the global norm runs over the flat buffer
+    # The hook is stream-ordered only, but capturing NCCL work into the update's CUDA graph bought nothing at 2 GPUs (2.67 ms
+    # per step either way) and left the process group hanging at shutdown: data-parallel updates stay eager.
+    hook.capturable = False
     return hook
 
 

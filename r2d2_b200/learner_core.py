@@ -383,7 +383,8 @@ class DeviceLearner:
         """One learner update on prepared device buffers.  Nothing in the launch sequence depends on host values that change
         between updates (update count and row count live on the device), so for a recurring set of buffers the ~45 launches
         are captured once in a CUDA graph and replayed."""
-        if not self.use_graph or self.grad_hook is not None or self.pre_td_hook is not None:
+        if not self.use_graph or self.pre_td_hook is not None or \
+                (self.grad_hook is not None and not getattr(self.grad_hook, "capturable", False)):
             return self._update_eager(b)
         key = (_lib.lib().r2d2_config_epoch(),) + tuple(None if v is None else (v.data_ptr() if isinstance(v, torch.Tensor) else v)
                                                       for v in (b.get(k) for k in _BATCH_KEYS))
@@ -398,8 +399,15 @@ class DeviceLearner:
             if len(self._graphs) >= 8:
                 self._graphs.clear()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._update_eager(b, _count=False)
+            try:
+                with torch.cuda.graph(g):
+                    self._update_eager(b, _count=False)
+            except Exception as e:                           # e.g. a collective that cannot be captured: stay eager from now on
+                import warnings
+                warnings.warn(f"CUDA-graph capture of the learner update failed ({e}); continuing with eager launches")
+                self.use_graph = False
+                torch.cuda.synchronize(self.device)
+                return self._update_eager(b)
             self._graphs[key] = (g, b)                       # the graph reads these buffers: keep them alive with it
             g = self._graphs[key]
         self._live = g[1]

@@ -313,6 +313,8 @@ class Learner:
         batch, idx, old_ptr = self.replay.sample(fuse_into=self.core)     # frames go straight into conv1's staging layout
         if self.is_weight_sync is not None:                               # data parallel: weights of one sampler over all shards
             self.is_weight_sync.correct(self.replay, batch, idx)
+            if self.core.pre_td_hook is None:                             # no hook installed (graph replay): join here
+                self.is_weight_sync.wait()
         self.core.update(batch)
         self.replay.update_priorities(idx, self.core.prio, old_ptr)
         self.env_steps = self.replay.env_steps
