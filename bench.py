@@ -266,6 +266,75 @@ def kernel_times(fn, steps=3):
     return "\n".join(lines)
 
 
+def run_ingest_mode(args, learner, replay, C, ms_step_plain):
+    """BASELINE config #3: the learner + HBM replay + sum tree (2^20 slots) while `--actors` producers feed blocks through the
+    pinned staging ring.  Runs the product's own Learner.run loop (prefetch thread packs blocks into pinned memory, the learner
+    thread commits them: one async H2D per block on the ingest stream, priorities enter the tree at the next sample) for a
+    fixed number of updates and reports learner throughput with ingest on, the achieved ingest rate and the slowdown against
+    the ingest-free number.  Producers replay pre-generated synthetic actor blocks at a fixed rate (emulator and actor
+    inference are outside the learner path; 8 CPU actors of the reference produce ~4 blocks/s, the default here is 50x that)."""
+    import queue
+    from r2d2_b200 import config
+    from r2d2_b200.synthetic import synthetic_blocks
+    from r2d2_b200.worker import BLOCK_MSG
+    updates = max(200, 10 * args.steps)
+    bq, pq = queue.Queue(256), queue.Queue()
+    learner.batch_queue, learner.priority_queue = bq, pq
+    learner.batched_data = []
+    pool = synthetic_blocks(8, A, C, seed=4242, burn_in=BURN, learning=LEARN, forward=FWD, block_len=BLOCK_LEN)
+    stop = threading.Event()
+    sent = [0] * args.actors
+    period = args.actors / float(args.ingest_blocks_per_s)
+
+    def producer(i):
+        k = i
+        nxt = time.perf_counter() + period * i / args.actors
+        while not stop.is_set():
+            blk, prio = pool[k % len(pool)]
+            try:
+                bq.put((BLOCK_MSG, blk, prio, None), timeout=0.05)
+                sent[i] += 1
+                k += args.actors
+            except queue.Full:
+                pass
+            nxt += period
+            time.sleep(max(0.0, nxt - time.perf_counter()))
+
+    def drain():
+        while not stop.is_set():
+            try:
+                pq.get(timeout=0.05)
+            except queue.Empty:
+                pass
+
+    start_updates = learner.num_updates
+    config.training_steps = start_updates + updates + 50
+    config.learning_starts = 0
+    b0 = replay.ingested_bytes
+    th = [threading.Thread(target=producer, args=(i,), daemon=True) for i in range(args.actors)] + [threading.Thread(target=drain, daemon=True)]
+    runner = threading.Thread(target=learner.run, daemon=True)
+    for t in th:
+        t.start()
+    runner.start()
+    while learner.num_updates < start_updates + 50:                     # warm-up with ingest running
+        time.sleep(0.005)
+    torch.cuda.synchronize()
+    u0, t0, bytes0 = learner.num_updates, time.perf_counter(), replay.ingested_bytes
+    while learner.num_updates < start_updates + 50 + updates - 5:
+        time.sleep(0.005)
+    torch.cuda.synchronize()
+    u1, t1, bytes1 = learner.num_updates, time.perf_counter(), replay.ingested_bytes
+    runner.join(timeout=30)
+    stop.set()
+    dt = t1 - t0
+    seq_s = (u1 - u0) * B / dt
+    return {"actors": args.actors, "updates_timed": u1 - u0, "value": seq_s, "unit": "sequences/s", "ms_per_step": 1e3 * dt / (u1 - u0),
+            "ingest_blocks_per_s": (bytes1 - bytes0) / replay.blob_bytes / dt, "ingest_gb_per_s": (bytes1 - bytes0) / dt / 1e9,
+            "block_bytes": replay.blob_bytes, "relative_to_no_ingest": seq_s / (B / (ms_step_plain * 1e-3)),
+            "note": "Learner.run loop, wall clock (host-timed: the loop polls its queue between updates); producers offer "
+                    f"{args.ingest_blocks_per_s} blocks/s in total; H2D copies on the ingest stream overlap the running update"}
+
+
 def run_ours(args):
     import torch.distributed as dist
     from r2d2_b200 import _lib, config
@@ -390,14 +459,16 @@ def run_ours(args):
             fl = flops_per_sequence(C) * B
             ach = fl / (ms_unroll * 1e-3) / 1e12
             traffic = None
-            tpath = os.path.join(ROOT, "profiles", "r01_unroll_traffic.json")
+            tpath = os.path.join(ROOT, "profiles", "r02_unroll_traffic.json")
             if os.path.exists(tpath) and C == 4 and args.precision == "strict":
                 with open(tpath) as f:
                     traffic = json.load(f)["bytes"]        # dram bytes of the same launches from the committed ncu pass
             line["roofline"] = {"bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s",
                                 "frac": ach / peaks["tflops"], "traffic": traffic, "peak_source": peaks["source"],
-                                "kernel": "K1+K1b unroll group (forward online+target, BPTT backward): winconv/winwgrad/umma2/rec_fwd/rec_bwd launches",
+                                "kernel": "K1+K1b unroll group (forward online+target, BPTT backward): winconv/winwgrad/umma3/umma2/rec2_fwd/rec2_bwd launches",
                                 "ms": ms_unroll, "algorithmic_gflop_per_launch": fl / 1e9}
+        if world == 1 and args.actors > 0:
+            line["ingest"] = run_ingest_mode(args, learner, replay, C, ms_step)
         if world == 1 and not args.no_cpu_baseline:
             torch.cuda.synchronize()
             cpu = reference_subprocess("cpu", 3, 3, C)               # the reference's CPU learner on this box's host cores
@@ -427,6 +498,10 @@ def main():
                     help="--impl reference only: cpu = the reference's CPU learner (the driver's reference arm), cuda = the reference's own "
                          "learner on this GPU through stock PyTorch eager (on-box comparator)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--actors", type=int, default=0,
+                    help="BASELINE config #3 (N = 1 only): also run the learner with this many block producers feeding the HBM replay "
+                         "through the pinned staging ring and report throughput with ingest on (adds an `ingest` object to the line)")
+    ap.add_argument("--ingest-blocks-per-s", type=float, default=200.0, help="total block rate the producers offer (400-step blocks)")
     ap.add_argument("--kernel-times", action="store_true", help="also write gpurun_out/kernel_times.txt (per-kernel CUPTI durations)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -409,6 +409,7 @@ constexpr int RB2_BOP = 2 * 4096;                  // dgates as B operand: [k-bl
 constexpr int RB2_SLOT = 2048;                     // one source's partial for my 32 units: [32][16] fp32
 constexpr int RB2_RECV = 2 * R2_CL * RB2_SLOT;     // [parity][source]
 constexpr int RB2_SMEM = RB2_WLO + RB2_BOP + RB2_RECV + 1024 + 256;
+constexpr int RB2_THREADS = 32 * R2_EW + 128;     // 16 pointwise / epilogue warps + 4 MMA-issue warps
 constexpr int RB2_ACC_COL = 256;                   // TMEM: W^T hi in columns [0,256), accumulators 4 x 32 columns at 256
 
 __device__ __forceinline__ void st_async_v4(uint32_t dst, uint32_t mbar, float a, float b, float c, float d) {
@@ -421,7 +422,7 @@ __device__ __forceinline__ float ld_nc_f1(const float* p) {
     return r;
 }
 
-__global__ void __launch_bounds__(R2_THREADS, 1) rec2_bwd_kernel(const RecBwdParams P) {
+__global__ void __launch_bounds__(RB2_THREADS, 1) rec2_bwd_kernel(const RecBwdParams P) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t pad = (1024u - (raw & 1023u)) & 1023u;
@@ -431,8 +432,8 @@ __global__ void __launch_bounds__(R2_THREADS, 1) rec2_bwd_kernel(const RecBwdPar
     const uint32_t sR = sB + RB2_BOP;                  // receive slots [parity][source]
     uint8_t* bop_ptr = smem + RB2_WLO;
     const float* recv_ptr = reinterpret_cast<const float*>(smem + RB2_WLO + RB2_BOP);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RB2_WLO + RB2_BOP + RB2_RECV);       // recv_full[2] | accf
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RB2_WLO + RB2_BOP + RB2_RECV);       // recv_full[2] | accf[4] (one per M-tile)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t c = cluster_ctarank();
@@ -441,7 +442,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) rec2_bwd_kernel(const RecBwdPar
     const bool want_lo = !P.fast;
 
     if (tid == 0) {
-        for (int i = 0; i < 3; ++i) mbar_init(smem_u32(&bars[i]), 1);
+        for (int i = 0; i < 6; ++i) mbar_init(smem_u32(&bars[i]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == R2_EW) {
@@ -450,7 +451,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) rec2_bwd_kernel(const RecBwdPar
     }
     // W^T lo plane -> shared memory: tile (m, kb) = units [128m, +128) x own gate rows [64 kb, +64), K-major SWIZZLE_128B
     if (want_lo) {
-        for (int u = tid; u < 4 * 2 * 128 * 8; u += R2_THREADS) {
+        for (int u = tid; u < 4 * 2 * 128 * 8; u += RB2_THREADS) {
             const int jj = u & 7, row = (u >> 3) & 127, tile = u >> 10, m = tile >> 1, kb = tile & 1;
             const uint32_t dst = (uint32_t)(tile * 16384 + (row >> 3) * 1024 + (row & 7) * 128 + ((jj ^ (row & 7)) << 4));
             cp_async16(sW + dst, P.WTlo + (size_t)(128 * m + row) * REC_G4 + 128 * (int)c + 64 * kb + 8 * jj, true);
@@ -540,7 +541,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) rec2_bwd_kernel(const RecBwdPar
                 fence_proxy_async_smem();
             }
             tc_fence_before();
-            asm volatile("bar.sync 2, %0;" ::"n"(R2_THREADS) : "memory");        // B operand complete -> MMA warp
+            asm volatile("bar.sync 2, %0;" ::"n"(RB2_THREADS) : "memory");       // B operand complete -> MMA warps
             // ---- off the critical path: dgates_t to global memory, operands of the next step
             if (own) {
                 const size_t o = ((size_t)t * B + b) * REC_G4 + 4 * unit;
@@ -550,7 +551,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) rec2_bwd_kernel(const RecBwdPar
             if (t == 0) break;                          // dh_{-1} is not needed
             prefetch(t - 1);
             // ---- reduce-scatter of this step's partial: warp (q, m) holds units [128 m + 32 q, +32) = CTA 4 m + q
-            mbar_wait(smem_u32(&bars[2]), (uint32_t)step & 1u);
+            mbar_wait(smem_u32(&bars[2 + m]), (uint32_t)step & 1u);
             tc_fence_after();
             float v[16];
             {
@@ -574,33 +575,32 @@ __global__ void __launch_bounds__(R2_THREADS, 1) rec2_bwd_kernel(const RecBwdPar
             tc_fence_before();
         }
     } else {
-        // ------------------------------------------------------------------ MMA issue
+        // ------------------------------------------------------------------ MMA issue: FOUR warps, one per M-tile of 128 units (a single
+        // issuing thread needs ~1 us for the step's 64 MMAs -- instruction-issue bound -- on a 4 us critical path)
         constexpr uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);
         constexpr uint32_t idesc2 = idesc_base | ((32u >> 3) << 17), idesc1 = idesc_base | ((16u >> 3) << 17);
+        const int mm = warp - R2_EW;
         const bool leader = elect_one();
         const uint32_t uW = __shfl_sync(0xffffffffu, sW, 0), uB = __shfl_sync(0xffffffffu, sB, 0);
         const uint32_t uT = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint32_t acc = uT + (uint32_t)(RB2_ACC_COL + 32 * mm);
         for (int t = T - 1; t >= 0; --t) {
-            asm volatile("bar.sync 2, %0;" ::"n"(R2_THREADS) : "memory");
+            asm volatile("bar.sync 2, %0;" ::"n"(RB2_THREADS) : "memory");
             if (t == 0) break;
             tc_fence_after();
             if (leader) {
 #pragma unroll
-                for (int mm = 0; mm < 4; ++mm) {
-                    const uint32_t acc = uT + (uint32_t)(RB2_ACC_COL + 32 * mm);
-#pragma unroll
-                    for (int kk = 0; kk < 8; ++kk) {
-                        const uint64_t b_hl = umma_desc_sw128(uB + (uint32_t)((kk >> 2) * 4096 + (kk & 3) * 32));      // rows 0-15 hi, 16-31 lo
-                        const uint32_t a_t = uT + (uint32_t)(64 * mm + 8 * kk);
-                        if (want_lo) {
-                            umma_bf16_ts(acc, a_t, b_hl, idesc2, kk ? 1u : 0u);
-                            umma_bf16(acc, umma_desc_sw128(uW + (uint32_t)((mm * 2 + (kk >> 2)) * 16384 + (kk & 3) * 32)), b_hl, idesc1, 1u);
-                        } else {
-                            umma_bf16_ts(acc, a_t, b_hl, idesc1, kk ? 1u : 0u);
-                        }
+                for (int kk = 0; kk < 8; ++kk) {
+                    const uint64_t b_hl = umma_desc_sw128(uB + (uint32_t)((kk >> 2) * 4096 + (kk & 3) * 32));      // rows 0-15 hi, 16-31 lo
+                    const uint32_t a_t = uT + (uint32_t)(64 * mm + 8 * kk);
+                    if (want_lo) {
+                        umma_bf16_ts(acc, a_t, b_hl, idesc2, kk ? 1u : 0u);
+                        umma_bf16(acc, umma_desc_sw128(uW + (uint32_t)((mm * 2 + (kk >> 2)) * 16384 + (kk & 3) * 32)), b_hl, idesc1, 1u);
+                    } else {
+                        umma_bf16_ts(acc, a_t, b_hl, idesc1, kk ? 1u : 0u);
                     }
                 }
-                umma_commit(smem_u32(&bars[2]));
+                umma_commit(smem_u32(&bars[2 + mm]));
             }
             __syncwarp();
         }
@@ -624,7 +624,7 @@ static inline cudaError_t launch_rec2_bwd(const RecBwdParams& P, cudaStream_t s)
     cudaLaunchAttribute attr[1];
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(((P.B + 15) / 16) * R2_CL);
-    cfg.blockDim = dim3(R2_THREADS);
+    cfg.blockDim = dim3(RB2_THREADS);
     cfg.dynamicSmemBytes = RB2_SMEM;
     cfg.stream = s;
     attr[0].id = cudaLaunchAttributeClusterDimension;

@@ -24,7 +24,7 @@ _FIELDS = ["obs", "last_action", "last_reward", "action", "n_step_reward", "gamm
 class DeviceReplay:
     def __init__(self, buffer_capacity: int, block_length: int, burn_in_steps: int, learning_steps: int, forward_steps: int,
                  action_dim: int, obs_shape=(1, 84, 84), hidden_dim: int = 512, alpha: float = 0.9, beta: float = 0.6,
-                 batch_size: int = 64, device=None, seed: int = 0, staging_slots: int = 4,
+                 batch_size: int = 64, device=None, seed: int = 0, staging_slots: int = 6,
                  tree_capacity: Optional[int] = None):
         _lib.require_device()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -51,6 +51,14 @@ class DeviceReplay:
         self._staging = [torch.zeros(self.blob_bytes, dtype=torch.uint8).pin_memory() for _ in range(staging_slots)]
         self._staging_events = [None] * staging_slots
         self._slot = 0
+        import threading
+        self._stage_lock = threading.Lock()
+        self._slot_free = [threading.Event() for _ in range(staging_slots)]
+        for e in self._slot_free:
+            e.set()
+        self._pending = []                      # committed blocks whose priorities have not entered the tree yet (commit(defer=True))
+        self._gather_event = None               # recorded after the most recent gather: an ingest copy may not overtake it
+        self.ingested_bytes = 0
         self.ingest_stream = torch.cuda.Stream(device=self.device)
         # reference bookkeeping (worker.py:50-68)
         self.block_ptr = 0
@@ -109,27 +117,40 @@ class DeviceReplay:
         put("num_seq", np.array([block.num_sequences], dtype=np.int32), np.int32)
         return self.blob_bytes
 
-    @_lib.on_device
-    def add(self, block, priority: np.ndarray, episode_reward: Optional[float] = None) -> None:
-        slot = self._slot
-        self._slot = (slot + 1) % len(self._staging)
+    def stage(self, block):
+        """Host half of an insertion: pack `block` into a free pinned staging slot.  Thread-safe and CUDA-free apart from
+        waiting for the slot's previous copy, so a prefetch thread can run it while the learner trains (12.5 MB of memcpy
+        per 4-channel block).  Returns a handle for commit()."""
+        with self._stage_lock:
+            slot = self._slot
+            self._slot = (slot + 1) % len(self._staging)
+        self._slot_free[slot].wait()              # staged but not yet committed by the consumer
+        self._slot_free[slot].clear()
         ev = self._staging_events[slot]
         if ev is not None:
             ev.synchronize()                      # the previous copy out of this pinned slot has completed
-        stage = self._staging[slot]
-        nbytes = self.pack(block, stage.numpy())
-        main = torch.cuda.current_stream(self.device)
+        nbytes = self.pack(block, self._staging[slot].numpy())
+        return slot, nbytes, int(np.sum(block.learning_steps, dtype=np.int64))
+
+    @_lib.on_device
+    def commit(self, handle, priority: np.ndarray, episode_reward: Optional[float] = None, defer: bool = False) -> None:
+        """Device half: ONE async H2D copy of the staged blob on the ingest stream (ordered after the last gather, which may
+        still read the ring slot being overwritten) + the reference's bookkeeping (worker.py:141-161).  The slot priorities
+        enter the sum tree, and the launching stream joins the copy, either now or -- defer=True -- at the next sample(),
+        so that the copy overlaps the update that is running."""
+        slot, nbytes, steps = handle
         with torch.cuda.stream(self.ingest_stream):
-            self.ingest_stream.wait_stream(main)  # do not overwrite a slot a running gather may still read
-            _lib.check(_lib.lib().r2d2_replay_ingest(self._h, self.block_ptr, stage.data_ptr(), nbytes,
+            if self._gather_event is not None:
+                self.ingest_stream.wait_event(self._gather_event)
+            _lib.check(_lib.lib().r2d2_replay_ingest(self._h, self.block_ptr, self._staging[slot].data_ptr(), nbytes,
                                                      self.ingest_stream.cuda_stream))
             done = torch.cuda.Event()
             done.record(self.ingest_stream)
         self._staging_events[slot] = done
-        main.wait_event(done)                     # later samples see the block
+        self._slot_free[slot].set()
         idxes = np.arange(self.block_ptr * self.seq_per_block, (self.block_ptr + 1) * self.seq_per_block, dtype=np.int64)
-        self.tree.update(idxes, np.asarray(priority, dtype=np.float32))
-        steps = int(np.sum(block.learning_steps, dtype=np.int64))
+        self._pending.append((done, idxes, np.asarray(priority, dtype=np.float32)))
+        self.ingested_bytes += nbytes
         self.size += steps - int(self._block_steps[self.block_ptr])
         self._block_steps[self.block_ptr] = steps
         self.env_steps += steps
@@ -137,16 +158,32 @@ class DeviceReplay:
         if episode_reward:
             self.episode_reward += episode_reward
             self.num_episodes += 1
+        if not defer:
+            self._activate_pending()
+
+    def _activate_pending(self) -> None:
+        main = torch.cuda.current_stream(self.device)
+        for done, idxes, prio in self._pending:
+            main.wait_event(done)                 # later samples see the block
+            self.tree.update(idxes, prio)
+        self._pending.clear()
+
+    def add(self, block, priority: np.ndarray, episode_reward: Optional[float] = None) -> None:
+        """ReplayBuffer.add (worker.py:141-161): stage + commit, priorities visible immediately."""
+        self.commit(self.stage(block), priority, episode_reward)
 
     # ------------------------------------------------------------------ sample_batch (worker.py:163-240), on device
     @_lib.on_device
     def sample(self, unit_uniforms: Optional[torch.Tensor] = None, fuse_into=None):
         """Returns (batch dict of device tensors, idxes int64 device, old_ptr).  With fuse_into = a DeviceLearner whose
         shape matches, frames are written straight into its space-to-depth staging buffer and batch["obs"] is None."""
+        self._activate_pending()
         idx, isw = self.tree.sample_device(self.batch_size, unit_uniforms)
-        if fuse_into is not None:
-            return self.gather_fused(idx, isw, fuse_into), idx, self.block_ptr
-        return self.gather(idx, isw), idx, self.block_ptr
+        out = self.gather_fused(idx, isw, fuse_into) if fuse_into is not None else self.gather(idx, isw)
+        if self._gather_event is None:
+            self._gather_event = torch.cuda.Event()
+        self._gather_event.record(torch.cuda.current_stream(self.device))
+        return out, idx, self.block_ptr
 
     def gather_fused(self, idx: torch.Tensor, isw: torch.Tensor, core) -> dict:
         assert core.B == self.batch_size and core.T == self.T and core.C == self.C

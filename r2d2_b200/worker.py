@@ -51,6 +51,7 @@ class Block:                       # worker.py:23-35
 
 
 BLOCK_MSG = "r2d2_b200.block"      # tag of (tag, block, priority, episode_reward) messages on batch_queue
+STAGED_MSG = "r2d2_b200.staged"    # (tag, staging handle, priority, episode_reward): a block already packed into pinned memory
 STATS_MSG = "r2d2_b200.stats"      # tag of (tag, training_steps, sum_loss, size, env_steps) messages on priority_queue
 
 
@@ -333,6 +334,10 @@ class Learner:
                        os.path.join('models', '{}{}.pth'.format(self.game_name, self.num_updates)))
 
     def _ingest(self, msg):
+        if msg[0] == STAGED_MSG:                                                   # packed into pinned memory by the prefetch thread
+            _, handle, priority, episode_reward = msg
+            self.replay.commit(handle, priority, episode_reward, defer=True)       # the H2D copy overlaps the running update
+            return
         _, block, priority, episode_reward = msg
         if self.replay is None:
             from .replay import DeviceReplay
@@ -345,7 +350,11 @@ class Learner:
     def prepare_data(self):                                                        # worker.py:309-316
         while True:
             if not self.batch_queue.empty() and len(self.batched_data) < 64:
-                self.batched_data.append(self.batch_queue.get_nowait())
+                data = self.batch_queue.get_nowait()
+                if self.replay is not None and isinstance(data, tuple) and len(data) == 4 and isinstance(data[0], str) and data[0] == BLOCK_MSG:
+                    # host half of the insertion here, off the learner thread: 3-12 MB of packing per block
+                    data = (STAGED_MSG, self.replay.stage(data[1]), data[2], data[3])
+                self.batched_data.append(data)
             else:
                 time.sleep(0.001)
 
@@ -360,7 +369,7 @@ class Learner:
             while self.batched_data:
                 data = self.batched_data.pop(0)
                 worked = True
-                if isinstance(data, tuple) and len(data) == 4 and isinstance(data[0], str) and data[0] == BLOCK_MSG:
+                if isinstance(data, tuple) and len(data) == 4 and isinstance(data[0], str) and data[0] in (BLOCK_MSG, STAGED_MSG):
                     self._ingest(data)
                 else:                                                              # reference-format 14-tuple
                     staged = data if (isinstance(data[0], str) and data[0] == "staged") else self.prefetch(data)

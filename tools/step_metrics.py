@@ -13,7 +13,7 @@ import json
 import re
 import sys
 
-UNROLL = ("umma2_kernel", "winconv_kernel", "winwgrad_kernel", "rec_fwd_kernel", "rec_bwd_kernel")
+UNROLL = ("umma2_kernel", "umma3_kernel", "winconv_kernel", "winwgrad_kernel", "rec_fwd_kernel", "rec_bwd_kernel", "rec2_fwd_kernel", "rec2_bwd_kernel")
 
 
 def num(x):
