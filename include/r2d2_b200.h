@@ -159,6 +159,9 @@ int r2d2_set_persistent_recurrence(int on);
 /* Debug: device buffer of T*8 uint64 that receives per-step globaltimer stamps of CTA 0 of the persistent recurrence
  * (poll start, flag acquired, tile staged, MMAs done, epilogue done, released); NULL detaches. */
 int r2d2_debug_rec_trace(void* device_buffer);
+/* The same for the cluster BPTT kernel (stamps: step start, partials received, dgates staged, barrier passed, accumulator
+ * ready, partial pushed). */
+int r2d2_debug_rec_trace_bwd(void* device_buffer);
 /* Test/debug access to device intermediates (see net.cu for the names). */
 void* r2d2_net_debug_ptr(r2d2_net* n, int which, const char* name);
 

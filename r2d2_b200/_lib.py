@@ -72,6 +72,7 @@ SIGNATURES = {
     "r2d2_debug_cluster_capacity": (C.c_int, []),
     "r2d2_config_epoch": (C.c_int, []),
     "r2d2_debug_rec_trace": (C.c_int, [p]),
+    "r2d2_debug_rec_trace_bwd": (C.c_int, [p]),
     "r2d2_net_debug_ptr": (p, [p, C.c_int, C.c_char_p]),
     "r2d2_replay_create": (C.c_int, [C.c_int] * 8 + [C.POINTER(p)]),
     "r2d2_replay_destroy": (C.c_int, [p]),

@@ -695,6 +695,7 @@ int g_cluster_recurrence = [] { const char* e = getenv("R2D2_CLUSTER_REC"); retu
 namespace r2d2 { int g_config_epoch = 0; }
 namespace r2d2 { int g_rec2_ns = [] { const char* e = getenv("R2D2_REC2_NS"); return e ? atoi(e) : 0; }(); }   // sequences per recurrence cluster: 0 auto, 16, 32
 int g_persistent_recurrence = 1;
+unsigned long long* g_rec_trace_bwd = nullptr; // same for the cluster BPTT kernel (r2d2_debug_rec_trace_bwd)
 unsigned long long* g_rec_trace = nullptr;   // debug: device buffer [T][8] of step timestamps (r2d2_debug_rec_trace)     // 0: per-step launches (also the path for B > 64)
 
 // device copy of the parameter offsets, kept in a side table keyed by handle
@@ -1248,6 +1249,7 @@ int r2d2_net_backward(r2d2_net* n, const float* params, const float* dq, float* 
         P.WThi = pk.WhhT_p.hi; P.WTlo = pk.WhhT_p.lo; P.dH = n->dH; P.Gs = ac.Gs; P.Cs = ac.Cs;
         P.c0 = n->hidden + H; P.ld_c0 = 2 * H; P.len = n->len_learn; P.DGhi = n->DG.hi; P.DGlo = n->DG.lo;
         P.partial = n->rec_partial; P.flags = n->rec_bar + 32; P.B = B; P.T = T; P.fast = g_fast_math == 1;
+        P.trace = g_rec_trace_bwd;
         cudaError_t e = g_cluster_recurrence ? launch_rec2_bwd(P, s) : cudaErrorNotSupported;     // 16-CTA clusters, DSMEM reduce-scatter
         if (e == cudaErrorNotSupported && B <= 64) e = launch_rec_bwd(P, s);                       // L2-flag cooperative kernel
         if (e != cudaErrorNotSupported) {
@@ -1373,6 +1375,13 @@ int r2d2_set_persistent_recurrence(int on) {
 int r2d2_debug_rec_trace(void* device_buffer) {
     ++g_config_epoch;
     g_rec_trace = (unsigned long long*)device_buffer;
+    return R2D2_OK;
+}
+
+/* debug: per-step globaltimer stamps of CTA 0 of the cluster BPTT kernel (T*8 uint64) */
+int r2d2_debug_rec_trace_bwd(void* device_buffer) {
+    ++g_config_epoch;
+    g_rec_trace_bwd = (unsigned long long*)device_buffer;
     return R2D2_OK;
 }
 

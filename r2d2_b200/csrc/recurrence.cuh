@@ -302,6 +302,7 @@ struct RecBwdParams {
     float* partial;                           // [2][8][64][512] fp32 scratch
     unsigned int* flags;                      // [8] flagDG + [16] flagDH, zero before launch
     int B, T, fast;
+    unsigned long long* trace = nullptr;      // optional [T][8] globaltimer stamps of CTA 0 (cluster kernel, debug)
 };
 
 __global__ void __launch_bounds__(UM_THREADS, 1) rec_bwd_kernel(const RecBwdParams P) {

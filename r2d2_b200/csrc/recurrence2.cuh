@@ -512,6 +512,8 @@ __global__ void __launch_bounds__(RB2_THREADS, 1) rec2_bwd_kernel(const RecBwdPa
             float dh = dh_n;
             const float ct = ct_n, cp = cp_n;
             const bool live = own && t < len;
+            const bool tr = P.trace && blockIdx.x == 0 && tid == 0;
+            if (tr) P.trace[step * 8 + 0] = gtime();
             if (step > 0) {                            // partials of dgates_{t+1} . W_hh for my units have landed (parity of t+1)
                 const int par = (t + 1) & 1;
                 if (tid == 0) mbar_arrive_expect_tx(smem_u32(&bars[par]), R2_CL * RB2_SLOT);
@@ -522,6 +524,7 @@ __global__ void __launch_bounds__(RB2_THREADS, 1) rec2_bwd_kernel(const RecBwdPa
                 for (int s = 0; s < R2_CL; ++s) acc += rp[s * (RB2_SLOT / 4)];
                 dh += acc;
             }
+            if (tr) P.trace[step * 8 + 1] = gtime() + (unsigned long long)(dh == 12345.f);
             float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
             if (live) {
                 const float tc = fast_tanh(ct);
@@ -541,7 +544,9 @@ __global__ void __launch_bounds__(RB2_THREADS, 1) rec2_bwd_kernel(const RecBwdPa
                 fence_proxy_async_smem();
             }
             tc_fence_before();
+            if (tr) P.trace[step * 8 + 2] = gtime();
             asm volatile("bar.sync 2, %0;" ::"n"(RB2_THREADS) : "memory");       // B operand complete -> MMA warps
+            if (tr) P.trace[step * 8 + 3] = gtime();
             // ---- off the critical path: dgates_t to global memory, operands of the next step
             if (own) {
                 const size_t o = ((size_t)t * B + b) * REC_G4 + 4 * unit;
@@ -553,6 +558,7 @@ __global__ void __launch_bounds__(RB2_THREADS, 1) rec2_bwd_kernel(const RecBwdPa
             // ---- reduce-scatter of this step's partial: warp (q, m) holds units [128 m + 32 q, +32) = CTA 4 m + q
             mbar_wait(smem_u32(&bars[2 + m]), (uint32_t)step & 1u);
             tc_fence_after();
+            if (tr) P.trace[step * 8 + 4] = gtime();
             float v[16];
             {
                 const uint32_t a0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(RB2_ACC_COL + 32 * m);
@@ -572,6 +578,7 @@ __global__ void __launch_bounds__(RB2_THREADS, 1) rec2_bwd_kernel(const RecBwdPa
 #pragma unroll
                 for (int i = 0; i < 4; ++i) st_async_v4(dst + 16 * i, bar, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
             }
+            if (tr) P.trace[step * 8 + 5] = gtime();
             tc_fence_before();
         }
     } else {
