@@ -464,6 +464,7 @@ def run_ours(args):
                 "config": {"workload": f"configs[1]: 1xB200 learner per rank, batch {B}/GPU, b/l/f {BURN}/{LEARN}/{FWD} (T={T}), "
                                        f"{C}x84x84 u8 frames, A={A}, HBM replay of {NUM_BLOCKS} blocks, sum tree 2^20",
                            "channels": C, "global_batch": world * B, "parallelism": f"dp{world}", "precision": args.precision,
+                           "host": f"staging copies on high-priority streams; CUDA_DEVICE_MAX_CONNECTIONS={os.environ.get('CUDA_DEVICE_MAX_CONNECTIONS')} (binding the process to the GPU's NUMA node was measured and made the copies slower on this pool: not done)",
                            "l2": f"inputs larger than L2: batches are gathered from a {NUM_BLOCKS * replay.blob_bytes / 1e9:.1f} GB HBM "
                                  f"block store; ~1 GB of activations streamed per step"},
                 "clocks": sampler.summary(),
@@ -519,6 +520,9 @@ def main():
     ap.add_argument("--ingest-blocks-per-s", type=float, default=200.0, help="total block rate the producers offer (400-step blocks)")
     ap.add_argument("--kernel-times", action="store_true", help="also write gpurun_out/kernel_times.txt (per-kernel CUPTI durations)")
     args = ap.parse_args()
+    # more hardware work queues than the default 8: the staging copies of the next batch must never share a queue with (and so
+    # wait behind) the CUDA graph of the running update.  Must be set before CUDA is initialised.
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     if args.impl == "reference":
         if args.device == "cpu":
             os.environ["CUDA_VISIBLE_DEVICES"] = ""                   # worker.py:283 takes cuda whenever it is visible

@@ -138,7 +138,10 @@ class BatchStager:
     def __init__(self, core: "DeviceLearner", slots: int = 2):
         d, B, T, A, R = core.device, core.B, core.T, core.A, core.rows_cap
         self.core = core
-        self.stream = torch.cuda.Stream(device=d)
+        # high priority: its copies are dispatched as soon as their slot is free instead of queueing behind the graph /
+        # kernels of the update that is running (measured: with a default-priority copy stream the 154 MB copy sometimes
+        # serialises behind the update's CUDA graph, 4.5-5.2 ms per step instead of 3.1)
+        self.stream = torch.cuda.Stream(device=d, priority=-1)
         self.slots = []
         for _ in range(slots):
             buf = dict(obs=torch.zeros(B, T, core.C, 84, 84, dtype=torch.uint8, device=d),

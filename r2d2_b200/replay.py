@@ -59,7 +59,7 @@ class DeviceReplay:
         self._pending = []                      # committed blocks whose priorities have not entered the tree yet (commit(defer=True))
         self._gather_event = None               # recorded after the most recent gather: an ingest copy may not overtake it
         self.ingested_bytes = 0
-        self.ingest_stream = torch.cuda.Stream(device=self.device)
+        self.ingest_stream = torch.cuda.Stream(device=self.device, priority=-1)   # copies must not queue behind a running update
         # reference bookkeeping (worker.py:50-68)
         self.block_ptr = 0
         self.size = 0
