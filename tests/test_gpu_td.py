@@ -11,9 +11,21 @@ pytestmark = pytest.mark.gpu
 
 
 def _run_gpu(q, qn_on, qn_tg, action, R, G, isw, learn):
-    from r2d2_b200 import ops
+    """r2d2_td_loss (K2) through the C ABI on device copies of the inputs."""
+    from r2d2_b200 import _lib
     c = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
-    td, prio, loss_sum, rows, dq = ops.td_loss(c(q), c(qn_on), c(qn_tg), c(action), c(R), c(G), c(isw), c(learn))
+    q, qn_on, qn_tg, action, R, G, isw, learn = (c(x) for x in (q, qn_on, qn_tg, action, R, G, isw, learn))
+    rows_n, A = q.shape
+    B = learn.numel()
+    assert action.dtype == torch.uint8 and learn.dtype == torch.uint8
+    td = torch.empty(rows_n, dtype=torch.float32, device="cuda")
+    prio = torch.empty(B, dtype=torch.float32, device="cuda")
+    loss_sum = torch.empty(1, dtype=torch.float32, device="cuda")
+    rows = torch.empty(1, dtype=torch.int32, device="cuda")
+    dq = torch.empty(rows_n, A, dtype=torch.float32, device="cuda")
+    p = _lib.ptr
+    _lib.check(_lib.lib().r2d2_td_loss(p(q), p(qn_on), p(qn_tg), p(action.reshape(-1)), p(R), p(G), p(isw), p(learn), B, A, p(td), p(prio),
+                                       p(loss_sum), p(rows), p(dq), _lib.stream_ptr()))
     torch.cuda.synchronize()
     return (td.cpu().numpy(), prio.cpu().numpy(), float(loss_sum.item()), int(rows.item()), dq.cpu().numpy())
 
