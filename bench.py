@@ -374,9 +374,8 @@ def run_ours(args):
     learner._start_time = time.time()
     if world > 1:
         r2dist.broadcast_parameters(learner.core)
-        learner.core.grad_hook = r2dist.make_overlapped_grad_hook(learner.core)   # dense-layer all-reduce overlaps the conv backward
         learner.is_weight_sync = r2dist.GlobalISWeights(dev, 0.6)                 # importance weights of one global sampler
-        learner.core.pre_td_hook = learner.is_weight_sync.wait                   # joined right before the TD kernel
+        learner.core.grad_hook = r2dist.make_overlapped_grad_hook(learner.core, is_sync=learner.is_weight_sync)   # dense all-reduce overlaps the conv backward
 
     # HBM replay shard of this rank: NUM_BLOCKS blocks, tree over 2^20 slots
     replay = DeviceReplay(NUM_BLOCKS * BLOCK_LEN, BLOCK_LEN, BURN, LEARN, FWD, A, (C, 84, 84), 512, 0.9, 0.6, B, device=dev,

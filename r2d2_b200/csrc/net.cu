@@ -1311,7 +1311,14 @@ int r2d2_net_backward(r2d2_net* n, const float* params, const float* dq, float* 
         R2D2_CUDA_CHECK(fin_flush(n, grads, d_off, s));            // every dense-layer gradient (heads, LSTM, FC) in one reduction launch
         // every gradient from feature.7.weight to the end of the flat layout (FC, LSTM, heads: 98 % of the bytes) is final:
         // a data-parallel caller can start reducing that range while the conv layers' backward still runs
-        if (n->dense_grads_event) R2D2_CUDA_CHECK(cudaEventRecord((cudaEvent_t)n->dense_grads_event, s));
+        if (n->dense_grads_event) {
+            // inside a stream capture a plain record would only mark a capture-internal point; the caller waits on this event
+            // from a stream OUTSIDE the graph, so it must become an external event-record node
+            cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+            R2D2_CUDA_CHECK(cudaStreamIsCapturing(s, &cap));
+            R2D2_CUDA_CHECK(cudaEventRecordWithFlags((cudaEvent_t)n->dense_grads_event, s,
+                                                     cap == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault));
+        }
         SrcMatK a2{n->dlat.hi, n->dlat.lo, NF, LATENT, LATENT};
         SrcMatMN b2{pk.Wfcp.hi, pk.Wfcp.lo, FLAT3, LATENT, FLAT3};
         Epi2MaskedToGrid3 e{n->dpre3, ro(ac.act3), NF};

@@ -11,9 +11,10 @@ all-reduce (issued in two pieces by the overlapped hook) that also carries the r
 
 which is exactly the gradient of the reference's ``(is_w * (q - target)**2).mean()`` (worker.py:354) taken over
 the GLOBAL batch, also when ranks hold different numbers of learning rows (ragged sequences).
-Priority updates stay shard-local.  Importance weights: GlobalISWeights rescales each rank's weights by one scalar so
-that they equal the weights of a single prioritized sampler over all shards (one MIN all-reduce of a float64, on a
-side stream); what remains of the sharding is stratification (every rank contributes exactly B sequences).
+Priority updates stay shard-local.  Importance weights: GlobalISWeights computes one scalar per rank that turns its
+weights into those of a single prioritized sampler over all shards (one MIN all-reduce of a float64, on a side
+stream); the loss is linear in the weights, so the gradient hooks apply it to this rank's gradient right before the
+reduction.  What remains of the sharding is stratification (every rank contributes exactly B sequences).
 """
 from __future__ import annotations
 
@@ -52,14 +53,18 @@ def _rows_slot(learner):
     return off[-1] - 1
 
 
-def make_grad_hook(group=None):
+def make_grad_hook(group=None, is_sync=None):
     """grad_hook for DeviceLearner: global-mean gradient across ranks (see module docstring) with ONE all-reduce: the
-    local row count rides in a padding slot of the flat gradient buffer (zeroed again before the optimizer sees it)."""
+    local row count rides in a padding slot of the flat gradient buffer (zeroed again before the optimizer sees it).
+    is_sync: optional GlobalISWeights whose per-rank factor scales this rank's gradient before the reduction."""
     state = {}
 
     def hook(learner):
         flat = learner.grads.flat
         slot = _rows_slot(learner)
+        if is_sync is not None:
+            is_sync.wait()
+            flat.mul_(is_sync.factor)
         if slot is None:                                      # no layout information: separate scalar reduction
             rows_g = state.get("rows")
             if rows_g is None or rows_g.device != flat.device:
@@ -74,10 +79,11 @@ def make_grad_hook(group=None):
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
         torch.reciprocal(flat[slot:slot + 1], out=learner.grad_scale)
         flat[slot:slot + 1].zero_()
+    hook.split_graph = True        # the learner may replay its gradient and optimizer phases as CUDA graphs around this (eager) hook
     return hook
 
 
-def make_overlapped_grad_hook(learner, group=None):
+def make_overlapped_grad_hook(learner, group=None, is_sync=None):
     """Same reduction as make_grad_hook, but the FC/LSTM/head range of the flat gradient (98 % of the bytes) is all-reduced
     from a side stream as soon as r2d2_net_backward has finished it (r2d2_net_set_dense_grads_event), i.e. WHILE the conv
     layers' data/weight gradients are still being computed; only the 0.3 MB conv range is reduced after the backward pass.
@@ -99,17 +105,25 @@ def make_overlapped_grad_hook(learner, group=None):
         assert lrn is learner and keep
         flat = lrn.grads.flat
         with torch.cuda.stream(side):
-            side.wait_event(ev)                               # recorded inside the backward call that just returned; the row
-            flat[slot:slot + 1].copy_(lrn.rows)               # count (K2, before the backward pass) is final by then as well
+            side.wait_event(ev)                               # recorded inside the backward call / graph that was just launched
+            if is_sync is not None:
+                side.wait_event(is_sync.ev)
+                flat[dense_off:].mul_(is_sync.factor)         # this rank's importance-weight correction (a scalar: the loss is linear in it)
+            flat[slot:slot + 1].copy_(lrn.rows)               # the row count (K2, before the backward pass) is final by then as well
             w_dense = dist.all_reduce(flat[dense_off:], op=dist.ReduceOp.SUM, group=group, async_op=True)
+        if is_sync is not None:
+            is_sync.wait()
+            flat[:dense_off].mul_(is_sync.factor)
         w_conv = dist.all_reduce(flat[:dense_off], op=dist.ReduceOp.SUM, group=group, async_op=True)
         w_dense.wait()
         w_conv.wait()
         torch.reciprocal(flat[slot:slot + 1], out=lrn.grad_scale)
         flat[slot:slot + 1].zero_()                           # padding must be zero again: the global norm runs over the flat buffer
-    # The hook is stream-ordered only, but capturing NCCL work into the update's CUDA graph bought nothing at 2 GPUs (2.67 ms
-    # per step either way) and left the process group hanging at shutdown: data-parallel updates stay eager.
+    # Capturing the NCCL calls themselves into the update's CUDA graph bought nothing at 2 GPUs and left the process group
+    # hanging at shutdown.  Instead the learner replays TWO graphs (gradients; optimizer) around this eager hook; the event the
+    # side stream waits on is recorded by an external event-record node inside the gradient graph (cudaEventRecordExternal).
     hook.capturable = False
+    hook.split_graph = True
     return hook
 
 
@@ -126,23 +140,28 @@ def global_is_factor(local_min_over_root: torch.Tensor, beta: float, group=None)
 
 
 class GlobalISWeights:
-    """Applies global_is_factor to a sampled batch on a side stream: the scalar reduction and the in-place scaling of
-    batch['is_weights'] overlap the forward unroll; `wait` (installed as DeviceLearner.pre_td_hook) joins before K2."""
+    """Computes this rank's global_is_factor for a sampled batch on a side stream (tiny kernels + one scalar MIN all-reduce,
+    overlapping the forward unroll).  The loss is linear in the importance weights and the factor is one scalar per rank, so
+    instead of rescaling batch['is_weights'] before K2 the gradient hooks multiply this rank's gradient of loss_sum by it
+    right before the reduction -- same global-mean gradient, nothing on the learner's critical path.  (TD errors and
+    priorities do not depend on the weights; the reported loss stays in local-weight units.)"""
 
     def __init__(self, device, beta: float, group=None):
         self.beta, self.group = beta, group
+        self.device = device
         self.side = torch.cuda.Stream(device=device)
         self.ev = torch.cuda.Event()
-        self.device = device
+        self.factor = torch.ones(1, dtype=torch.float32, device=device)
+        self.ev.record(torch.cuda.current_stream(device))
 
     def correct(self, replay, batch, idx) -> None:
         main = torch.cuda.current_stream(self.device)
         with torch.cuda.stream(self.side):
-            self.side.wait_stream(main)                       # after the sample / gather kernels
+            self.side.wait_stream(main)                       # after the sample kernels of this update (and the previous hook's reads of `factor`)
             nodes = replay.tree.nodes_device()
             leaf_base = (1 << (replay.tree.num_layers - 1)) - 1
             m = (nodes[leaf_base + idx].min() / nodes[0]).reshape(1)
-            batch["is_weights"].mul_(global_is_factor(m, self.beta, self.group).to(torch.float32))
+            self.factor.copy_(global_is_factor(m, self.beta, self.group))
             self.ev.record(self.side)
 
     def wait(self, learner=None) -> None:

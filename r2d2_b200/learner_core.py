@@ -381,41 +381,64 @@ class DeviceLearner:
             self.grad_hook(self)
         self.apply_gradients(_count)
 
+    def _graph_for(self, key, fn):
+        """CUDA graph of `fn` for this key, captured the second time the key is seen; None while still eager."""
+        g = self._graphs.get(key)
+        if g is not None:
+            return g
+        if len(self._graph_seen) > 256:
+            self._graph_seen.clear()
+        seen = self._graph_seen.get(key, 0) + 1
+        self._graph_seen[key] = seen
+        if seen < 2:
+            return None                                       # first sight: eager (also sets per-function attributes, not capturable)
+        if len(self._graphs) >= 16:
+            self._graphs.clear()
+        g = torch.cuda.CUDAGraph()
+        try:
+            with torch.cuda.graph(g):
+                fn()
+        except Exception as e:                                # stay eager from now on
+            import warnings
+            warnings.warn(f"CUDA-graph capture of the learner update failed ({e}); continuing with eager launches")
+            self.use_graph = False
+            torch.cuda.synchronize(self.device)
+            return None
+        self._graphs[key] = g
+        return g
+
     @_lib.on_device
     def update(self, b: dict) -> None:
         """One learner update on prepared device buffers.  Nothing in the launch sequence depends on host values that change
         between updates (update count and row count live on the device), so for a recurring set of buffers the ~45 launches
-        are captured once in a CUDA graph and replayed."""
-        if not self.use_graph or self.pre_td_hook is not None or \
-                (self.grad_hook is not None and not getattr(self.grad_hook, "capturable", False)):
+        are captured once in a CUDA graph and replayed.  With a data-parallel grad_hook that declares `split_graph` the
+        update is two graphs -- gradients, optimizer -- with the (eager) collective between them."""
+        hook = self.grad_hook
+        split = hook is not None and getattr(hook, "split_graph", False)
+        if not self.use_graph or self.pre_td_hook is not None or (hook is not None and not split):
             return self._update_eager(b)
         key = (_lib.lib().r2d2_config_epoch(),) + tuple(None if v is None else (v.data_ptr() if isinstance(v, torch.Tensor) else v)
                                                       for v in (b.get(k) for k in _BATCH_KEYS))
-        g = self._graphs.get(key)
-        if g is None:
-            if len(self._graph_seen) > 256:
-                self._graph_seen.clear()
-            seen = self._graph_seen.get(key, 0) + 1
-            self._graph_seen[key] = seen
-            if seen < 2:
-                return self._update_eager(b)                 # also the run that sets per-function attributes (not capturable)
-            if len(self._graphs) >= 8:
-                self._graphs.clear()
-            g = torch.cuda.CUDAGraph()
-            try:
-                with torch.cuda.graph(g):
-                    self._update_eager(b, _count=False)
-            except Exception as e:                           # e.g. a collective that cannot be captured: stay eager from now on
-                import warnings
-                warnings.warn(f"CUDA-graph capture of the learner update failed ({e}); continuing with eager launches")
-                self.use_graph = False
-                torch.cuda.synchronize(self.device)
+        self._live = b
+        if not split:
+            g = self._graph_for(key, lambda: self._update_eager(b, _count=False))
+            if g is None:
                 return self._update_eager(b)
-            self._graphs[key] = (g, b)                       # the graph reads these buffers: keep them alive with it
-            g = self._graphs[key]
-        self._live = g[1]
-        self._num_updates += 1
-        g[0].replay()
+            self._num_updates += 1
+            g.replay()
+            return
+        ga = self._graph_for(key + ("grad",), lambda: self.compute_gradients(b))
+        if ga is None:
+            self.compute_gradients(b)
+        else:
+            ga.replay()
+        hook(self)
+        gb = self._graph_for(key[:1] + ("apply",), lambda: self.apply_gradients(_count=False))
+        if gb is None:
+            self.apply_gradients()
+        else:
+            self._num_updates += 1
+            gb.replay()
 
     # ------------------------------------------------------------------ debug
     def debug_split(self, which: int, name: str, numel: int) -> torch.Tensor:

@@ -313,9 +313,7 @@ class Learner:
     def update_from_replay(self):
         batch, idx, old_ptr = self.replay.sample(fuse_into=self.core)     # frames go straight into conv1's staging layout
         if self.is_weight_sync is not None:                               # data parallel: weights of one sampler over all shards
-            self.is_weight_sync.correct(self.replay, batch, idx)
-            if self.core.pre_td_hook is None:                             # no hook installed (graph replay): join here
-                self.is_weight_sync.wait()
+            self.is_weight_sync.correct(self.replay, batch, idx)          # side stream; consumed by the gradient hook
         self.core.update(batch)
         self.replay.update_priorities(idx, self.core.prio, old_ptr)
         self.env_steps = self.replay.env_steps
