@@ -266,6 +266,33 @@ def kernel_times(fn, steps=3):
     return "\n".join(lines)
 
 
+def kernel_timeline(fn, steps=3, profile_here=True):
+    """Chronological list of the device activities of `steps` warm learner steps: start offset, duration, stream, name
+    (CUPTI via torch.profiler).  Used to see which part of a data-parallel step is exposed; every rank runs the steps,
+    rank 0 profiles."""
+    import re
+    from torch.profiler import ProfilerActivity, profile
+    torch.cuda.synchronize()
+    if not profile_here:
+        for i in range(steps):
+            fn(i)
+        torch.cuda.synchronize()
+        return ""
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for i in range(steps):
+            fn(i)
+        torch.cuda.synchronize()
+    evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    evs.sort(key=lambda e: e.time_range.start)
+    t0 = evs[0].time_range.start
+    lines = []
+    for e in evs:
+        name = re.sub(r"\(.*", "", re.sub(r"^void ", "", e.name))[:110]
+        dur = e.device_time if hasattr(e, "device_time") else e.cuda_time
+        lines.append(f"{e.time_range.start - t0:10.1f} us  +{dur:8.1f} us  {name}")
+    return "\n".join(lines)
+
+
 def run_ingest_mode(args, learner, replay, C, ms_step_plain):
     """BASELINE config #3: the learner + HBM replay + sum tree (2^20 slots) while `--actors` producers feed blocks through the
     pinned staging ring.  Runs the product's own Learner.run loop (prefetch thread packs blocks into pinned memory, the learner
@@ -374,8 +401,26 @@ def run_ours(args):
     learner._start_time = time.time()
     if world > 1:
         r2dist.broadcast_parameters(learner.core)
-        learner.is_weight_sync = r2dist.GlobalISWeights(dev, 0.6)                 # importance weights of one global sampler
-        learner.core.grad_hook = r2dist.make_overlapped_grad_hook(learner.core, is_sync=learner.is_weight_sync)   # dense all-reduce overlaps the conv backward
+        exchange = None
+        if os.environ.get("R2D2_DP_NCCL") != "1":                                 # our all-reduce kernels over NVLink peer memory (csrc/dp.cu)
+            try:
+                exchange = r2dist.PeerExchange(learner.core)
+            except Exception as e:                                                # noqa: BLE001  (no symmetric memory on this box)
+                print(f"[bench] rank {rank}: peer-memory exchange unavailable ({e!r}); falling back to NCCL", file=sys.stderr)
+            ok = torch.tensor([1 if exchange is not None else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)                             # all ranks take the same path
+            if int(ok.item()) == 0:
+                exchange = None
+        if exchange is None:                                                      # comparison arm: the same exchange on NCCL calls
+            learner.is_weight_sync = r2dist.GlobalISWeights(dev, 0.6)             # importance weights of one global sampler
+            learner.core.grad_hook = r2dist.make_overlapped_grad_hook(learner.core, is_sync=learner.is_weight_sync)
+        else:
+            learner.is_weight_sync = r2dist.PeerISWeights(exchange, 0.6)
+            learner.core.pre_td_hook = learner.is_weight_sync.apply
+            learner.core.grad_hook = r2dist.make_peer_grad_hook(learner.core, exchange)   # dense range overlaps the conv backward
+        dp_exchange = "nccl" if exchange is None else ("peer-memory kernels, multimem" if exchange.multicast else "peer-memory kernels, p2p")
+    else:
+        dp_exchange = None
 
     # HBM replay shard of this rank: NUM_BLOCKS blocks, tree over 2^20 slots
     replay = DeviceReplay(NUM_BLOCKS * BLOCK_LEN, BLOCK_LEN, BURN, LEARN, FWD, A, (C, 84, 84), 512, 0.9, 0.6, B, device=dev,
@@ -449,6 +494,12 @@ def run_ours(args):
         with open(os.path.join(ROOT, "gpurun_out", "kernel_times.txt"), "w") as f:
             f.write(text + "\n")
         print(text, file=sys.stderr)
+    if args.timeline:
+        text = kernel_timeline(step_resident, profile_here=rank < 2)
+        if rank < 2:
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            with open(os.path.join(ROOT, "gpurun_out", f"timeline_n{world}" + ("" if rank == 0 else f"_rank{rank}") + ".txt"), "w") as f:
+                f.write(text + "\n")
     ours, other = count_kernels(lambda: step_resident(0))      # every rank runs it: the step contains the all-reduce
     if rank == 0:
         peaks = measured_peaks()
@@ -462,7 +513,7 @@ def run_ours(args):
                 "data": "synthetic",
                 "config": {"workload": f"configs[1]: 1xB200 learner per rank, batch {B}/GPU, b/l/f {BURN}/{LEARN}/{FWD} (T={T}), "
                                        f"{C}x84x84 u8 frames, A={A}, HBM replay of {NUM_BLOCKS} blocks, sum tree 2^20",
-                           "channels": C, "global_batch": world * B, "parallelism": f"dp{world}", "precision": args.precision,
+                           "channels": C, "global_batch": world * B, "parallelism": f"dp{world}", "exchange": dp_exchange, "precision": args.precision,
                            "host": f"staging copies on high-priority streams; CUDA_DEVICE_MAX_CONNECTIONS={os.environ.get('CUDA_DEVICE_MAX_CONNECTIONS')} (binding the process to the GPU's NUMA node was measured and made the copies slower on this pool: not done)",
                            "l2": f"inputs larger than L2: batches are gathered from a {NUM_BLOCKS * replay.blob_bytes / 1e9:.1f} GB HBM "
                                  f"block store; ~1 GB of activations streamed per step"},
@@ -517,6 +568,7 @@ def main():
                     help="BASELINE config #3 (N = 1 only): also run the learner with this many block producers feeding the HBM replay "
                          "through the pinned staging ring and report throughput with ingest on (adds an `ingest` object to the line)")
     ap.add_argument("--ingest-blocks-per-s", type=float, default=200.0, help="total block rate the producers offer (400-step blocks)")
+    ap.add_argument("--timeline", action="store_true", help="also write gpurun_out/timeline_n<N>.txt (chronological device activities of 3 steps; ranks 0 and 1)")
     ap.add_argument("--kernel-times", action="store_true", help="also write gpurun_out/kernel_times.txt (per-kernel CUPTI durations)")
     args = ap.parse_args()
     # more hardware work queues than the default 8: the staging copies of the next batch must never share a queue with (and so

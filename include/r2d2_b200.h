@@ -234,6 +234,40 @@ int r2d2_clip_adam_dev(float* params, const float* grads, float* exp_avg, float*
                        const float* grad_scale, const int32_t* rows_dev, double* partial_ws, float max_norm, float lr, float beta1,
                        float beta2, float eps, const int64_t* step_dev, float* norm_out, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Data-parallel exchange step over NVLink peer memory (the reference has ONE learner,
+ * worker.py:363-365 is a local backward + optimizer step, so these have no upstream counterpart:
+ * they sit between r2d2_net_backward and r2d2_clip_adam_dev when there is one learner per GPU).
+ * Every rank maps every rank's gradient buffer and a small control block (symmetric memory:
+ * grad_ptrs[i] / ctl_ptrs[i] are THIS process's addresses of rank i's copies; mc_grad_ptr is the
+ * NVSwitch multicast address of the gradient buffers or 0).  Control blocks are
+ * r2d2_dp_ctl_bytes() bytes, zeroed on every rank before the first call.
+ *  r2d2_dp_allreduce   in-place SUM over ranks of grads[off, off+len) (floats, multiples of 4).
+ *      Rank r reduces slice r (multimem.ld_reduce in the switch, or P2P loads) and writes it to
+ *      all ranks.  rows_dev / rows_slot / grad_scale_dev (all or none): the local int32 row count
+ *      is written to grads[rows_slot] (a padding element inside the range) before the reduction;
+ *      afterwards grad_scale = 1 / (global rows) and the slot is zero again.  channel 0/1: two
+ *      reductions may be in flight on different streams.  ctas x threads: launch shape (threads a
+ *      multiple of 32, <= 512); no shared memory, so the CTAs fit next to resident GEMM CTAs.
+ *  r2d2_dp_is_post / r2d2_dp_is_apply   importance weights of one global prioritized sampler
+ *      (priority_tree.py:39-41 over all shards).  post, right after sampling: min over the sampled
+ *      leaves / root from the tree's node array -> every peer.  apply, before K2 of the same update:
+ *      is_weights[0, rows) *= ((min_local/root_local) / min over ranks)^-beta; factor_out optional.
+ *      Exactly one post and one apply per update; they may run on different streams (apply waits
+ *      for every rank's flag, this rank's included).
+ * All calls are stream-ordered and graph-replayable; a rank that waits ~2 s for a peer traps
+ * (r2d2_dp_error then reports which barrier).
+ * ---------------------------------------------------------------------------------------- */
+size_t r2d2_dp_ctl_bytes(void);
+int r2d2_dp_create(int rank, int world, const unsigned long long* grad_ptrs, unsigned long long mc_grad_ptr,
+                   const unsigned long long* ctl_ptrs, void** handle);
+void r2d2_dp_destroy(void* handle);
+int r2d2_dp_allreduce(void* handle, long long off, long long len, int channel, const int32_t* rows_dev, long long rows_slot,
+                      float* grad_scale_dev, int ctas, int threads, int use_multicast, void* stream);
+int r2d2_dp_is_post(void* handle, const double* nodes, long long leaf_base, const long long* idx, int n, void* stream);
+int r2d2_dp_is_apply(void* handle, double beta, float* is_weights, int rows, float* factor_out, void* stream);
+int r2d2_dp_error(void* handle, unsigned int* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,6 +19,7 @@ reduction.  What remains of the sharding is stratification (every rank contribut
 from __future__ import annotations
 
 import os
+from typing import Optional
 
 import torch
 import torch.distributed as dist
@@ -122,6 +123,157 @@ def make_overlapped_grad_hook(learner, group=None, is_sync=None):
     # Capturing the NCCL calls themselves into the update's CUDA graph bought nothing at 2 GPUs and left the process group
     # hanging at shutdown.  Instead the learner replays TWO graphs (gradients; optimizer) around this eager hook; the event the
     # side stream waits on is recorded by an external event-record node inside the gradient graph (cudaEventRecordExternal).
+    hook.capturable = False
+    hook.split_graph = True
+    return hook
+
+
+class PeerExchange:
+    """The data-parallel exchange step on our own kernels over NVLink peer memory (csrc/dp.cu) instead of NCCL calls.
+
+    torch's symmetric memory does the plumbing only (allocation, handle exchange between the processes, the NVSwitch
+    multicast mapping); the gradient all-reduce (`allreduce`, multimem.ld_reduce / multimem.st with flag barriers in peer
+    memory) and the global importance-weight factor (`is_factor`) are r2d2_dp_* launches on the caller's streams.  The
+    learner's flat gradient buffer is moved into symmetric memory (DeviceLearner.use_grad_buffer)."""
+
+    def __init__(self, learner, group=None, use_multicast: Optional[bool] = None):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        self.learner = learner
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        dev = learner.device
+        lib = _lib.lib()
+        with torch.cuda.device(dev):
+            self.grads = symm.empty(learner.grads.flat.numel(), dtype=torch.float32, device=dev)
+            self.ctl = symm.empty(lib.r2d2_dp_ctl_bytes() // 4, dtype=torch.int32, device=dev)
+            self.grads.zero_()
+            self.ctl.zero_()
+            self._hg = symm.rendezvous(self.grads, self.group)
+            self._hc = symm.rendezvous(self.ctl, self.group)
+            learner.use_grad_buffer(self.grads)
+            torch.cuda.synchronize(dev)
+            dist.barrier(self.group)                                # every control block is zero before any rank signals
+            mc = int(self._hg.multicast_ptr or 0)
+            if use_multicast is None:
+                use_multicast = os.environ.get("R2D2_DP_NO_MULTICAST") != "1"
+            self.multicast = bool(use_multicast and mc)
+            gp = (C.c_ulonglong * self.world)(*[int(x) for x in self._hg.buffer_ptrs])
+            cp = (C.c_ulonglong * self.world)(*[int(x) for x in self._hc.buffer_ptrs])
+            h = C.c_void_p()
+            _lib.check(lib.r2d2_dp_create(self.rank, self.world, gp, mc, cp, C.byref(h)))
+        self._h = h
+        self.device = dev
+
+    def allreduce(self, off: int, length: int, channel: int, ctas: int, threads: int, with_rows: bool = False) -> None:
+        """In-place SUM over ranks of grads[off, off+length) on the current stream; with_rows also turns the row count in
+        the padding slot into learner.grad_scale = 1 / (global rows)."""
+        from . import _lib
+        lrn = self.learner
+        slot = _rows_slot(lrn)
+        _lib.check(_lib.lib().r2d2_dp_allreduce(self._h, off, length, channel, _lib.ptr(lrn.rows) if with_rows else None,
+                                                slot if with_rows else 0, _lib.ptr(lrn.grad_scale) if with_rows else None,
+                                                ctas, threads, 1 if self.multicast else 0,
+                                                torch.cuda.current_stream(self.device).cuda_stream))
+
+    def is_post(self, replay, idx) -> None:
+        """Right after sampling: this rank's min(p_i)/root of the sampled leaves goes to every peer (nobody waits)."""
+        from . import _lib
+        tree = replay.tree
+        leaf_base = (1 << (tree.num_layers - 1)) - 1
+        _lib.check(_lib.lib().r2d2_dp_is_post(self._h, tree.nodes_device().data_ptr(), leaf_base, _lib.ptr(idx), idx.numel(),
+                                              torch.cuda.current_stream(self.device).cuda_stream))
+
+    def is_apply(self, is_weights: torch.Tensor, beta: float) -> None:
+        """Before K2 of the same update: is_weights *= global_is_factor of this rank, in place on the current stream."""
+        from . import _lib
+        _lib.check(_lib.lib().r2d2_dp_is_apply(self._h, float(beta), _lib.ptr(is_weights), is_weights.numel(), None,
+                                               torch.cuda.current_stream(self.device).cuda_stream))
+
+    def error(self) -> int:
+        import ctypes as C
+        from . import _lib
+        out = C.c_uint(0)
+        _lib.check(_lib.lib().r2d2_dp_error(self._h, C.byref(out)))
+        return out.value
+
+    def close(self) -> None:
+        from . import _lib
+        if self._h is not None:
+            _lib.lib().r2d2_dp_destroy(self._h)
+            self._h = None
+
+
+class PeerISWeights:
+    """Learner.is_weight_sync for PeerExchange.  `correct` (after sampling) posts this rank's scalar to the peers; the learner's
+    pre_td_hook (`apply`, a graph-capturable launch right before K2) turns the ranks' scalars into this rank's factor and scales
+    batch['is_weights'] -- a millisecond after the post, so no rank waits for another one."""
+
+    def __init__(self, exchange: PeerExchange, beta: float):
+        self.exchange, self.beta = exchange, beta
+        self._weights = None
+        self.apply.__func__.capturable = True
+        dev = exchange.device
+        self.side = torch.cuda.Stream(device=dev, priority=-1)   # the post's system-scope release took 45 us behind the 300 MB gather
+        self._sampled, self._posted = torch.cuda.Event(), torch.cuda.Event()
+        self._idx = None
+
+    def correct(self, replay, batch, idx) -> None:
+        main = torch.cuda.current_stream(self.exchange.device)
+        self._sampled.record(main)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(self._sampled)
+            self.exchange.is_post(replay, idx)
+            self._posted.record(self.side)
+        self._idx = idx                                           # keeps the index tensor alive until `join`
+        self._weights = batch["is_weights"]
+
+    def join(self) -> None:
+        """Before the tree / index buffers the post reads are modified again (priority update): long finished by then."""
+        torch.cuda.current_stream(self.exchange.device).wait_event(self._posted)
+        self._idx = None
+
+    def apply(self, learner) -> None:
+        # only for the batch `correct` posted for (every post needs exactly one apply and vice versa): batches that did not
+        # come from this rank's replay shard (reference-format tuples from the host) carry their sampler's own weights
+        b = learner._live
+        if self._weights is None or b is None or b.get("is_weights") is not self._weights:
+            return
+        self.exchange.is_apply(self._weights, self.beta)
+
+
+def make_peer_grad_hook(learner, exchange: PeerExchange, dense_ctas: Optional[int] = None, conv_ctas: Optional[int] = None):
+    """grad_hook on PeerExchange: the FC/LSTM/head range (98 % of the bytes, with the row count) is reduced from a side stream
+    as soon as the backward pass has finished it -- a few small CTAs running next to the conv layers' backward kernels --
+    and the 0.3 MB conv range on the learner's stream after the backward pass.  Two launches, no NCCL, no torch ops."""
+    from . import _lib
+    from .learner_core import PARAM_NAMES
+    dev = learner.device
+    side = torch.cuda.Stream(device=dev, priority=-1)
+    ev, done = torch.cuda.Event(), torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(dev))                 # materialise the cudaEvent_t
+    _lib.check(_lib.lib().r2d2_net_set_dense_grads_event(learner._h, ev.cuda_event))
+    n = learner.grads.flat.numel()
+    dense_off = learner.grads.offsets[PARAM_NAMES.index("feature.7.weight")]
+    slot = _rows_slot(learner)
+    assert slot is not None and slot >= dense_off and dense_off % 4 == 0 and n % 4 == 0
+    # dense range: spread thin (one warp per SM) so that no SM of the concurrent backward kernels is slowed much; conv range:
+    # nothing else is running, latency matters
+    dense_ctas = dense_ctas or int(os.environ.get("R2D2_DP_DENSE_CTAS", "148"))
+    dense_threads = int(os.environ.get("R2D2_DP_DENSE_THREADS", "32"))
+    conv_ctas = conv_ctas or int(os.environ.get("R2D2_DP_CONV_CTAS", "8"))
+    keep = {"event": ev, "stream": side}                      # owned by the hook: the library only borrows the event
+
+    def hook(lrn):
+        assert lrn is learner and keep
+        main = torch.cuda.current_stream(dev)
+        with torch.cuda.stream(side):
+            side.wait_event(ev)                               # recorded inside the backward call / graph that was just launched
+            exchange.allreduce(dense_off, n - dense_off, 0, dense_ctas, dense_threads, with_rows=True)
+            done.record(side)
+        exchange.allreduce(0, dense_off, 1, conv_ctas, 256)
+        main.wait_event(done)
     hook.capturable = False
     hook.split_graph = True
     return hook

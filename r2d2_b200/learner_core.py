@@ -47,10 +47,13 @@ def param_offsets(action_dim: int, in_channels: int = 1):
 class FlatParams:
     """One flat fp32 device buffer + per-tensor views named like the reference state_dict."""
 
-    def __init__(self, action_dim: int, in_channels: int, device):
+    def __init__(self, action_dim: int, in_channels: int, device, flat: Optional[torch.Tensor] = None):
         self.offsets = param_offsets(action_dim, in_channels)
         self.shapes = param_shapes(action_dim, in_channels)
-        self.flat = torch.zeros(self.offsets[-1], dtype=torch.float32, device=device)
+        if flat is None:
+            flat = torch.zeros(self.offsets[-1], dtype=torch.float32, device=device)
+        assert flat.dtype == torch.float32 and flat.numel() == self.offsets[-1] and flat.is_contiguous()
+        self.flat = flat
         self.views: Dict[str, torch.Tensor] = {}
         for i, name in enumerate(PARAM_NAMES):
             shape = self.shapes[name]
@@ -320,6 +323,14 @@ class DeviceLearner:
         return out
 
     @_lib.on_device
+    def use_grad_buffer(self, flat: torch.Tensor) -> None:
+        """Rebind the flat gradient buffer (same layout) to caller-provided device memory -- e.g. symmetric memory that the
+        other ranks of a data-parallel run have mapped (dist.PeerExchange).  Call before the first update."""
+        assert not self._graphs, "rebind the gradient buffer before any update has been captured"
+        assert flat.device == self.device
+        flat.zero_()
+        self.grads = FlatParams(self.A, self.C, self.device, flat=flat)
+
     def forward(self, which: int, b: dict, q_learn: Optional[torch.Tensor], q_shift: Optional[torch.Tensor]) -> None:
         flat = self.online.flat if which == 0 else self.target.flat
         p = _lib.ptr
@@ -415,7 +426,8 @@ class DeviceLearner:
         update is two graphs -- gradients, optimizer -- with the (eager) collective between them."""
         hook = self.grad_hook
         split = hook is not None and getattr(hook, "split_graph", False)
-        if not self.use_graph or self.pre_td_hook is not None or (hook is not None and not split):
+        pre = self.pre_td_hook                                   # plain stream-ordered launches may declare themselves capturable
+        if not self.use_graph or (pre is not None and not getattr(pre, "capturable", False)) or (hook is not None and not split):
             return self._update_eager(b)
         key = (_lib.lib().r2d2_config_epoch(),) + tuple(None if v is None else (v.data_ptr() if isinstance(v, torch.Tensor) else v)
                                                       for v in (b.get(k) for k in _BATCH_KEYS))

@@ -315,6 +315,8 @@ class Learner:
         if self.is_weight_sync is not None:                               # data parallel: weights of one sampler over all shards
             self.is_weight_sync.correct(self.replay, batch, idx)          # side stream; consumed by the gradient hook
         self.core.update(batch)
+        if self.is_weight_sync is not None and hasattr(self.is_weight_sync, "join"):
+            self.is_weight_sync.join()                                     # side-stream reads of the tree end before it changes
         self.replay.update_priorities(idx, self.core.prio, old_ptr)
         self.env_steps = self.replay.env_steps
         self._after_update()
