@@ -274,11 +274,15 @@ def kernel_timeline(fn, steps=3, profile_here=True):
     from torch.profiler import ProfilerActivity, profile
     torch.cuda.synchronize()
     if not profile_here:
+        if torch.distributed.is_initialized():
+            torch.distributed.barrier()                   # the profiling ranks need seconds to attach CUPTI
         for i in range(steps):
             fn(i)
         torch.cuda.synchronize()
         return ""
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        if torch.distributed.is_initialized():
+            torch.distributed.barrier()
         for i in range(steps):
             fn(i)
         torch.cuda.synchronize()
@@ -431,6 +435,8 @@ def run_ours(args):
         replay.add(blk, prio, None)
     learner.replay = replay
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()                                             # ranks finish their set-up seconds apart
 
     tuples = [reference_tuple(synthetic_batch(B, A, BURN, LEARN, FWD, channels=C, seed=100 * rank + i), pinned=True) for i in range(3)]
     in_bytes = sum(v.numel() * v.element_size() for v in tuples[0] if isinstance(v, torch.Tensor))

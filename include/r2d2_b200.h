@@ -255,7 +255,7 @@ int r2d2_clip_adam_dev(float* params, const float* grads, float* exp_avg, float*
  *      is_weights[0, rows) *= ((min_local/root_local) / min over ranks)^-beta; factor_out optional.
  *      Exactly one post and one apply per update; they may run on different streams (apply waits
  *      for every rank's flag, this rank's included).
- * All calls are stream-ordered and graph-replayable; a rank that waits ~2 s for a peer traps
+ * All calls are stream-ordered and graph-replayable; a rank that waits ~60 s for a peer traps
  * (r2d2_dp_error then reports which barrier).
  * ---------------------------------------------------------------------------------------- */
 size_t r2d2_dp_ctl_bytes(void);

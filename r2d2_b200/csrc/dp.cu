@@ -19,7 +19,7 @@
 // therefore spread thin -- one warp-sized CTA per SM, no shared memory, 8 loads in flight per thread.
 //
 // Barriers count epochs in device memory (nothing changes on the host between calls), so the launches can be replayed from a
-// CUDA graph.  A rank that waits more than ~2 s traps instead of hanging the GPU.
+// CUDA graph.  A rank that waits more than a minute for a peer traps instead of hanging the GPU.
 #include "common.cuh"
 
 namespace r2d2 {
@@ -78,11 +78,13 @@ __device__ __forceinline__ void multimem_st_f4(float* p, float4 v) {
     asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-// Spin until *flag has reached `epoch` (wrap-safe); a peer that never arrives is a lost rank: record it and trap.
+// Spin until *flag has reached `epoch` (wrap-safe); a peer that never arrives is a lost rank: record it and trap.  The bound
+// has to cover honest host-side skew between ranks (start-up, a profiler attaching, a checkpoint being written): ~60 s.
+constexpr long long kDpTimeoutClocks = 120000000000ll;
 __device__ __forceinline__ void dp_wait_flag(const unsigned int* flag, unsigned int epoch, DpLocal* L, unsigned int code) {
     const long long t0 = clock64();
     while ((int)(ld_acquire_sys(flag) - epoch) < 0) {
-        if (clock64() - t0 > 4000000000ll) {
+        if (clock64() - t0 > kDpTimeoutClocks) {
             L->error = code;
             __threadfence_system();
             __trap();

@@ -1,4 +1,4 @@
-"""Two-GPU checks of the data-parallel exchange step (skipped on single-GPU boxes; the host logic is covered on CPU by
+"""Checks of the data-parallel exchange step (the two-GPU one is skipped on single-GPU boxes; the host logic is covered on CPU by
 tests/test_dist_gloo.py)."""
 import os
 import subprocess
@@ -23,3 +23,13 @@ def test_overlapped_hook_matches_plain_hook_on_two_gpus():
     assert r.returncode == 0, tail
     # NCCL hooks (plain / overlapped / overlapped between two graphs) and our peer-memory kernels (multicast and P2P)
     assert r.stdout.count("overlapped == plain: True; peer kernels ok: True; IS factor ok: True; ranks agree: True") == 2, tail
+
+
+def test_peer_exchange_kernels_two_emulated_ranks_on_one_gpu():
+    """tools/check_dp_single_gpu.py: csrc/dp.cu's all-reduce (row-count slot, both channels, several epochs) and its
+    importance-weight exchange with two ranks emulated on one GPU (own buffers, control blocks and streams; P2P path), in a
+    child process because a rank that loses its peer traps."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "check_dp_single_gpu.py")], capture_output=True, text=True,
+                       timeout=300, cwd=ROOT)
+    tail = (r.stdout + r.stderr)[-3000:]
+    assert r.returncode == 0 and "two emulated ranks: OK" in r.stdout, tail
