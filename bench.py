@@ -480,6 +480,13 @@ def run_ours(args):
 
     sampler = ClockSampler(local)
     sampler.start()
+    ms_step_seq = None
+    nccl_dp = world > 1 and dp_exchange == "nccl"                     # the NCCL hooks keep per-batch state in Python: sequential there
+    if not args.no_sample_ahead and not nccl_dp:
+        ms_step_seq = timed(step_resident, args.steps, args.warmup)   # strictly sequential loop first (reported next to the headline)
+        learner.sample_ahead = True                                   # batch i+1 is sampled + gathered while update i runs
+        for w in range(6):                                            # untimed: the second set of batch buffers gets its CUDA graph
+            step_resident(w)                                          # (a key is captured the second time it is seen)
     ms_step = timed(step_resident, args.steps, args.warmup)
     ms_e2e = timed(step_e2e, args.steps, args.warmup)
     sampler.stop_flag = True
@@ -487,7 +494,7 @@ def run_ours(args):
     ms_unroll = None
     if world == 1:                                 # K1 + K1b only, on the launching stream, for the roofline
         core = learner.core
-        b0 = replay.batch
+        b0 = dict(replay.batch, obs=None)          # frames: whatever the last gather staged (obs=None: no u8 -> s2d conversion pass)
 
         def unroll_only(i):
             core.compute_forward(b0)
@@ -506,6 +513,7 @@ def run_ours(args):
             os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
             with open(os.path.join(ROOT, "gpurun_out", f"timeline_n{world}" + ("" if rank == 0 else f"_rank{rank}") + ".txt"), "w") as f:
                 f.write(text + "\n")
+    step_resident(0)                                           # (re-)primes the sample-ahead pipeline after the host-batch phase
     ours, other = count_kernels(lambda: step_resident(0))      # every rank runs it: the step contains the all-reduce
     if rank == 0:
         peaks = measured_peaks()
@@ -521,12 +529,18 @@ def run_ours(args):
                                        f"{C}x84x84 u8 frames, A={A}, HBM replay of {NUM_BLOCKS} blocks, sum tree 2^20",
                            "channels": C, "global_batch": world * B, "parallelism": f"dp{world}", "exchange": dp_exchange, "precision": args.precision,
                            "host": f"staging copies on high-priority streams; CUDA_DEVICE_MAX_CONNECTIONS={os.environ.get('CUDA_DEVICE_MAX_CONNECTIONS')} (binding the process to the GPU's NUMA node was measured and made the copies slower on this pool: not done)",
+                           "sampling": ("batch i+1 is sampled and gathered on a second stream while update i runs (lag 1; the reference's "
+                                        "buffer process keeps batches queued ahead of its learner, worker.py:124-139,309-316); the gather's "
+                                        "copy CTAs are steered onto the SMs the BPTT recurrence leaves idle")
+                                       if ms_step_seq is not None else "sequential: sample -> update -> priority update",
                            "l2": f"inputs larger than L2: batches are gathered from a {NUM_BLOCKS * replay.blob_bytes / 1e9:.1f} GB HBM "
                                  f"block store; ~1 GB of activations streamed per step"},
                 "clocks": sampler.summary(),
                 "e2e": {"value": e2e, "unit": "sequences/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": in_bytes,
                         "d2h_bytes_per_step": B * 4 + 8},
                 "gpu_launches": ours, "other_launches": other}
+        if ms_step_seq is not None:                # the strictly sequential loop (every sample sees the priorities of the update before it)
+            line["sequential_sampling"] = {"ms_per_step": ms_step_seq, "value": world * B / (ms_step_seq * 1e-3), "unit": "sequences/s"}
         if ms_unroll is not None:
             fl = flops_per_sequence(C) * B
             ach = fl / (ms_unroll * 1e-3) / 1e12
@@ -574,6 +588,8 @@ def main():
                     help="BASELINE config #3 (N = 1 only): also run the learner with this many block producers feeding the HBM replay "
                          "through the pinned staging ring and report throughput with ingest on (adds an `ingest` object to the line)")
     ap.add_argument("--ingest-blocks-per-s", type=float, default=200.0, help="total block rate the producers offer (400-step blocks)")
+    ap.add_argument("--no-sample-ahead", action="store_true",
+                    help="time the strictly sequential loop only (default: batch i+1 is sampled and gathered while update i runs)")
     ap.add_argument("--timeline", action="store_true", help="also write gpurun_out/timeline_n<N>.txt (chronological device activities of 3 steps; ranks 0 and 1)")
     ap.add_argument("--kernel-times", action="store_true", help="also write gpurun_out/kernel_times.txt (per-kernel CUPTI durations)")
     args = ap.parse_args()

@@ -107,6 +107,18 @@ int r2d2_net_rows_capacity(const r2d2_net* n);
 int r2d2_net_ku(const r2d2_net* n);
 /* Device pointer of the frame staging buffer conv1 reads: bf16 [B*T][21][21][16*C] (frames after space-to-depth by 4). */
 void* r2d2_net_s2d_buffer(r2d2_net* n);
+/* Two staging buffers so that the gather of batch i+1 can run while update i still reads batch i (the reference keeps its
+ * batches prefetched in a queue, worker.py:124-139,309-316): _at(idx) is the address to gather into (buffer 1 is allocated on
+ * first use, not during a stream capture), select makes idx the one the following forward / backward calls read. */
+void* r2d2_net_s2d_buffer_at(r2d2_net* n, int idx);
+int r2d2_net_select_s2d(r2d2_net* n, int idx);
+/* Optional cudaEvent_t recorded by r2d2_net_forward_pair right before its recurrence launch. */
+int r2d2_net_set_rec_event(r2d2_net* n, void* cuda_event);
+/* One-warp kernel on `stream` that returns once the backward recurrence of the update it is paired with is executing (or
+ * after ~20 ms): work enqueued behind it lands on the 84 SMs that kernel leaves idle (see r2d2_replay_set_copy_smem).
+ * Pairing: one gate per update; _reset (stream-ordered, before the first update of such a pipeline) re-bases the count. */
+int r2d2_net_shadow_gate(r2d2_net* n, void* stream);
+int r2d2_net_shadow_gate_reset(r2d2_net* n, void* stream);
 /* Re-lay out `params` for slot `which` (0 = online, 1 = target).  Call after every change of that
  * slot's parameters (optimizer step, target sync; worker.py:365,376-377). */
 int r2d2_net_pack(r2d2_net* n, int which, const float* params, void* stream);
@@ -189,8 +201,11 @@ int r2d2_replay_gather(r2d2_replay* r, const int64_t* idx, const float* isw, int
                        float* last_reward, float* hidden, uint8_t* action, float* n_step_reward, float* gamma, uint8_t* burn,
                        uint8_t* learn, uint8_t* fwd, float* is_weights_rows, int32_t* rows_out, void* stream);
 
+/* bytes of unused dynamic shared memory per copy CTA of the gathers (0 = default): with 32 KB the CTAs cannot share an SM with
+ * a ~200 KB GEMM / recurrence CTA, so a gather that runs next to an update only takes idle SMs. */
+int r2d2_replay_set_copy_smem(r2d2_replay* r, int bytes);
 /* The same gather writing the frames straight into the network's space-to-depth bf16 staging buffer
- * (s2d_out = r2d2_net_s2d_buffer(net)); r2d2_net_forward_pair is then called with obs == NULL. */
+ * (s2d_out = r2d2_net_s2d_buffer(net) or _at(net, idx)); r2d2_net_forward_pair is then called with obs == NULL. */
 int r2d2_replay_gather_s2d(r2d2_replay* r, const int64_t* idx, const float* isw, int B, int T, void* s2d_out, uint8_t* last_action,
                            float* last_reward, float* hidden, uint8_t* action, float* n_step_reward, float* gamma, uint8_t* burn,
                            uint8_t* learn, uint8_t* fwd, float* is_weights_rows, int32_t* rows_out, void* stream);

@@ -30,13 +30,14 @@ constexpr int DP_CHANNELS = 2;                     // independent flag sets: two
 struct DpShared {                                  // peer-visible control block (symmetric memory, zeroed by the host)
     unsigned int flag[2 * DP_CHANNELS][DP_MAX_RANKS];      // [2 * channel + (0 entry | 1 exit)][writer rank] = epoch
     unsigned int is_flag[DP_MAX_RANKS];
-    double is_min[2][DP_MAX_RANKS];                // [epoch parity][writer rank]
+    double is_min[4][DP_MAX_RANKS];                // [epoch & 3][writer rank]: a post may run up to two epochs ahead of the applies
 };
 
 struct DpLocal {                                   // this rank's own state (plain device memory)
     unsigned int epoch[DP_CHANNELS];
     unsigned int done[DP_CHANNELS];                // CTAs that have finished their part of the slice
-    unsigned int is_epoch;
+    unsigned int is_epoch;                         // applies done
+    unsigned int is_post_epoch;                    // posts done (a learner that samples ahead posts batch i+1 before it applies batch i)
     unsigned int error;
 };
 
@@ -170,7 +171,9 @@ __global__ void __launch_bounds__(512) dp_allreduce_kernel(const DpPeers P, DpLo
 // minimum of min_s / root_s over ranks.  Two one-CTA kernels so that no rank ever waits for another one here:
 //   post   (after sampling, on a side stream)  local minimum over the sampled leaves -> one double + flag to every rank
 //   apply  (right before K2, ~1 ms later: the values have long arrived)  factor -> is_weights scaled in place.
-// apply is ordered after this rank's own post by the flag in its own control block, not by the stream.
+// apply is ordered after this rank's own post by the flag in its own control block, not by the stream.  Posts and applies
+// count their epochs separately: a learner that samples batch i+1 while update i runs posts i+1 before it applies i (values
+// are kept for four epochs; a rank can be at most two posts ahead of the slowest apply).
 __global__ void __launch_bounds__(256) dp_is_post_kernel(const DpPeers P, DpLocal* __restrict__ L, const double* __restrict__ nodes,
                                                          long long leaf_base, const long long* __restrict__ idx, int n) {
     __shared__ double s[8];
@@ -181,15 +184,17 @@ __global__ void __launch_bounds__(256) dp_is_post_kernel(const DpPeers P, DpLoca
     for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((tid & 31) == 0) s[tid >> 5] = m;
     __syncthreads();
-    const unsigned int ep = *reinterpret_cast<volatile unsigned int*>(&L->is_epoch) + 1u;
+    const unsigned int ep = *reinterpret_cast<volatile unsigned int*>(&L->is_post_epoch) + 1u;
     double local = s[0];
     for (int w = 1; w < 8; ++w) local = fmin(local, s[w]);
     local /= nodes[0];
     if (tid < world) {
         DpShared* peer = P.ctl[tid];
-        *reinterpret_cast<volatile double*>(&peer->is_min[ep & 1u][rank]) = local;       // own control block included
+        *reinterpret_cast<volatile double*>(&peer->is_min[ep & 3u][rank]) = local;       // own control block included
         st_release_sys(&peer->is_flag[rank], ep);                                        // release: ordered after the value by this thread
     }
+    __syncthreads();
+    if (tid == 0) *reinterpret_cast<volatile unsigned int*>(&L->is_post_epoch) = ep;
 }
 
 __global__ void __launch_bounds__(256) dp_is_apply_kernel(const DpPeers P, DpLocal* __restrict__ L, double beta,
@@ -201,8 +206,8 @@ __global__ void __launch_bounds__(256) dp_is_apply_kernel(const DpPeers P, DpLoc
     __syncthreads();
     if (tid == 0) {
         double g = 1e300;
-        for (int r = 0; r < world; ++r) g = fmin(g, *reinterpret_cast<volatile double*>(&P.ctl[rank]->is_min[ep & 1u][r]));
-        const double local = *reinterpret_cast<volatile double*>(&P.ctl[rank]->is_min[ep & 1u][rank]);
+        for (int r = 0; r < world; ++r) g = fmin(g, *reinterpret_cast<volatile double*>(&P.ctl[rank]->is_min[ep & 3u][r]));
+        const double local = *reinterpret_cast<volatile double*>(&P.ctl[rank]->is_min[ep & 3u][rank]);
         s_factor = pow(local / g, -beta);
         if (factor_out != nullptr) *factor_out = (float)s_factor;
     }

@@ -81,7 +81,10 @@ struct r2d2_net {
     int64_t off[r2d2::NPARAM + 1];
     r2d2::Packed pk[2];
     r2d2::Acts ac[2];
-    r2d2::bf16* s2d;                 // shared by both slots
+    r2d2::bf16* s2d;                 // shared by both slots: the staging buffer the next forward / backward reads (= s2d_buf[s2d_idx])
+    r2d2::bf16* s2d_buf[2];          // [1] is allocated on first use: batch i+1 is gathered into it while update i still reads the other one
+    int s2d_idx;
+    void* rec_event;                 // optional cudaEvent_t recorded right before the forward recurrence of r2d2_net_forward_pair
     r2d2::SplitW W1both;             // conv1 weights of both slots stacked [64][64C]: one launch shares the frame tile
     int *row_src, *len_full, *len_learn, *d_rows;     // row_src: [2*Rmax]  (q rows | shifted rows)
     unsigned int* rec_bar;                            // [2] step counters of the persistent recurrence
@@ -760,6 +763,7 @@ int r2d2_net_create(int B, int T, int C, int A, int Lmax, int max_forward, r2d2_
     if (rc) return rc;
     R2D2_CUDA_CHECK(cudaMalloc(&n->s2d, (NF * 441 + 32) * 16 * C * sizeof(bf16)));     // + slack rows: the C = 1 wgrad reads taps of junk pixels
     R2D2_CUDA_CHECK(cudaMemset(n->s2d, 0, (NF * 441 + 32) * 16 * C * sizeof(bf16)));
+    n->s2d_buf[0] = n->s2d; n->s2d_buf[1] = nullptr; n->s2d_idx = 0;
     rc |= alloc_s(&n->W1both, 64ull * 64 * C);
     R2D2_CUDA_CHECK(cudaMalloc(&n->row_src, 2 * n->Rmax * sizeof(int)));
     R2D2_CUDA_CHECK(cudaMalloc(&n->len_full, B * sizeof(int)));
@@ -805,7 +809,7 @@ int r2d2_net_destroy(r2d2_net* n) {
     for (SplitW* x : ss) free_s(*x);
     float* fs[] = {n->dH, n->dhrec, n->dcrec, n->dout16, n->ws, n->colws, n->rec_partial};
     for (float* x : fs) cudaFree(x);
-    cudaFree(n->rec_bar); cudaFree(n->s2d); cudaFree(n->row_src); cudaFree(n->len_full); cudaFree(n->len_learn); cudaFree(n->d_rows);
+    cudaFree(n->rec_bar); cudaFree(n->s2d_buf[0]); cudaFree(n->s2d_buf[1]); cudaFree(n->row_src); cudaFree(n->len_full); cudaFree(n->len_learn); cudaFree(n->d_rows);
     cudaFree(g_doff[n]);
     g_doff.erase(n);
     delete n;
@@ -815,6 +819,27 @@ int r2d2_net_destroy(r2d2_net* n) {
 int r2d2_net_rows_capacity(const r2d2_net* n) { return n ? n->Rmax : -1; }
 /* device pointer of the space-to-depth frame staging buffer, bf16 [B*T][21][21][16*C] */
 void* r2d2_net_s2d_buffer(r2d2_net* n) { return n ? (void*)n->s2d : nullptr; }
+/* Two staging buffers: r2d2_net_s2d_buffer_at(n, idx) is the address to gather a batch into (the second buffer is allocated
+ * on first use -- not during a stream capture), r2d2_net_select_s2d(n, idx) makes it the one the following forward / backward
+ * calls read.  A learner gathers batch i+1 into the idle buffer while update i runs (worker.py:309-316 keeps its batches
+ * prefetched in a queue the same way). */
+static int ensure_s2d(r2d2_net* n, int idx) {
+    R2D2_REQUIRE(n && (idx == 0 || idx == 1), "bad staging buffer index");
+    if (!n->s2d_buf[idx]) {
+        const size_t bytes = ((size_t)n->NF * 441 + 32) * 16 * n->C * sizeof(r2d2::bf16);
+        R2D2_CUDA_CHECK(cudaMalloc(&n->s2d_buf[idx], bytes));
+        R2D2_CUDA_CHECK(cudaMemset(n->s2d_buf[idx], 0, bytes));
+    }
+    return R2D2_OK;
+}
+void* r2d2_net_s2d_buffer_at(r2d2_net* n, int idx) { return (n && ensure_s2d(n, idx) == R2D2_OK) ? (void*)n->s2d_buf[idx] : nullptr; }
+int r2d2_net_select_s2d(r2d2_net* n, int idx) {
+    int rc = ensure_s2d(n, idx);
+    if (rc) return rc;
+    n->s2d = n->s2d_buf[idx];
+    n->s2d_idx = idx;
+    return R2D2_OK;
+}
 int r2d2_net_ku(const r2d2_net* n) { return n ? n->KU : -1; }
 
 /* re-lay out the caller's flat parameter buffer (reference state_dict layout) for slot `which` */
@@ -1154,6 +1179,68 @@ int r2d2_net_set_dense_grads_event(r2d2_net* n, void* cuda_event) {
     n->dense_grads_event = cuda_event;
     return R2D2_OK;
 }
+/* Optional cudaEvent_t recorded by r2d2_net_forward_pair right before its recurrence launch: for ~270 us from there 84 of
+ * the 148 SMs are idle (the recurrence clusters hold 64), which is where a learner puts the gather of its NEXT batch. */
+int r2d2_net_set_rec_event(r2d2_net* n, void* cuda_event) {
+    R2D2_REQUIRE(n, "null handle");
+    n->rec_event = cuda_event;
+    return R2D2_OK;
+}
+/* r2d2_net_shadow_gate: a one-warp kernel on `stream` that returns once the BPTT recurrence of the update it belongs to is
+ * executing (or after ~20 ms).  That kernel holds 4 clusters of 16 SMs for ~350 us and leaves the other 84 SMs idle; work
+ * enqueued behind the gate (the gather of the next batch, launched with a shared-memory footprint that does not fit next to a
+ * recurrence CTA) runs on exactly those SMs.  Launching it BEFORE the recurrence instead would let its CTAs take SMs in every
+ * GPC, and a 16-CTA cluster needs a whole GPC's worth of free SMs to start.
+ * Pairing: every update launches one BPTT kernel (it counts itself in ctl[0] when it begins) and the caller one gate;
+ * r2d2_net_shadow_gate_reset (stream-ordered, before the first update of the pipeline) notes how many BPTT kernels have run
+ * so far, gate number g then waits for BPTT number base + g.  A gate that runs late (its recurrence already over) passes. */
+__global__ void r2d2_shadow_gate_kernel(volatile unsigned int* ctl /* [0] BPTT kernels started, [1] base, [2] gates so far */) {
+    if (threadIdx.x != 0) return;
+    const unsigned int g = ctl[2] + 1u;
+    const unsigned int target = ctl[1] + g;
+    const long long t0 = clock64();
+    while ((int)(ctl[0] - target) < 0 && clock64() - t0 < 40000000ll) __nanosleep(500);
+    ctl[2] = g;
+    __nanosleep(3000);                                       // the other clusters of the launch are placed within this
+}
+__global__ void r2d2_shadow_gate_reset_kernel(volatile unsigned int* ctl) {
+    if (threadIdx.x == 0) { ctl[1] = ctl[0]; ctl[2] = 0u; }
+}
+static int shadow_gate_configure() {
+    static unsigned long long configured = 0;
+    int dev = 0;
+    R2D2_CUDA_CHECK(cudaGetDevice(&dev));
+    if (!(configured & (1ull << (dev & 63)))) {              // a shared-memory-free CTA must not flip its SM to the large-L1 carveout (dp.cu)
+        R2D2_CUDA_CHECK(cudaFuncSetAttribute(r2d2_shadow_gate_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        R2D2_CUDA_CHECK(cudaFuncSetAttribute(r2d2_shadow_gate_reset_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        configured |= 1ull << (dev & 63);
+    }
+    return R2D2_OK;
+}
+int r2d2_net_shadow_gate(r2d2_net* n, void* stream) {
+    R2D2_REQUIRE(n, "null handle");
+    int rc = shadow_gate_configure();
+    if (rc) return rc;
+    r2d2_shadow_gate_kernel<<<1, 32, 0, as_stream(stream)>>>(n->rec_bar + 60);
+    R2D2_LAUNCH_CHECK();
+    return R2D2_OK;
+}
+int r2d2_net_shadow_gate_reset(r2d2_net* n, void* stream) {
+    R2D2_REQUIRE(n, "null handle");
+    int rc = shadow_gate_configure();
+    if (rc) return rc;
+    r2d2_shadow_gate_reset_kernel<<<1, 32, 0, as_stream(stream)>>>(n->rec_bar + 60);
+    R2D2_LAUNCH_CHECK();
+    return R2D2_OK;
+}
+// inside a stream capture a plain record would only mark a capture-internal point; callers wait on these events from a
+// stream OUTSIDE the graph, so the record must become an external event-record node
+static cudaError_t record_user_event(void* ev, cudaStream_t s) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaError_t e = cudaStreamIsCapturing(s, &cap);
+    if (e != cudaSuccess) return e;
+    return cudaEventRecordWithFlags((cudaEvent_t)ev, s, cap == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault);
+}
 
 /* (h, c) of slot `which` after time step t of the last forward, as [B][2][512] -- what an actor carries to its next
  * step (model.py:65-79 returns it; worker.py:533-541).  With T = 1 nets this turns r2d2_net_forward into a batched
@@ -1186,6 +1273,7 @@ int r2d2_net_forward_pair(r2d2_net* n, const float* params_online, const float* 
     }
     if (!rc) rc = net_encode(n, 0, f0, s, true);
     if (!rc) rc = net_encode(n, 1, f1, s, true);
+    if (!rc && n->rec_event) R2D2_CUDA_CHECK(record_user_event(n->rec_event, s));
     if (!rc) rc = net_recurrence(n, 2, hidden, s);
     if (!rc) rc = net_heads(n, 0, params_online, q_learn_out, qn_online_out, s, false);
     if (!rc) rc = net_heads(n, 1, params_target, nullptr, qn_target_out, s, false);
@@ -1250,6 +1338,7 @@ int r2d2_net_backward(r2d2_net* n, const float* params, const float* dq, float* 
         P.c0 = n->hidden + H; P.ld_c0 = 2 * H; P.len = n->len_learn; P.DGhi = n->DG.hi; P.DGlo = n->DG.lo;
         P.partial = n->rec_partial; P.flags = n->rec_bar + 32; P.B = B; P.T = T; P.fast = g_fast_math == 1;
         P.trace = g_rec_trace_bwd;
+        P.started = n->rec_bar + 60;
         cudaError_t e = g_cluster_recurrence ? launch_rec2_bwd(P, s) : cudaErrorNotSupported;     // 16-CTA clusters, DSMEM reduce-scatter
         if (e == cudaErrorNotSupported && B <= 64) e = launch_rec_bwd(P, s);                       // L2-flag cooperative kernel
         if (e != cudaErrorNotSupported) {
@@ -1311,14 +1400,7 @@ int r2d2_net_backward(r2d2_net* n, const float* params, const float* dq, float* 
         R2D2_CUDA_CHECK(fin_flush(n, grads, d_off, s));            // every dense-layer gradient (heads, LSTM, FC) in one reduction launch
         // every gradient from feature.7.weight to the end of the flat layout (FC, LSTM, heads: 98 % of the bytes) is final:
         // a data-parallel caller can start reducing that range while the conv layers' backward still runs
-        if (n->dense_grads_event) {
-            // inside a stream capture a plain record would only mark a capture-internal point; the caller waits on this event
-            // from a stream OUTSIDE the graph, so it must become an external event-record node
-            cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-            R2D2_CUDA_CHECK(cudaStreamIsCapturing(s, &cap));
-            R2D2_CUDA_CHECK(cudaEventRecordWithFlags((cudaEvent_t)n->dense_grads_event, s,
-                                                     cap == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault));
-        }
+        if (n->dense_grads_event) R2D2_CUDA_CHECK(record_user_event(n->dense_grads_event, s));
         SrcMatK a2{n->dlat.hi, n->dlat.lo, NF, LATENT, LATENT};
         SrcMatMN b2{pk.Wfcp.hi, pk.Wfcp.lo, FLAT3, LATENT, FLAT3};
         Epi2MaskedToGrid3 e{n->dpre3, ro(ac.act3), NF};

@@ -303,6 +303,7 @@ struct RecBwdParams {
     unsigned int* flags;                      // [8] flagDG + [16] flagDH, zero before launch
     int B, T, fast;
     unsigned long long* trace = nullptr;      // optional [T][8] globaltimer stamps of CTA 0 (cluster kernel, debug)
+    unsigned int* started = nullptr;          // optional counter, +1 when the cluster kernel has begun executing (r2d2_net_shadow_gate)
 };
 
 __global__ void __launch_bounds__(UM_THREADS, 1) rec_bwd_kernel(const RecBwdParams P) {

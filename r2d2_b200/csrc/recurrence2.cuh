@@ -441,6 +441,7 @@ __global__ void __launch_bounds__(RB2_THREADS, 1) rec2_bwd_kernel(const RecBwdPa
     const int B = P.B, T = P.T;
     const bool want_lo = !P.fast;
 
+    if (blockIdx.x == 0 && tid == 0 && P.started != nullptr) atomicAdd(P.started, 1u);     // "the clusters are resident from here on"
     if (tid == 0) {
         for (int i = 0; i < 6; ++i) mbar_init(smem_u32(&bars[i]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");

@@ -38,6 +38,7 @@ struct r2d2_replay {
     uint8_t* store;          // [num_blocks][lay.total]
     r2d2::SeqDesc* desc;     // [desc_cap]
     int desc_cap;
+    int copy_smem;           // dynamic shared memory the gather's copy CTAs ask for without using it (r2d2_replay_set_copy_smem)
 };
 
 namespace r2d2 {
@@ -236,10 +237,27 @@ static int replay_gather_impl(r2d2_replay* r, const int64_t* idx, const float* i
     }
     cudaStream_t s = as_stream(stream);
     replay_meta_kernel<<<1, 256, B * sizeof(int), s>>>(r->store, r->lay, r->spb, r->num_blocks, idx, B, r->desc, burn, learn, fwd, rows_out);
-    replay_copy_kernel<<<dim3(T, B), 256, 0, s>>>(r->store, r->lay, r->desc, isw, T, r->C, r->A, r->H, r->frame_bytes, obs,
+    replay_copy_kernel<<<dim3(T, B), 256, r->copy_smem, s>>>(r->store, r->lay, r->desc, isw, T, r->C, r->A, r->H, r->frame_bytes, obs,
                                                   (__nv_bfloat16*)s2d, last_action,
                                                   last_reward, hidden, action, n_step_reward, gamma, is_weights_rows);
     R2D2_LAUNCH_CHECK();
+    return R2D2_OK;
+}
+
+/* Placement control for a gather that runs next to a learner update (worker.py:309-316 prefetches its batches the same way):
+ * with `bytes` of (unused) dynamic shared memory per copy CTA, the CTAs do not fit on an SM that holds a ~200 KB GEMM /
+ * recurrence CTA, so the copy only takes SMs the update leaves idle (r2d2_net_shadow_gate); 0 = anywhere (default). */
+int r2d2_replay_set_copy_smem(r2d2_replay* r, int bytes) {
+    R2D2_REQUIRE(r && bytes >= 0 && bytes <= 48 * 1024, "bad arguments");
+    static unsigned long long configured = 0;
+    int dev = 0;
+    R2D2_CUDA_CHECK(cudaGetDevice(&dev));
+    if (!(configured & (1ull << (dev & 63)))) {
+        R2D2_CUDA_CHECK(cudaFuncSetAttribute(replay_copy_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        R2D2_CUDA_CHECK(cudaFuncSetAttribute(replay_meta_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        configured |= 1ull << (dev & 63);
+    }
+    r->copy_smem = bytes;
     return R2D2_OK;
 }
 

@@ -221,6 +221,7 @@ class DeviceLearner:
         self.exp_avg = torch.zeros_like(self.online.flat)
         self.exp_avg_sq = torch.zeros_like(self.online.flat)
         self._num_updates = 0
+        self._s2d_idx = 0
         h = C.c_void_p()
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().r2d2_net_create(batch_size, seq_frames, in_channels, action_dim, max_learning,
@@ -323,6 +324,14 @@ class DeviceLearner:
         return out
 
     @_lib.on_device
+    @_lib.on_device
+    def select_s2d(self, idx: int) -> None:
+        """Which of the two frame staging buffers the following forward / backward calls read (the other one may be filled
+        with the next batch meanwhile: DeviceReplay.sample(fuse_into=self, slot=...))."""
+        if idx != self._s2d_idx:
+            _lib.check(_lib.lib().r2d2_net_select_s2d(self._h, int(idx)))
+            self._s2d_idx = int(idx)
+
     def use_grad_buffer(self, flat: torch.Tensor) -> None:
         """Rebind the flat gradient buffer (same layout) to caller-provided device memory -- e.g. symmetric memory that the
         other ranks of a data-parallel run have mapped (dist.PeerExchange).  Call before the first update."""
@@ -429,7 +438,7 @@ class DeviceLearner:
         pre = self.pre_td_hook                                   # plain stream-ordered launches may declare themselves capturable
         if not self.use_graph or (pre is not None and not getattr(pre, "capturable", False)) or (hook is not None and not split):
             return self._update_eager(b)
-        key = (_lib.lib().r2d2_config_epoch(),) + tuple(None if v is None else (v.data_ptr() if isinstance(v, torch.Tensor) else v)
+        key = (_lib.lib().r2d2_config_epoch(), self._s2d_idx) + tuple(None if v is None else (v.data_ptr() if isinstance(v, torch.Tensor) else v)
                                                       for v in (b.get(k) for k in _BATCH_KEYS))
         self._live = b
         if not split:

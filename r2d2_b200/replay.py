@@ -82,9 +82,13 @@ class DeviceReplay:
         return self.size
 
     def _alloc_batch(self):
+        self.batches = [self._new_batch()]          # a second set is created on first use (sample(slot=1): sampling ahead)
+        self.batch = self.batches[0]
+
+    def _new_batch(self):
         d, B, T, A = self.device, self.batch_size, self.T, self.A
         R = self.rows_cap
-        self.batch = dict(
+        return dict(
             obs=torch.zeros(B, T, self.C, 84, 84, dtype=torch.uint8, device=d),
             last_action=torch.zeros(B, T, A, dtype=torch.uint8, device=d),
             last_reward=torch.zeros(B, T, device=d), hidden=torch.zeros(B, 2, self.H, device=d),
@@ -174,21 +178,31 @@ class DeviceReplay:
 
     # ------------------------------------------------------------------ sample_batch (worker.py:163-240), on device
     @_lib.on_device
-    def sample(self, unit_uniforms: Optional[torch.Tensor] = None, fuse_into=None):
+    def sample(self, unit_uniforms: Optional[torch.Tensor] = None, fuse_into=None, slot: int = 0):
         """Returns (batch dict of device tensors, idxes int64 device, old_ptr).  With fuse_into = a DeviceLearner whose
-        shape matches, frames are written straight into its space-to-depth staging buffer and batch["obs"] is None."""
+        shape matches, frames are written straight into its space-to-depth staging buffer and batch["obs"] is None.
+        slot 0/1: which of two sets of output buffers (and of the learner's two staging buffers) receives the batch, so that
+        batch i+1 can be gathered while update i still reads batch i."""
         self._activate_pending()
         idx, isw = self.tree.sample_device(self.batch_size, unit_uniforms)
-        out = self.gather_fused(idx, isw, fuse_into) if fuse_into is not None else self.gather(idx, isw)
+        while len(self.batches) <= slot:
+            self.batches.append(self._new_batch())
+        out = self.gather_fused(idx, isw, fuse_into, slot) if fuse_into is not None else self.gather(idx, isw, slot)
         if self._gather_event is None:
             self._gather_event = torch.cuda.Event()
         self._gather_event.record(torch.cuda.current_stream(self.device))
         return out, idx, self.block_ptr
 
-    def gather_fused(self, idx: torch.Tensor, isw: torch.Tensor, core) -> dict:
+    def set_copy_smem(self, nbytes: int) -> None:
+        """Shared-memory footprint of the gather's copy CTAs (placement control, r2d2_replay_set_copy_smem)."""
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().r2d2_replay_set_copy_smem(self._h, int(nbytes)))
+
+    def gather_fused(self, idx: torch.Tensor, isw: torch.Tensor, core, slot: int = 0) -> dict:
         assert core.B == self.batch_size and core.T == self.T and core.C == self.C
-        b, p = self.batch, _lib.ptr
-        s2d = _lib.lib().r2d2_net_s2d_buffer(core._h)
+        b, p = self.batches[slot], _lib.ptr
+        s2d = _lib.lib().r2d2_net_s2d_buffer_at(core._h, slot)
+        assert s2d, "no staging buffer"
         _lib.check(_lib.lib().r2d2_replay_gather_s2d(self._h, p(idx), p(isw), self.batch_size, self.T, s2d, p(b["last_action"]),
                                                      p(b["last_reward"]), p(b["hidden"]), p(b["action"]), p(b["n_step_reward"]),
                                                      p(b["gamma"]), p(b["burn_in"]), p(b["learning"]), p(b["forward"]),
@@ -197,8 +211,8 @@ class DeviceReplay:
         out["obs"] = None
         return out
 
-    def gather(self, idx: torch.Tensor, isw: torch.Tensor) -> dict:
-        b, p = self.batch, _lib.ptr
+    def gather(self, idx: torch.Tensor, isw: torch.Tensor, slot: int = 0) -> dict:
+        b, p = self.batches[slot], _lib.ptr
         _lib.check(_lib.lib().r2d2_replay_gather(self._h, p(idx), p(isw), self.batch_size, self.T, p(b["obs"]), p(b["last_action"]),
                                                  p(b["last_reward"]), p(b["hidden"]), p(b["action"]), p(b["n_step_reward"]),
                                                  p(b["gamma"]), p(b["burn_in"]), p(b["learning"]), p(b["forward"]),

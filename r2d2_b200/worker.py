@@ -27,7 +27,7 @@ from typing import Tuple
 import numpy as np
 import torch
 
-from . import config
+from . import _lib, config
 from .environment import create_env
 from .model import AgentState, Network
 from .priority_tree import PriorityTree  # noqa: F401  (re-exported like the reference module does)
@@ -237,6 +237,13 @@ class Learner:
         self.game_name = game_name
         self.replay = None                     # DeviceReplay, created on the first forwarded block
         self.is_weight_sync = None             # dist.GlobalISWeights in data-parallel runs
+        # Sample batch i+1 while update i runs (the reference's buffer process keeps sampled batches queued ahead of its
+        # learner the same way, worker.py:124-139 / 309-316): the gather leaves the update's critical path.  Off by default:
+        # the strictly sequential loop (sample sees the priorities of the update just before it) is what the closed-loop
+        # parity test pins; R2D2_SAMPLE_AHEAD=1 / sample_ahead = True switch it on.
+        self.sample_ahead = os.environ.get("R2D2_SAMPLE_AHEAD") == "1"
+        self._ahead = None
+        self._ahead_at = -1
         self._results = None                   # two pinned result slots (priorities, loss) for enqueue_update/collect
         self._sum_loss = 0.0
         self.env_steps = 0
@@ -311,13 +318,61 @@ class Learner:
 
     # -- one update from the HBM-resident replay (sample -> update -> priority update, no host round trip) --------
     def update_from_replay(self):
+        if self.sample_ahead:
+            return self._update_from_replay_ahead()
         batch, idx, old_ptr = self.replay.sample(fuse_into=self.core)     # frames go straight into conv1's staging layout
+        self.core.select_s2d(0)
         if self.is_weight_sync is not None:                               # data parallel: weights of one sampler over all shards
             self.is_weight_sync.correct(self.replay, batch, idx)          # side stream; consumed by the gradient hook
         self.core.update(batch)
         if self.is_weight_sync is not None and hasattr(self.is_weight_sync, "join"):
             self.is_weight_sync.join()                                     # side-stream reads of the tree end before it changes
         self.replay.update_priorities(idx, self.core.prio, old_ptr)
+        self.env_steps = self.replay.env_steps
+        self._after_update()
+
+    # -- the same update with the NEXT batch sampled and gathered while this one trains ---------------------------
+    def _sample_ahead(self, slot: int, shadow: bool) -> dict:
+        """Sample + gather one batch into buffer set `slot` on the sampling stream: after the previous priority update, and
+        (shadow) behind r2d2_net_shadow_gate, i.e. on the SMs the running update's BPTT recurrence leaves idle."""
+        dev = self.device
+        if getattr(self, "_sample_stream", None) is None:
+            self._sample_stream = torch.cuda.Stream(device=dev)
+            self._tree_updated = torch.cuda.Event()
+            self._tree_updated.record(torch.cuda.current_stream(dev))
+            self.replay.set_copy_smem(32 * 1024)                          # copy CTAs cannot share an SM with a recurrence / GEMM CTA
+        st = self._sample_stream
+        with torch.cuda.stream(st):
+            st.wait_event(self._tree_updated)                             # the priorities of the previous update are in the tree (recorded
+                                                                          # right before the running update was launched)
+            if shadow:
+                _lib.check(_lib.lib().r2d2_net_shadow_gate(self.core._h, st.cuda_stream))
+            batch, idx, old_ptr = self.replay.sample(fuse_into=self.core, slot=slot)
+            if self.is_weight_sync is not None:
+                self.is_weight_sync.correct(self.replay, batch, idx)
+            ready = torch.cuda.Event()
+            ready.record(st)
+        return dict(batch=batch, idx=idx, old_ptr=old_ptr, ready=ready, slot=slot)
+
+    @_lib.on_device
+    def _update_from_replay_ahead(self):
+        main = torch.cuda.current_stream(self.device)
+        if self._ahead is not None and self._ahead_at != self.core.num_updates:
+            self._ahead = None                                            # other updates ran in between: the gates lost their pairing
+        if self._ahead is None:
+            _lib.check(_lib.lib().r2d2_net_shadow_gate_reset(self.core._h, main.cuda_stream))
+            self._ahead = self._sample_ahead(0, shadow=False)
+        cur = self._ahead
+        main.wait_event(cur["ready"])
+        self.core.select_s2d(cur["slot"])
+        self._tree_updated.record(main)                                   # every tree write so far (priority update, ingested blocks)
+        self.core.update(cur["batch"])
+        self._ahead = self._sample_ahead(1 - cur["slot"], shadow=True)    # enqueued now, runs mid-update
+        main.wait_event(self._ahead["ready"])                             # the tree must not change under the sampler (long done)
+        if self.is_weight_sync is not None and hasattr(self.is_weight_sync, "join"):
+            self.is_weight_sync.join()
+        self.replay.update_priorities(cur["idx"], self.core.prio, cur["old_ptr"])
+        self._ahead_at = self.core.num_updates
         self.env_steps = self.replay.env_steps
         self._after_update()
 
