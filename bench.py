@@ -482,9 +482,11 @@ def run_ours(args):
     sampler.start()
     ms_step_seq = None
     nccl_dp = world > 1 and dp_exchange == "nccl"                     # the NCCL hooks keep per-batch state in Python: sequential there
+    learner.sample_ahead = False
     if not args.no_sample_ahead and not nccl_dp:
-        ms_step_seq = timed(step_resident, args.steps, args.warmup)   # strictly sequential loop first (reported next to the headline)
-        learner.sample_ahead = True                                   # batch i+1 is sampled + gathered while update i runs
+        learner.sample_ahead = False
+        ms_step_seq = timed(step_resident, args.steps, args.warmup)   # plain sequential loop first (reported next to the headline)
+        learner.sample_ahead = True                                   # priority update i / sample i+1 / gather i+1 under update i's backward
         for w in range(6):                                            # untimed: the second set of batch buffers gets its CUDA graph
             step_resident(w)                                          # (a key is captured the second time it is seen)
     ms_step = timed(step_resident, args.steps, args.warmup)
@@ -529,9 +531,9 @@ def run_ours(args):
                                        f"{C}x84x84 u8 frames, A={A}, HBM replay of {NUM_BLOCKS} blocks, sum tree 2^20",
                            "channels": C, "global_batch": world * B, "parallelism": f"dp{world}", "exchange": dp_exchange, "precision": args.precision,
                            "host": f"staging copies on high-priority streams; CUDA_DEVICE_MAX_CONNECTIONS={os.environ.get('CUDA_DEVICE_MAX_CONNECTIONS')} (binding the process to the GPU's NUMA node was measured and made the copies slower on this pool: not done)",
-                           "sampling": ("batch i+1 is sampled and gathered on a second stream while update i runs (lag 1; the reference's "
-                                        "buffer process keeps batches queued ahead of its learner, worker.py:124-139,309-316); the gather's "
-                                        "copy CTAs are steered onto the SMs the BPTT recurrence leaves idle")
+                           "sampling": ("priority update of update i, sampling and gather of batch i+1 on a second stream while update i's "
+                                        "backward pass runs (same tree operation sequence and bit-identical results as the sequential "
+                                        "loop); the gather's copy CTAs are steered onto the SMs the BPTT recurrence leaves idle")
                                        if ms_step_seq is not None else "sequential: sample -> update -> priority update",
                            "l2": f"inputs larger than L2: batches are gathered from a {NUM_BLOCKS * replay.blob_bytes / 1e9:.1f} GB HBM "
                                  f"block store; ~1 GB of activations streamed per step"},

@@ -112,10 +112,11 @@ void* r2d2_net_s2d_buffer(r2d2_net* n);
  * first use, not during a stream capture), select makes idx the one the following forward / backward calls read. */
 void* r2d2_net_s2d_buffer_at(r2d2_net* n, int idx);
 int r2d2_net_select_s2d(r2d2_net* n, int idx);
-/* Optional cudaEvent_t recorded by r2d2_net_forward_pair right before its recurrence launch. */
-int r2d2_net_set_rec_event(r2d2_net* n, void* cuda_event);
+/* cudaEventRecord for an event that a stream OUTSIDE a CUDA graph waits on: an external event-record node while `stream` is
+ * being captured, a plain record otherwise. */
+int r2d2_event_record(void* cuda_event, void* stream);
 /* One-warp kernel on `stream` that returns once the backward recurrence of the update it is paired with is executing (or
- * after ~20 ms): work enqueued behind it lands on the 84 SMs that kernel leaves idle (see r2d2_replay_set_copy_smem).
+ * after ~1 s; placement only): work enqueued behind it lands on the 84 SMs that kernel leaves idle (see r2d2_replay_set_copy_smem).
  * Pairing: one gate per update; _reset (stream-ordered, before the first update of such a pipeline) re-bases the count. */
 int r2d2_net_shadow_gate(r2d2_net* n, void* stream);
 int r2d2_net_shadow_gate_reset(r2d2_net* n, void* stream);

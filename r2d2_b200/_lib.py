@@ -83,7 +83,7 @@ SIGNATURES = {
     "r2d2_net_s2d_buffer": (p, [p]),
     "r2d2_net_s2d_buffer_at": (p, [p, C.c_int]),
     "r2d2_net_select_s2d": (C.c_int, [p, C.c_int]),
-    "r2d2_net_set_rec_event": (C.c_int, [p, p]),
+    "r2d2_event_record": (C.c_int, [p, p]),
     "r2d2_net_shadow_gate": (C.c_int, [p, p]),
     "r2d2_net_shadow_gate_reset": (C.c_int, [p, p]),
     "r2d2_replay_set_copy_smem": (C.c_int, [p, C.c_int]),

@@ -84,7 +84,6 @@ struct r2d2_net {
     r2d2::bf16* s2d;                 // shared by both slots: the staging buffer the next forward / backward reads (= s2d_buf[s2d_idx])
     r2d2::bf16* s2d_buf[2];          // [1] is allocated on first use: batch i+1 is gathered into it while update i still reads the other one
     int s2d_idx;
-    void* rec_event;                 // optional cudaEvent_t recorded right before the forward recurrence of r2d2_net_forward_pair
     r2d2::SplitW W1both;             // conv1 weights of both slots stacked [64][64C]: one launch shares the frame tile
     int *row_src, *len_full, *len_learn, *d_rows;     // row_src: [2*Rmax]  (q rows | shifted rows)
     unsigned int* rec_bar;                            // [2] step counters of the persistent recurrence
@@ -829,6 +828,7 @@ static int ensure_s2d(r2d2_net* n, int idx) {
         const size_t bytes = ((size_t)n->NF * 441 + 32) * 16 * n->C * sizeof(r2d2::bf16);
         R2D2_CUDA_CHECK(cudaMalloc(&n->s2d_buf[idx], bytes));
         R2D2_CUDA_CHECK(cudaMemset(n->s2d_buf[idx], 0, bytes));
+        R2D2_CUDA_CHECK(cudaDeviceSynchronize());      // the memset runs on the legacy stream: it must not land after a gather on another stream
     }
     return R2D2_OK;
 }
@@ -1179,15 +1179,8 @@ int r2d2_net_set_dense_grads_event(r2d2_net* n, void* cuda_event) {
     n->dense_grads_event = cuda_event;
     return R2D2_OK;
 }
-/* Optional cudaEvent_t recorded by r2d2_net_forward_pair right before its recurrence launch: for ~270 us from there 84 of
- * the 148 SMs are idle (the recurrence clusters hold 64), which is where a learner puts the gather of its NEXT batch. */
-int r2d2_net_set_rec_event(r2d2_net* n, void* cuda_event) {
-    R2D2_REQUIRE(n, "null handle");
-    n->rec_event = cuda_event;
-    return R2D2_OK;
-}
 /* r2d2_net_shadow_gate: a one-warp kernel on `stream` that returns once the BPTT recurrence of the update it belongs to is
- * executing (or after ~20 ms).  That kernel holds 4 clusters of 16 SMs for ~350 us and leaves the other 84 SMs idle; work
+ * executing (or after ~1 s: placement only, correctness never depends on it).  That kernel holds 4 clusters of 16 SMs for ~350 us and leaves the other 84 SMs idle; work
  * enqueued behind the gate (the gather of the next batch, launched with a shared-memory footprint that does not fit next to a
  * recurrence CTA) runs on exactly those SMs.  Launching it BEFORE the recurrence instead would let its CTAs take SMs in every
  * GPC, and a 16-CTA cluster needs a whole GPC's worth of free SMs to start.
@@ -1199,7 +1192,7 @@ __global__ void r2d2_shadow_gate_kernel(volatile unsigned int* ctl /* [0] BPTT k
     const unsigned int g = ctl[2] + 1u;
     const unsigned int target = ctl[1] + g;
     const long long t0 = clock64();
-    while ((int)(ctl[0] - target) < 0 && clock64() - t0 < 40000000ll) __nanosleep(500);
+    while ((int)(ctl[0] - target) < 0 && clock64() - t0 < 2000000000ll) __nanosleep(500);
     ctl[2] = g;
     __nanosleep(3000);                                       // the other clusters of the launch are placed within this
 }
@@ -1241,6 +1234,13 @@ static cudaError_t record_user_event(void* ev, cudaStream_t s) {
     if (e != cudaSuccess) return e;
     return cudaEventRecordWithFlags((cudaEvent_t)ev, s, cap == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault);
 }
+/* cudaEventRecord for events that streams OUTSIDE a CUDA graph wait on: an external event-record node while `stream` is being
+ * captured, a plain record otherwise.  (The learner marks "K2 done: priorities final" this way for its sampling stream.) */
+int r2d2_event_record(void* cuda_event, void* stream) {
+    R2D2_REQUIRE(cuda_event, "null event");
+    R2D2_CUDA_CHECK(record_user_event(cuda_event, as_stream(stream)));
+    return R2D2_OK;
+}
 
 /* (h, c) of slot `which` after time step t of the last forward, as [B][2][512] -- what an actor carries to its next
  * step (model.py:65-79 returns it; worker.py:533-541).  With T = 1 nets this turns r2d2_net_forward into a batched
@@ -1273,7 +1273,6 @@ int r2d2_net_forward_pair(r2d2_net* n, const float* params_online, const float* 
     }
     if (!rc) rc = net_encode(n, 0, f0, s, true);
     if (!rc) rc = net_encode(n, 1, f1, s, true);
-    if (!rc && n->rec_event) R2D2_CUDA_CHECK(record_user_event(n->rec_event, s));
     if (!rc) rc = net_recurrence(n, 2, hidden, s);
     if (!rc) rc = net_heads(n, 0, params_online, q_learn_out, qn_online_out, s, false);
     if (!rc) rc = net_heads(n, 1, params_target, nullptr, qn_target_out, s, false);

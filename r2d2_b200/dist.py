@@ -210,6 +210,8 @@ class PeerISWeights:
     pre_td_hook (`apply`, a graph-capturable launch right before K2) turns the ranks' scalars into this rank's factor and scales
     batch['is_weights'] -- a millisecond after the post, so no rank waits for another one."""
 
+    ahead_safe = True          # post(i+1) may run before apply(i): Learner.update_from_replay's sample-ahead pipeline
+
     def __init__(self, exchange: PeerExchange, beta: float):
         self.exchange, self.beta = exchange, beta
         self._weights = None

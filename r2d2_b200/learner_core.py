@@ -154,6 +154,11 @@ class BatchStager:
                        burn_in=torch.zeros(B, dtype=torch.uint8, device=d), learning=torch.zeros(B, dtype=torch.uint8, device=d),
                        forward=torch.zeros(B, dtype=torch.uint8, device=d), is_weights=torch.zeros(R, device=d))
             self.slots.append(dict(buf=buf, ready=torch.cuda.Event(), free=None, tmax=T))
+        # the zero fills above were enqueued on the CURRENT stream, possibly behind a running update: the copy stream must not
+        # overtake them (the first staged batch would be zeroed after it had arrived)
+        filled = torch.cuda.Event()
+        filled.record(torch.cuda.current_stream(d))
+        self.stream.wait_event(filled)
         self._next = 0
 
     @staticmethod
@@ -252,6 +257,10 @@ class DeviceLearner:
         self.grad_hook: Optional[Callable[["DeviceLearner"], None]] = None
         # hook called between the forward unroll and the TD kernel (e.g. join a side stream that rescales is_weights)
         self.pre_td_hook: Optional[Callable[["DeviceLearner"], None]] = None
+        # recorded after K2 (an external event-record node when the update is replayed from a graph): "priorities final" --
+        # Learner's sampling stream waits on it to apply them and sample the next batch while the backward pass runs
+        self.td_event = torch.cuda.Event()
+        self.td_event.record(torch.cuda.current_stream(self.device))       # materialise the cudaEvent_t
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -369,6 +378,8 @@ class DeviceLearner:
                                            p(b["n_step_reward"]), p(b["gamma"]), p(b["is_weights"]), p(b["learning"]),
                                            self.B, self.A, p(self.td), p(self.prio), p(self.loss_sum), p(self.rows),
                                            p(self.dq), _lib.stream_ptr()))
+        if self.td_event is not None:
+            _lib.check(_lib.lib().r2d2_event_record(self.td_event.cuda_event, _lib.stream_ptr()))
 
     @_lib.on_device
     def compute_gradients(self, b: dict) -> None:

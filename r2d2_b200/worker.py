@@ -237,11 +237,11 @@ class Learner:
         self.game_name = game_name
         self.replay = None                     # DeviceReplay, created on the first forwarded block
         self.is_weight_sync = None             # dist.GlobalISWeights in data-parallel runs
-        # Sample batch i+1 while update i runs (the reference's buffer process keeps sampled batches queued ahead of its
-        # learner the same way, worker.py:124-139 / 309-316): the gather leaves the update's critical path.  Off by default:
-        # the strictly sequential loop (sample sees the priorities of the update just before it) is what the closed-loop
-        # parity test pins; R2D2_SAMPLE_AHEAD=1 / sample_ahead = True switch it on.
-        self.sample_ahead = os.environ.get("R2D2_SAMPLE_AHEAD") == "1"
+        # update_from_replay can run the priority update of update i and the sampling + gather of batch i+1 on a second
+        # stream WHILE update i's backward pass runs (the priorities are final after K2): same sequence of tree operations
+        # as the sequential loop, bit-identical results (tests/test_gpu_sample_ahead.py), off the critical path.
+        # R2D2_SAMPLE_AHEAD=0 / sample_ahead = False keep the plain sequential loop.
+        self.sample_ahead = os.environ.get("R2D2_SAMPLE_AHEAD", "1") != "0"
         self._ahead = None
         self._ahead_at = -1
         self._results = None                   # two pinned result slots (priorities, loss) for enqueue_update/collect
@@ -318,7 +318,7 @@ class Learner:
 
     # -- one update from the HBM-resident replay (sample -> update -> priority update, no host round trip) --------
     def update_from_replay(self):
-        if self.sample_ahead:
+        if self.sample_ahead and (self.is_weight_sync is None or getattr(self.is_weight_sync, "ahead_safe", False)):
             return self._update_from_replay_ahead()
         batch, idx, old_ptr = self.replay.sample(fuse_into=self.core)     # frames go straight into conv1's staging layout
         self.core.select_s2d(0)
@@ -332,24 +332,24 @@ class Learner:
         self._after_update()
 
     # -- the same update with the NEXT batch sampled and gathered while this one trains ---------------------------
-    def _sample_ahead(self, slot: int, shadow: bool) -> dict:
-        """Sample + gather one batch into buffer set `slot` on the sampling stream: after the previous priority update, and
-        (shadow) behind r2d2_net_shadow_gate, i.e. on the SMs the running update's BPTT recurrence leaves idle."""
-        dev = self.device
-        if getattr(self, "_sample_stream", None) is None:
-            self._sample_stream = torch.cuda.Stream(device=dev)
-            self._tree_updated = torch.cuda.Event()
-            self._tree_updated.record(torch.cuda.current_stream(dev))
-            self.replay.set_copy_smem(32 * 1024)                          # copy CTAs cannot share an SM with a recurrence / GEMM CTA
+    def _sample_ahead(self, slot: int, after=None) -> dict:
+        """Sampling stream: [priority update of the running update `after`] -> sample -> gather into buffer set `slot`.
+        With `after`, everything sits behind r2d2_net_shadow_gate: it starts when that update's BPTT recurrence is executing --
+        its priorities are final by then (K2 precedes the backward pass) -- and runs on the SMs the recurrence leaves idle.
+        The tree therefore sees exactly the sequence priority-update(i) -> sample(i+1) of the sequential loop."""
         st = self._sample_stream
+        sync = self.is_weight_sync
         with torch.cuda.stream(st):
-            st.wait_event(self._tree_updated)                             # the priorities of the previous update are in the tree (recorded
-                                                                          # right before the running update was launched)
-            if shadow:
-                _lib.check(_lib.lib().r2d2_net_shadow_gate(self.core._h, st.cuda_stream))
+            st.wait_event(self._tree_safe)                                # tree writes issued on the learner's stream so far
+            if after is not None:
+                st.wait_event(self.core.td_event)                         # K2 of the running update has written its priorities
+                _lib.check(_lib.lib().r2d2_net_shadow_gate(self.core._h, st.cuda_stream))   # placement: start under its BPTT kernel
+                if sync is not None and hasattr(sync, "join"):
+                    sync.join()                                           # its reads of the tree end before the tree changes
+                self.replay.update_priorities(after["idx"], self.core.prio, after["old_ptr"])
             batch, idx, old_ptr = self.replay.sample(fuse_into=self.core, slot=slot)
-            if self.is_weight_sync is not None:
-                self.is_weight_sync.correct(self.replay, batch, idx)
+            if sync is not None:
+                sync.correct(self.replay, batch, idx)
             ready = torch.cuda.Event()
             ready.record(st)
         return dict(batch=batch, idx=idx, old_ptr=old_ptr, ready=ready, slot=slot)
@@ -360,18 +360,20 @@ class Learner:
         if self._ahead is not None and self._ahead_at != self.core.num_updates:
             self._ahead = None                                            # other updates ran in between: the gates lost their pairing
         if self._ahead is None:
+            if getattr(self, "_sample_stream", None) is None:
+                self._sample_stream = torch.cuda.Stream(device=self.device)
+                self._tree_safe = torch.cuda.Event()
+                self.replay.set_copy_smem(32 * 1024)                      # copy CTAs cannot share an SM with a recurrence / GEMM CTA
             _lib.check(_lib.lib().r2d2_net_shadow_gate_reset(self.core._h, main.cuda_stream))
-            self._ahead = self._sample_ahead(0, shadow=False)
+            self._tree_safe.record(main)
+            self._ahead = self._sample_ahead(0)
         cur = self._ahead
         main.wait_event(cur["ready"])
         self.core.select_s2d(cur["slot"])
-        self._tree_updated.record(main)                                   # every tree write so far (priority update, ingested blocks)
+        self._tree_safe.record(main)                                      # e.g. blocks ingested since the last update
         self.core.update(cur["batch"])
-        self._ahead = self._sample_ahead(1 - cur["slot"], shadow=True)    # enqueued now, runs mid-update
-        main.wait_event(self._ahead["ready"])                             # the tree must not change under the sampler (long done)
-        if self.is_weight_sync is not None and hasattr(self.is_weight_sync, "join"):
-            self.is_weight_sync.join()
-        self.replay.update_priorities(cur["idx"], self.core.prio, cur["old_ptr"])
+        self._ahead = self._sample_ahead(1 - cur["slot"], after=cur)      # enqueued now, runs mid-update
+        main.wait_event(self._ahead["ready"])                             # the learner's stream finds the tree quiescent after the update
         self._ahead_at = self.core.num_updates
         self.env_steps = self.replay.env_steps
         self._after_update()
