@@ -505,10 +505,17 @@ def run_ours(args):
             unroll_only(w)
         torch.cuda.synchronize()
         # the same launches as one CUDA graph (as the update itself runs them): no host enqueue gaps inside the timed region
+        ug = None
         if core.use_graph:
-            ug = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(ug):
-                unroll_only(0)
+            try:
+                ug = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(ug):
+                    unroll_only(0)
+            except Exception as e:                 # noqa: BLE001
+                print(f"[bench] unroll group not captured ({e!r}); timing eager launches", file=sys.stderr)
+                ug = None
+                torch.cuda.synchronize()
+        if ug is not None:
             ms_unroll = timed(lambda i: ug.replay(), max(5, args.steps // 2), 3)
         else:                                      # R2D2_CUDA_GRAPH=0 (profiler runs): eager launches
             ms_unroll = timed(unroll_only, max(5, args.steps // 2), 3)
