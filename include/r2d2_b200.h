@@ -249,6 +249,10 @@ int r2d2_clip_adam(float* params, const float* grads, float* exp_avg, float* exp
 int r2d2_clip_adam_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                        const float* grad_scale, const int32_t* rows_dev, double* partial_ws, float max_norm, float lr, float beta1,
                        float beta2, float eps, const int64_t* step_dev, float* norm_out, void* stream);
+/* The same with the increment of the update count done on the device as well (step_dev += 1 before the Adam kernel reads it). */
+int r2d2_clip_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                        const float* grad_scale, const int32_t* rows_dev, double* partial_ws, float max_norm, float lr, float beta1,
+                        float beta2, float eps, int64_t* step_dev, float* norm_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Data-parallel exchange step over NVLink peer memory (the reference has ONE learner,

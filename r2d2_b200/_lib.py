@@ -97,6 +97,7 @@ SIGNATURES = {
     "r2d2_debug_mma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, p, p]),
     "r2d2_clip_adam": (C.c_int, [p, p, p, p, i64, p, p, f32, f32, f32, f32, f32, i64, p, p]),
     "r2d2_clip_adam_dev": (C.c_int, [p, p, p, p, i64, p, p, p, f32, f32, f32, f32, f32, p, p, p]),
+    "r2d2_clip_adam_step": (C.c_int, [p, p, p, p, i64, p, p, p, f32, f32, f32, f32, f32, p, p, p]),
     "r2d2_dp_ctl_bytes": (C.c_size_t, []),
     "r2d2_dp_create": (C.c_int, [C.c_int, C.c_int, p, C.c_ulonglong, p, p]),
     "r2d2_dp_destroy": (None, [p]),

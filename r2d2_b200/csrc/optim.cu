@@ -14,7 +14,8 @@ constexpr int kNormBlocks = 148 * 4;
 constexpr int kNormThreads = 256;
 
 __global__ void __launch_bounds__(kNormThreads) sumsq_partial_kernel(const float* __restrict__ g, int64_t n,
-                                                                   double* __restrict__ partial) {
+                                                                   double* __restrict__ partial, int64_t* __restrict__ step_inc = nullptr) {
+    if (step_inc != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *step_inc += 1;     // the update count the NEXT launch (Adam) reads
     __shared__ double s[kNormThreads / 32];
     double acc = 0.0;
     const int64_t n4 = n >> 2;
@@ -115,16 +116,32 @@ int r2d2_clip_adam(float* params, const float* grads, float* exp_avg, float* exp
  * caller on the same stream) and, optionally, the gradient scale derived from a device row count (rows_dev: int32,
  * scale = 1 / rows; overrides grad_scale).  Nothing in the argument list changes between updates, so the whole learner
  * update can be captured once in a CUDA graph and replayed. */
-int r2d2_clip_adam_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
-                       const float* grad_scale, const int32_t* rows_dev, double* partial_ws, float max_norm, float lr, float beta1,
-                       float beta2, float eps, const int64_t* step_dev, float* norm_out, void* stream) {
+static int clip_adam_dev_impl(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                             const float* grad_scale, const int32_t* rows_dev, double* partial_ws, float max_norm, float lr, float beta1,
+                             float beta2, float eps, int64_t* step_dev, bool increment, float* norm_out, void* stream) {
     R2D2_REQUIRE(params && grads && exp_avg && exp_avg_sq && partial_ws && n > 0 && step_dev, "bad arguments");
     cudaStream_t s = as_stream(stream);
-    sumsq_partial_kernel<<<kNormBlocks, kNormThreads, 0, s>>>(grads, n, partial_ws);
+    sumsq_partial_kernel<<<kNormBlocks, kNormThreads, 0, s>>>(grads, n, partial_ws, increment ? step_dev : nullptr);
     clip_adam_kernel<<<kNormBlocks, 256, 0, s>>>(params, grads, exp_avg, exp_avg_sq, n, partial_ws, grad_scale, max_norm, lr,
                                                beta1, beta2, eps, 1.f, 1.f, norm_out, step_dev, rows_dev);
     R2D2_LAUNCH_CHECK();
     return R2D2_OK;
+}
+
+int r2d2_clip_adam_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                       const float* grad_scale, const int32_t* rows_dev, double* partial_ws, float max_norm, float lr, float beta1,
+                       float beta2, float eps, const int64_t* step_dev, float* norm_out, void* stream) {
+    return clip_adam_dev_impl(params, grads, exp_avg, exp_avg_sq, n, grad_scale, rows_dev, partial_ws, max_norm, lr, beta1, beta2, eps,
+                              const_cast<int64_t*>(step_dev), false, norm_out, stream);
+}
+
+/* The same, and the update count is incremented on the device first (by the norm kernel, before the Adam kernel reads it):
+ * the caller needs no launch of its own to keep the count. */
+int r2d2_clip_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                        const float* grad_scale, const int32_t* rows_dev, double* partial_ws, float max_norm, float lr, float beta1,
+                        float beta2, float eps, int64_t* step_dev, float* norm_out, void* stream) {
+    return clip_adam_dev_impl(params, grads, exp_avg, exp_avg_sq, n, grad_scale, rows_dev, partial_ws, max_norm, lr, beta1, beta2, eps,
+                              step_dev, true, norm_out, stream);
 }
 
 }  // extern "C"

@@ -395,11 +395,10 @@ class DeviceLearner:
         this batch's device-side row count."""
         if _count:
             self._num_updates += 1
-        self._step_dev.add_(1)
-        p = _lib.ptr
+        p = _lib.ptr                                     # (the device mirror of the update count is incremented by the norm kernel)
         b1, b2 = self.betas
         hooked = self.grad_hook is not None
-        _lib.check(_lib.lib().r2d2_clip_adam_dev(p(self.online.flat), p(self.grads.flat), p(self.exp_avg), p(self.exp_avg_sq),
+        _lib.check(_lib.lib().r2d2_clip_adam_step(p(self.online.flat), p(self.grads.flat), p(self.exp_avg), p(self.exp_avg_sq),
                                                  self.online.flat.numel(), p(self.grad_scale) if hooked else None,
                                                  None if hooked else p(self.rows), p(self._norm_ws), float(self.grad_norm),
                                                  float(self.lr), float(b1), float(b2), float(self.eps), p(self._step_dev),
