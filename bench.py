@@ -7,7 +7,10 @@ One "step" = one learner update on one batch of 64 replay sequences (b/l/f = 40/
 of C x 84 x 84 u8 each):
 
   value  : HBM-resident pipeline   K3 sample -> K4 gather -> K1 unroll(online+target) -> K2 TD ->
-           K1b BPTT -> [NCCL all-reduce] -> K5 clip+Adam -> K3 priority update      (worker.Learner.update_from_replay)
+           K1b BPTT -> [gradient exchange over NVLink, N > 1] -> K5 clip+Adam -> K3 priority update
+           (worker.Learner.update_from_replay; the priority update and the next batch's sample + gather run on a second
+           stream under the BPTT recurrence -- same operation order on the tree, bit-identical results; the strictly
+           sequential loop is timed as well and reported as `sequential_sampling`)
   e2e    : the same update through the reference-facing call with HOST buffers: a 14-tuple in pinned host
            memory (worker.py:219-238) -> H2D -> update -> priorities + loss back to the host
            (worker.Learner.update_from_batch)
